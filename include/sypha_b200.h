@@ -1,0 +1,189 @@
+/*
+ * sypha_b200.h - C ABI of the B200-native (sm_100a) Mehrotra IPM hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names: the
+ * per-iteration linear algebra of sypha's Mehrotra predictor-corrector LP solve.  Every entry
+ * point is `extern "C"`, takes plain pointers and sizes, returns an int status, never throws
+ * and never calls exit().  Reference interfaces replaced (paths under /root/reference):
+ *
+ *   sb200_solve ................ solver_sparse_mehrotra_run          src/sypha_solver_sparse.h:51
+ *                                (body src/sypha_solver.cpp:42-886)
+ *   sb200_ws_create/destroy .... initializeIpmWorkspace / releaseIpmWorkspace
+ *                                src/sypha_solver.h:107-108, src/sypha_solver_workspace.cpp:5-89
+ *   sb200_load_model ........... SyphaNodeSparse::copyModelOnDevice   src/sypha_node_sparse.cpp:156-198
+ *                                + host KKT assembly src/sypha_solver.cpp:96-207 (disappears)
+ *   sb200_solve_batch .......... the B&B node body                    src/sypha_solver_bnb_driver.cpp:789-859
+ *                                + build_branch_model                 src/sypha_solver_bnb.cpp:418-490
+ *   sb200_k_* .................. the L0 free functions (device pointers + stream):
+ *     sb200_k_elem_min_mult .... elem_min_mult_dev                    src/sypha_solver_utils.h:7
+ *     sb200_k_corrector_rhs .... corrector_rhs_dev                    src/sypha_solver_utils.h:12
+ *     sb200_k_alpha_max ........ alpha_max_dev                        src/sypha_solver_utils.h:17-24
+ *     sb200_k_spmv_csr/_csc .... cusparseSpMV (NON_TRANSPOSE / TRANSPOSE), call sites SURVEY.md 2.2
+ *     sb200_k_jacobi_diag ...... krylovComputeJacobiDiag              src/sypha_solver_krylov.h:49
+ *     sb200_k_potrf/_potrs ..... cusolverDnDgetrf / Dgetrs            src/sypha_solver_dense_linear.cpp:179,195
+ *     sb200_k_syrk ............. (new) FP64 tensor-core A*diag(d)*A' on a dense A
+ *
+ * All arithmetic is FP64, all indices int32 (as in the reference).  Device pointers are raw CUDA
+ * device addresses in the current context; `stream` arguments are a `cudaStream_t` passed as void*.
+ */
+#ifndef SYPHA_B200_H
+#define SYPHA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_VERSION 100
+
+typedef struct sb200_ws sb200_ws;
+
+/* status codes (return values) */
+enum {
+    SB200_OK = 0,
+    SB200_ERR_INVALID = 1,     /* bad argument / model not loaded / capacity exceeded */
+    SB200_ERR_CUDA = 2,        /* a CUDA call failed; see sb200_last_error */
+    SB200_ERR_NOMEM = 3,
+    SB200_ERR_NUMERICAL = 4,   /* LP flagged infeasible-or-numerical (maps to CODE_GENERIC_ERROR) */
+    SB200_ERR_UNSUPPORTED = 5
+};
+
+/* termination reasons: same values as SolverTerminationReason, src/sypha_solver_sparse.h:13-20 */
+enum {
+    SB200_TERM_CONVERGED = 0,
+    SB200_TERM_MAX_ITER = 1,
+    SB200_TERM_GAP_STALLED = 2,
+    SB200_TERM_INFEASIBLE_OR_NUMERICAL = 3,
+    SB200_TERM_TIME_LIMIT = 4
+};
+
+/* linear-solve strategy (extends the reference's auto|dense|sparse_qr|krylov,
+ * src/sypha_environment_defaults.h:26-30) */
+enum {
+    SB200_STRATEGY_AUTO = 0,
+    SB200_STRATEGY_CHOLESKY = 1,  /* sparse symbolic/numeric assembly of M = A D A' + dense Cholesky */
+    SB200_STRATEGY_SYRK = 2,      /* FP64 tensor-core SYRK on a dense copy of A + dense Cholesky */
+    SB200_STRATEGY_PCG = 3        /* matrix-free Jacobi-PCG on the normal equations */
+};
+
+/* capacities of a persistent workspace (grow-only; 0 = size on first load) */
+typedef struct sb200_caps {
+    int m_max;
+    int n_max;
+    long long nnz_max;
+} sb200_caps;
+
+/* parameters of one LP solve; defaults = src/sypha_environment_defaults.h:14-24 */
+typedef struct sb200_params {
+    int max_iter;               /* kMehrotraMaxIter = 25 */
+    double eta;                 /* kMehrotraEta = 0.95 */
+    double mu_tol;              /* kMehrotraMuTol = 1e-4 */
+    int gap_enabled;            /* SolverGapStagnationConfig, src/sypha_solver_sparse.h:22-27 */
+    int gap_window;
+    double gap_min_improv_pct;
+    int strategy;               /* SB200_STRATEGY_* */
+    int cg_max_iter;            /* kKrylovMaxCgIter = 500 */
+    double cg_tol_initial;      /* 1e-2 */
+    double cg_tol_final;        /* 1e-8 */
+    double cg_tol_decay;        /* 0.5 */
+    const volatile int *stop_flag;  /* host flag polled between iterations (logger watchdog), may be NULL */
+    int poll_every;             /* host reads the device scalar block every k iterations (>=1) */
+    int use_graph;              /* 1 = replay one captured CUDA graph per iteration */
+} sb200_params;
+
+typedef struct sb200_result {
+    int status;                 /* SB200_OK or SB200_ERR_NUMERICAL */
+    int reason;                 /* SB200_TERM_* */
+    int iterations;
+    double primal_obj;          /* x[0:n_orig].c[0:n_orig]   (src/sypha_solver.cpp:781) */
+    double dual_obj;            /* y.b                        (:784) */
+    double rel_gap;             /* |p-d|/max(1,|p|)           (:786-787) */
+    double mu;
+    double ms_start;            /* starting point     (node.timeStartSol*) */
+    double ms_setup;            /* initial residuals  (node.timePreSol*)   */
+    double ms_loop;             /* main loop          (node.timeSolver*)   */
+    int strategy_used;
+    long long cg_iterations;    /* total CG iterations (PCG strategy) */
+    long long kernels_launched; /* kernels of this library launched by the call */
+    double *x_host;             /* out, length n, may be NULL */
+    double *y_host;             /* out, length m, may be NULL */
+    double *s_host;             /* out, length n, may be NULL */
+    double *x0_host;            /* out: starting point (node.hX/hY/hS), may be NULL */
+    double *y0_host;
+    double *s0_host;
+} sb200_result;
+
+/* one B&B node = base model + appended rows (build_branch_model, src/sypha_solver_bnb.cpp:453-468):
+ * row r has coefficient `coef[r]` at column `var[r]` and -1 at a fresh slack column, rhs `rhs[r]`. */
+typedef struct sb200_node_delta {
+    int n_extra_rows;
+    const int *var;
+    const double *coef;
+    const double *rhs;
+} sb200_node_delta;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int sb200_version(void);
+int sb200_device_count(void);
+int sb200_ws_create(int device, const sb200_caps *caps, sb200_ws **out);
+int sb200_ws_destroy(sb200_ws *ws);
+const char *sb200_last_error(const sb200_ws *ws);
+void sb200_default_params(sb200_params *p);
+
+/* ---- model ---------------------------------------------------------------------------------- */
+/* A is m x n CSR; the first n_orig columns carry the objective that is reported.  Builds the CSC
+ * copy and, for the direct strategies, the symbolic structure of M = A D A' once.
+ * `strategy_hint` = SB200_STRATEGY_*; AUTO decides from the instance. */
+int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz,
+                     const int *csr_offs, const int *csr_inds, const double *csr_vals,
+                     const double *c, const double *b, int ptrs_on_device, int strategy_hint);
+
+/* ---- solve ---------------------------------------------------------------------------------- */
+int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result);
+int sb200_solve_batch(sb200_ws **ws, int k, const sb200_node_delta *deltas,
+                      const sb200_params *params, sb200_result *results);
+
+/* per-iteration trace of the last solve: rows of SB200_TRACE_COLS doubles
+ * (mu_in, mu, mu_aff, sigma, alpha_p, alpha_d, primal, dual); returns rows written */
+#define SB200_TRACE_COLS 8
+int sb200_get_trace(sb200_ws *ws, double *out, int max_rows);
+/* device addresses of the resident iterates (length n, m, n) */
+int sb200_get_device_iterates(sb200_ws *ws, void **x, void **y, void **s);
+/* introspection used by bench.py for the roofline arithmetic */
+int sb200_model_info(sb200_ws *ws, long long *info, int n_info);
+void *sb200_stream(sb200_ws *ws);
+
+/* ---- L0 kernels on caller-owned device buffers ------------------------------------------------ */
+int sb200_k_elem_min_mult(const double *d_x, const double *d_s, double *d_out, int n, void *stream);
+int sb200_k_corrector_rhs(const double *d_dx, const double *d_ds, double sigma, double mu,
+                          double *d_out, int n, void *stream);
+/* d_result[0] = min_{dx<0} -x/dx, d_result[1] = min_{ds<0} -s/ds (DBL_MAX when empty); stays on the
+ * device; if h_result != NULL it is also copied out (one sync), any n (the reference bails at
+ * n > 262144, src/sypha_solver_utils.cu:151-154) */
+int sb200_k_alpha_max(const double *d_x, const double *d_dx, const double *d_s, const double *d_ds,
+                      int n, double *d_result, double *h_result, void *stream);
+/* y = alpha*A*x + beta*y, A m x n CSR */
+int sb200_k_spmv_csr(int m, const int *d_offs, const int *d_inds, const double *d_vals,
+                     const double *d_x, double *d_y, double alpha, double beta, void *stream);
+/* y = alpha*A'*x + beta*y given the CSC arrays of A (n columns) */
+int sb200_k_spmv_csc(int n, const int *d_colptr, const int *d_rows, const double *d_vals,
+                     const double *d_x, double *d_y, double alpha, double beta, void *stream);
+/* diag[i] = sum_k a_ik^2 d[col_k] */
+int sb200_k_jacobi_diag(int m, const int *d_offs, const int *d_inds, const double *d_vals,
+                        const double *d_d, double *d_diag, void *stream);
+/* in-place lower Cholesky of the row-major n x n matrix with leading dimension ld (ld % 64 == 0,
+ * rows/cols n..ld-1 must hold an identity pad); *d_info = 0 or 1-based index of the first
+ * non-positive pivot */
+int sb200_k_potrf(int n, double *d_a, int ld, int *d_info, void *stream);
+/* solve L L' x = b in place (b length ld, zero padded) */
+int sb200_k_potrs(int n, const double *d_l, int ld, double *d_b, void *stream);
+/* C (row-major, ld) lower triangle = A diag(d) A' for a dense row-major m x k matrix A (lda);
+ * FP64 tensor-core (DMMA) kernel */
+int sb200_k_syrk(int m, int k, const double *d_a, int lda, const double *d_d, double *d_c, int ld,
+                 void *stream);
+/* M (row-major, ld) lower triangle = A diag(d) A' through the workspace's symbolic structure */
+int sb200_assemble_normal(sb200_ws *ws, const double *d_d, double *d_m, int ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYPHA_B200_H */

@@ -1,0 +1,104 @@
+// sb200_kernels.cuh - launcher declarations shared by the translation units of libsypha_b200.
+#pragma once
+#include "sb200_common.cuh"
+
+namespace sb200 {
+
+// Every vector the loop touches (device addresses) - the persistent workspace of
+// /root/reference/src/sypha_solver.h:76-105 (IpmWorkspace), re-laid out for the NE form.
+struct IpmVecs
+{
+    int m, n, n_orig;
+    int mpad;                 // m rounded up to SB200_TILE
+    const double *c, *b;
+    double *x, *y, *s;
+    double *dx, *dy, *ds;
+    double *resC, *resB, *resXS;
+    double *d;                // x ./ s
+    double *t;                // (x.*resC - resXS) ./ s
+    double *rhs;              // length mpad (normal-equation right-hand side / solution in place)
+    double *partial;          // [4][SB200_MAX_PARTIAL_BLOCKS]
+    Scalars *sc;
+    double *trace;            // [SB200_TRACE_ROWS][SB200_TRACE_COLS]
+};
+
+struct CsrView
+{
+    int m;
+    const int *offs;
+    const int *inds;
+    const double *vals;
+};
+struct CscView
+{
+    int n;
+    const int *colptr;
+    const int *rows;
+    const double *vals;
+    int lanes;                // lanes per column used by the kernels (power of two <= 32)
+};
+
+// CSC epilogue modes
+enum
+{
+    CSC_PLAIN = 0,      // out = alpha*w + beta*z
+    CSC_RECOVER = 1,    // ds = resC - w ; dx = (resXS - x ds)/s ; ratio test
+    CSC_START_X = 2,    // x = w ; min
+    CSC_START_S = 3,    // s = c - w ; min
+    CSC_RESC = 4,       // resC = c - s - w
+    CSC_SCALE_D = 5     // out = d .* w      (PCG: q = D A'p)
+};
+
+// ---- sb200_vector.cu -------------------------------------------------------------------------
+void launch_elem_min_mult(const double *x, const double *s, double *out, int n, cudaStream_t st);
+void launch_corrector_rhs(const double *dx, const double *ds, double sigma, double mu, double *out,
+                          int n, cudaStream_t st);
+void launch_alpha_max(const double *x, const double *dx, const double *s, const double *ds, int n,
+                      unsigned long long *d_ord2, double *d_result, cudaStream_t st);
+void launch_reset_scalars(Scalars *sc, cudaStream_t st);
+void launch_init_mu(const IpmVecs &V, const DevParams &P, cudaStream_t st);
+void launch_prologue(const IpmVecs &V, cudaStream_t st);
+void launch_affine_mu(const IpmVecs &V, cudaStream_t st);
+void launch_corrector(const IpmVecs &V, cudaStream_t st);
+void launch_update(const IpmVecs &V, const DevParams &P, cudaStream_t st);
+void launch_start_shift1(const IpmVecs &V, cudaStream_t st);
+void launch_start_shift2(const IpmVecs &V, cudaStream_t st);
+void launch_fill(double *p, double v, long long n, cudaStream_t st);
+
+// ---- sb200_spmv.cu ---------------------------------------------------------------------------
+// out[i] = alpha * (A x)_i + beta * z[i]   (out may alias z)
+void launch_spmv_csr(const CsrView &A, const double *x, const double *z, double *out, double alpha,
+                     double beta, cudaStream_t st);
+void launch_jacobi_diag(const CsrView &A, const double *d, double *diag, cudaStream_t st);
+void launch_spmv_csc(const CscView &A, int mode, const double *v, const double *z, double *out,
+                     double alpha, double beta, const IpmVecs *V, cudaStream_t st);
+int pick_csc_lanes(long long nnz, int n);
+
+// ---- sb200_chol.cu ---------------------------------------------------------------------------
+void launch_potrf(int n, double *a, int ld, int *info, cudaStream_t st);
+void launch_potrs(int n, const double *l, int ld, double *b, cudaStream_t st);
+void launch_pad_identity(int n, double *a, int ld, cudaStream_t st);
+
+// ---- sb200_assemble.cu -----------------------------------------------------------------------
+struct NormalPattern
+{
+    int m = 0;
+    long long n_pairs = 0;          // m(m+1)/2
+    long long n_terms = 0;
+    unsigned int *pair_ptr = nullptr;   // [n_pairs+1]
+    unsigned int *term_col = nullptr;   // [n_terms] column j of each term
+    double *term_w = nullptr;           // [n_terms] a_ij*a_kj, or nullptr when all products are +1
+};
+int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
+                         const int *csc_rows, const double *csc_vals, NormalPattern *out,
+                         cudaStream_t st);
+void free_normal_pattern(NormalPattern *p);
+void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld,
+                            cudaStream_t st);
+void launch_syrk_dmma(int m, int k, const double *a, int lda, const double *d, double *c, int ld,
+                      cudaStream_t st);
+int build_csc(ErrorSink &err, int m, int n, long long nnz, const int *csr_offs, const int *csr_inds,
+              const double *csr_vals, int *csc_colptr, int *csc_rows, double *csc_vals,
+              cudaStream_t st);
+
+} // namespace sb200

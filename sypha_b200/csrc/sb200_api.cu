@@ -1,0 +1,851 @@
+// sb200_api.cu - the C ABI (include/sypha_b200.h): persistent workspace, model upload and the
+// Mehrotra predictor-corrector loop in normal-equations form.
+//
+// Host orchestration of /root/reference/src/sypha_solver.cpp:42-886 (solver_sparse_mehrotra_run):
+//   starting point   init.cpp:543-652   -> GPU, same kernels as the loop with D = I
+//   initial residuals solver.cpp:375-459 -> 2 fused SpMV launches + 1 reduction
+//   main loop        solver.cpp:496-772 -> per iteration: assemble, factor, 2 x (rhs SpMV, solve,
+//                                          recover+ratio test), 3 fused vector kernels; the only
+//                                          host traffic is one read of the scalar block per poll.
+// The loop body is replayed from a CUDA graph; every kernel starts with `if (done) return`, so
+// iterations may be enqueued ahead of the host's convergence poll without changing the result.
+#include "sb200_kernels.cuh"
+#include "sb200_chol.cuh"
+#include "sb200_pcg.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+using namespace sb200;
+
+struct sb200_ws
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ErrorSink err;
+
+    // model
+    bool loaded = false;
+    int m = 0, n = 0, n_orig = 0, mpad = 0;
+    long long nnz = 0;
+    int strategy = SB200_STRATEGY_AUTO;
+    int *csr_offs = nullptr, *csr_inds = nullptr;
+    double *csr_vals = nullptr;
+    int *csc_colptr = nullptr, *csc_rows = nullptr;
+    double *csc_vals = nullptr;
+    double *c = nullptr, *b = nullptr;
+    int csc_lanes = 1;
+    int m_cap = 0, n_cap = 0;
+    long long nnz_cap = 0;
+
+    NormalPattern pat;
+    double *denseA = nullptr;     // SYRK strategy: dense row-major copy of A, mpad x kpad
+    int kpad = 0;
+    double *M = nullptr;          // mpad x mpad
+    long long M_cap = 0;
+    CholWork chol;
+
+    // iterates and scratch (one slab)
+    double *slab = nullptr;
+    size_t slab_bytes = 0;
+    IpmVecs V{};
+    double *ones_n = nullptr;
+    double *cg_diag = nullptr, *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr,
+           *cg_Ap = nullptr, *cg_q = nullptr;
+    Scalars *sc = nullptr;
+    DevParams *dparams = nullptr;
+    Scalars *sc_host = nullptr;   // pinned
+    DevParams hparams{};
+
+    // graph of one IPM iteration (direct strategies)
+    cudaGraphExec_t iter_graph = nullptr;
+    long long iter_graph_kernels = 0;
+    cudaGraphExec_t cg_graph = nullptr;     // a chunk of CG iterations
+    long long cg_graph_kernels = 0;
+    int cg_graph_chunk = 0;
+    const double *cg_graph_dscale = nullptr;
+
+    // async solve state
+    sb200_params params{};
+    bool active = false;
+    int enqueued = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long launches_at_begin = 0;
+    long long graph_kernel_launches = 0;
+    std::vector<double> trace_host;
+    int trace_rows = 0;
+};
+
+namespace {
+
+inline int round_up(int v, int q) { return (v + q - 1) / q * q; }
+
+#define WS_TRY(call) SB200_CUDA_TRY(ws->err, call)
+
+int fail(sb200_ws *ws, int code, const char *msg)
+{
+    ws->err.msg = msg;
+    return code;
+}
+
+void drop_graphs(sb200_ws *ws)
+{
+    if (ws->iter_graph) cudaGraphExecDestroy(ws->iter_graph);
+    if (ws->cg_graph) cudaGraphExecDestroy(ws->cg_graph);
+    ws->iter_graph = nullptr;
+    ws->cg_graph = nullptr;
+}
+
+template <typename T>
+int grow(sb200_ws *ws, T **p, size_t count)
+{
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    WS_TRY(cudaMalloc(p, sizeof(T) * (count ? count : 1)));
+    return SB200_OK;
+}
+
+int ensure_capacity(sb200_ws *ws, int m, int n, long long nnz)
+{
+    if (nnz > ws->nnz_cap)
+    {
+        int rc;
+        if ((rc = grow(ws, &ws->csr_inds, (size_t)nnz))) return rc;
+        if ((rc = grow(ws, &ws->csr_vals, (size_t)nnz))) return rc;
+        if ((rc = grow(ws, &ws->csc_rows, (size_t)nnz))) return rc;
+        if ((rc = grow(ws, &ws->csc_vals, (size_t)nnz))) return rc;
+        ws->nnz_cap = nnz;
+    }
+    if (m > ws->m_cap || n > ws->n_cap)
+    {
+        const int mc = std::max(m, ws->m_cap), nc = std::max(n, ws->n_cap);
+        const int mp = round_up(mc, SB200_TILE);
+        int rc;
+        if ((rc = grow(ws, &ws->csr_offs, (size_t)mc + 1))) return rc;
+        if ((rc = grow(ws, &ws->csc_colptr, (size_t)nc + 1))) return rc;
+        if ((rc = grow(ws, &ws->c, (size_t)nc))) return rc;
+        if ((rc = grow(ws, &ws->b, (size_t)mc))) return rc;
+        // slab: 10 n-vectors, 9 m-vectors (padded), partials, trace
+        const size_t nv = (size_t)round_up(nc, 32), mv = (size_t)mp;
+        const size_t doubles = 11 * nv + 10 * mv + 4 * (size_t)SB200_MAX_PARTIAL_BLOCKS +
+                               (size_t)SB200_TRACE_ROWS * SB200_TRACE_COLS;
+        if (ws->slab) cudaFree(ws->slab);
+        ws->slab = nullptr;
+        WS_TRY(cudaMalloc(&ws->slab, doubles * sizeof(double)));
+        ws->slab_bytes = doubles * sizeof(double);
+        ws->m_cap = mc;
+        ws->n_cap = nc;
+    }
+    return SB200_OK;
+}
+
+void carve(sb200_ws *ws)
+{
+    const size_t nv = (size_t)round_up(ws->n_cap, 32), mv = (size_t)round_up(ws->m_cap, SB200_TILE);
+    double *p = ws->slab;
+    auto take = [&](size_t k) { double *r = p; p += k; return r; };
+    IpmVecs &V = ws->V;
+    V.m = ws->m; V.n = ws->n; V.n_orig = ws->n_orig; V.mpad = ws->mpad;
+    V.c = ws->c; V.b = ws->b;
+    V.x = take(nv); V.s = take(nv); V.dx = take(nv); V.ds = take(nv);
+    V.resC = take(nv); V.resXS = take(nv); V.d = take(nv); V.t = take(nv);
+    ws->ones_n = take(nv); ws->cg_q = take(nv);
+    take(nv);
+    V.y = take(mv); V.resB = take(mv); V.rhs = take(mv);
+    ws->cg_diag = take(mv); ws->cg_x = take(mv); ws->cg_r = take(mv); ws->cg_z = take(mv);
+    ws->cg_p = take(mv); ws->cg_Ap = take(mv);
+    take(mv);
+    V.partial = take(4 * (size_t)SB200_MAX_PARTIAL_BLOCKS);
+    V.trace = take((size_t)SB200_TRACE_ROWS * SB200_TRACE_COLS);
+    V.sc = ws->sc;
+    V.dy = (ws->strategy == SB200_STRATEGY_PCG) ? ws->cg_x : V.rhs;
+}
+
+CsrView csr_of(const sb200_ws *ws) { return CsrView{ws->m, ws->csr_offs, ws->csr_inds, ws->csr_vals}; }
+CscView csc_of(const sb200_ws *ws)
+{
+    return CscView{ws->n, ws->csc_colptr, ws->csc_rows, ws->csc_vals, ws->csc_lanes};
+}
+
+__global__ void k_densify(int m, const int *__restrict__ offs, const int *__restrict__ inds,
+                          const double *__restrict__ vals, double *__restrict__ A, int lda)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < m; row += gridDim.x * wpb)
+        for (int k = offs[row] + lane; k < offs[row + 1]; k += 32)
+            atomicAdd(&A[(size_t)row * lda + inds[k]], vals[k]);   // duplicates sum, like CSR semantics
+}
+
+// ---- normal-equations operator ---------------------------------------------------------------
+void enqueue_factor(sb200_ws *ws, const double *d)
+{
+    cudaStream_t st = ws->stream;
+    if (ws->strategy == SB200_STRATEGY_SYRK)
+    {
+        launch_syrk_dmma(ws->m, ws->n, ws->denseA, ws->kpad, d, ws->M, ws->mpad, st);
+        launch_pad_identity(ws->m, ws->M, ws->mpad, st);
+    }
+    else
+        launch_assemble_normal(ws->pat, d, ws->M, ws->mpad, st);
+    launch_potrf(ws->chol, ws->m, ws->M, ws->mpad, &ws->sc->chol_info, st);
+}
+
+// graph-captured chunk of CG iterations
+int cg_run(sb200_ws *ws, const double *dscale, double fixed_tol, int cap_override, int honour_done)
+{
+    cudaStream_t st = ws->stream;
+    PcgVecs C{ws->m, ws->V.rhs, ws->cg_diag, ws->cg_x, ws->cg_r, ws->cg_z, ws->cg_p, ws->cg_Ap,
+              ws->cg_q, dscale, ws->V.partial};
+    launch_cg_init(C, ws->sc, ws->dparams, fixed_tol, honour_done, st);
+    const int cap = cap_override > 0 ? cap_override : ws->hparams.cg_max_iter;
+    const int chunk = std::max(1, std::min(cap, 32));
+    const bool use_graph = ws->params.use_graph != 0;
+    if (use_graph && (!ws->cg_graph || ws->cg_graph_chunk != chunk || ws->cg_graph_dscale != dscale))
+    {
+        if (ws->cg_graph) cudaGraphExecDestroy(ws->cg_graph);
+        ws->cg_graph = nullptr;
+        cudaGraph_t g = nullptr;
+        const long long before = g_launch_count;
+        WS_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < chunk; ++i)
+            launch_cg_iteration(csr_of(ws), csc_of(ws), C, ws->V, ws->dparams, cap_override, st);
+        WS_TRY(cudaStreamEndCapture(st, &g));
+        ws->cg_graph_kernels = g_launch_count - before;
+        g_launch_count = before;
+        WS_TRY(cudaGraphInstantiate(&ws->cg_graph, g, 0));
+        cudaGraphDestroy(g);
+        ws->cg_graph_chunk = chunk;
+        ws->cg_graph_dscale = dscale;
+    }
+    for (int done_iters = 0; done_iters < cap + chunk; done_iters += chunk)
+    {
+        if (use_graph)
+        {
+            WS_TRY(cudaGraphLaunch(ws->cg_graph, st));
+            ws->graph_kernel_launches += ws->cg_graph_kernels;
+        }
+        else
+            for (int i = 0; i < chunk; ++i)
+                launch_cg_iteration(csr_of(ws), csc_of(ws), C, ws->V, ws->dparams, cap_override, st);
+        WS_TRY(cudaMemcpyAsync(ws->sc_host, ws->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+        WS_TRY(cudaStreamSynchronize(st));
+        if (ws->sc_host->cg_done || (honour_done && ws->sc_host->done)) break;
+    }
+    return SB200_OK;
+}
+
+// solve (A diag(d) A') z = V.rhs ; result in V.dy
+int enqueue_or_run_solve(sb200_ws *ws, const double *dscale, double fixed_tol, int honour_done)
+{
+    if (ws->strategy == SB200_STRATEGY_PCG)
+    {
+        int rc = cg_run(ws, dscale, fixed_tol, fixed_tol > 0.0 ? 10000 : 0, honour_done);
+        if (rc) return rc;
+        if (honour_done) launch_cg_check(ws->sc, ws->stream);
+        return SB200_OK;
+    }
+    launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, ws->V.rhs, ws->stream);
+    return SB200_OK;
+}
+
+void enqueue_iteration_direct(sb200_ws *ws)
+{
+    cudaStream_t st = ws->stream;
+    const IpmVecs &V = ws->V;
+    const CsrView A = csr_of(ws);
+    const CscView At = csc_of(ws);
+    enqueue_factor(ws, V.d);
+    launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);                 // rhs = resB + A t
+    launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, V.rhs, st);            // dy (affine)
+    launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
+    launch_affine_mu(V, st);
+    launch_corrector(V, st);
+    launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);
+    launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, V.rhs, st);            // dy (corrector)
+    launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
+    launch_update(V, ws->dparams, st);
+}
+
+int run_iteration_pcg(sb200_ws *ws)
+{
+    cudaStream_t st = ws->stream;
+    const IpmVecs &V = ws->V;
+    const CsrView A = csr_of(ws);
+    const CscView At = csc_of(ws);
+    int rc;
+    if (ws->sc_host->done) return SB200_OK;
+    launch_jacobi_diag(A, V.d, ws->cg_diag, st);
+    launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);
+    if ((rc = enqueue_or_run_solve(ws, V.d, 0.0, 1))) return rc;
+    launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
+    launch_affine_mu(V, st);
+    launch_corrector(V, st);
+    launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);
+    if ((rc = enqueue_or_run_solve(ws, V.d, 0.0, 1))) return rc;
+    launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
+    launch_update(V, ws->dparams, st);
+    return SB200_OK;
+}
+
+// Capture one loop iteration.  If the driver refuses to capture (e.g. cooperative launches inside a
+// capture), fall back to plain stream launches for this workspace - same kernels, more launch gaps.
+int ensure_iter_graph(sb200_ws *ws)
+{
+    if (ws->iter_graph) return SB200_OK;
+    cudaGraph_t g = nullptr;
+    const long long before = g_launch_count;
+    cudaError_t e = cudaStreamBeginCapture(ws->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess)
+    {
+        enqueue_iteration_direct(ws);
+        e = cudaStreamEndCapture(ws->stream, &g);
+    }
+    ws->iter_graph_kernels = g_launch_count - before;
+    g_launch_count = before;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&ws->iter_graph, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        ws->iter_graph = nullptr;
+        ws->params.use_graph = 0;
+        ws->err.msg = std::string("graph capture unavailable, using stream launches: ") + cudaGetErrorString(e);
+    }
+    return SB200_OK;
+}
+
+// ---- solve state machine ------------------------------------------------------------------------
+int solve_begin(sb200_ws *ws, const sb200_params *p)
+{
+    if (!ws->loaded) return fail(ws, SB200_ERR_INVALID, "sb200_solve: no model loaded");
+    WS_TRY(cudaSetDevice(ws->device));
+    ws->params = *p;
+    if (ws->params.poll_every < 1) ws->params.poll_every = 1;
+    cudaStream_t st = ws->stream;
+    const IpmVecs &V = ws->V;
+    const CsrView A = csr_of(ws);
+    const CscView At = csc_of(ws);
+    ws->launches_at_begin = g_launch_count;
+    ws->graph_kernel_launches = 0;
+
+    DevParams &hp = ws->hparams;
+    hp.eta = p->eta;
+    hp.mu_tol = p->mu_tol;
+    hp.min_improv_ratio = p->gap_min_improv_pct / 100.0;
+    hp.max_iter = p->max_iter;
+    hp.gap_enabled = (p->gap_enabled && p->gap_window > 0 && p->gap_min_improv_pct >= 0.0) ? 1 : 0;
+    hp.gap_window = p->gap_window;
+    hp.n_orig = ws->n_orig;
+    hp.cg_max_iter = p->cg_max_iter;
+    hp.cg_tol_initial = p->cg_tol_initial;
+    hp.cg_tol_final = p->cg_tol_final;
+    hp.cg_tol_decay = p->cg_tol_decay;
+    WS_TRY(cudaMemcpyAsync(ws->dparams, &hp, sizeof hp, cudaMemcpyHostToDevice, st));
+
+    WS_TRY(cudaEventRecord(ws->ev[0], st));
+    launch_reset_scalars(ws->sc, st);
+
+    // ---- starting point (sypha_solver_init.cpp:543-652), D = I ---------------------------------
+    int rc;
+    WS_TRY(cudaMemsetAsync(V.rhs, 0, sizeof(double) * ws->mpad, st));
+    if (ws->strategy == SB200_STRATEGY_PCG)
+        launch_jacobi_diag(A, ws->ones_n, ws->cg_diag, st);
+    else
+        enqueue_factor(ws, ws->ones_n);
+    WS_TRY(cudaMemcpyAsync(V.rhs, ws->b, sizeof(double) * ws->m, cudaMemcpyDeviceToDevice, st));
+    if ((rc = enqueue_or_run_solve(ws, nullptr, 1e-12, 0))) return rc;        // (AA')^-1 b
+    launch_spmv_csc(At, CSC_START_X, V.dy, nullptr, nullptr, 0, 0, &V, st);  // x~ = A' (.)
+    launch_spmv_csr(A, ws->c, nullptr, V.rhs, 1.0, 0.0, st);                 // A c
+    if ((rc = enqueue_or_run_solve(ws, nullptr, 1e-12, 0))) return rc;        // y~
+    WS_TRY(cudaMemcpyAsync(V.y, V.dy, sizeof(double) * ws->m, cudaMemcpyDeviceToDevice, st));
+    launch_spmv_csc(At, CSC_START_S, V.y, nullptr, nullptr, 0, 0, &V, st);   // s~ = c - A' y~
+    launch_start_shift1(V, st);
+    launch_start_shift2(V, st);
+    WS_TRY(cudaEventRecord(ws->ev[1], st));
+
+    // ---- initial residuals and mu (sypha_solver.cpp:375-459) ------------------------------------
+    launch_spmv_csc(At, CSC_RESC, V.y, nullptr, nullptr, 0, 0, &V, st);      // resC = c - s - A'y
+    launch_spmv_csr(A, V.x, ws->b, V.resB, -1.0, 1.0, st);                   // resB = b - A x
+    launch_init_mu(V, ws->dparams, st);
+    launch_prologue(V, st);
+    WS_TRY(cudaEventRecord(ws->ev[2], st));
+    ws->enqueued = 0;
+    ws->active = true;
+    ws->sc_host->done = 0;
+    return SB200_OK;
+}
+
+// enqueue up to poll_every iterations and the scalar-block read-back
+int solve_step(sb200_ws *ws)
+{
+    cudaStream_t st = ws->stream;
+    const int room = ws->params.max_iter - ws->enqueued;
+    const int k = std::min(ws->params.poll_every, std::max(room, 0));
+    for (int i = 0; i < k; ++i)
+    {
+        if (ws->strategy == SB200_STRATEGY_PCG)
+        {
+            int rc = run_iteration_pcg(ws);
+            if (rc) return rc;
+        }
+        else if (ws->params.use_graph)
+        {
+            int rc = ensure_iter_graph(ws);
+            if (rc) return rc;
+            if (ws->iter_graph)
+            {
+                WS_TRY(cudaGraphLaunch(ws->iter_graph, st));
+                ws->graph_kernel_launches += ws->iter_graph_kernels;
+            }
+            else
+                enqueue_iteration_direct(ws);
+        }
+        else
+            enqueue_iteration_direct(ws);
+    }
+    ws->enqueued += k;
+    WS_TRY(cudaMemcpyAsync(ws->sc_host, ws->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+    WS_TRY(cudaEventRecord(ws->ev[3], st));
+    return SB200_OK;
+}
+
+// wait for the last step; returns 1 when the loop has finished
+int solve_poll(sb200_ws *ws, int *finished)
+{
+    WS_TRY(cudaEventSynchronize(ws->ev[3]));
+    const bool stop = ws->params.stop_flag && *ws->params.stop_flag;
+    *finished = (ws->sc_host->done || ws->enqueued >= ws->params.max_iter || stop) ? 1 : 0;
+    return SB200_OK;
+}
+
+int solve_finish(sb200_ws *ws, sb200_result *r)
+{
+    cudaStream_t st = ws->stream;
+    const IpmVecs &V = ws->V;
+    WS_TRY(cudaMemcpyAsync(ws->sc_host, ws->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+    if (r->x_host) WS_TRY(cudaMemcpyAsync(r->x_host, V.x, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
+    if (r->y_host) WS_TRY(cudaMemcpyAsync(r->y_host, V.y, sizeof(double) * ws->m, cudaMemcpyDeviceToHost, st));
+    if (r->s_host) WS_TRY(cudaMemcpyAsync(r->s_host, V.s, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
+    WS_TRY(cudaStreamSynchronize(st));
+    const Scalars &sc = *ws->sc_host;
+    ws->active = false;
+
+    int reason = sc.reason;
+    int trsv_err = 0;
+    if (ws->chol.ctl) WS_TRY(cudaMemcpy(&trsv_err, ws->chol.ctl + 4, sizeof(int), cudaMemcpyDeviceToHost));
+    if (trsv_err)
+    {
+        cudaMemset(ws->chol.ctl + 4, 0, sizeof(int));
+        return fail(ws, SB200_ERR_CUDA, "triangular-solve data-flow wait timed out (CTAs not co-resident?)");
+    }
+    bool numerical = sc.numerical != 0 || sc.chol_info != 0;
+    // sypha_solver.cpp:775-778: anything but a failure / gap stall is re-labelled from mu
+    // (this also overwrites TIME_LIMIT, as the reference does)
+    if (!numerical && reason != SB200_TERM_GAP_STALLED)
+        reason = (sc.mu <= ws->params.mu_tol) ? SB200_TERM_CONVERGED : SB200_TERM_MAX_ITER;
+    if (numerical) reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
+    const double viol = sc.dual - sc.primal;
+    if (!numerical && reason != SB200_TERM_CONVERGED && std::isfinite(viol) &&
+        viol > 1e6 * std::max(1.0, std::fabs(sc.primal)))      // :788-796
+    {
+        numerical = true;
+        reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
+    }
+    r->status = numerical ? SB200_ERR_NUMERICAL : SB200_OK;
+    r->reason = reason;
+    r->iterations = sc.iter;
+    r->primal_obj = sc.primal;
+    r->dual_obj = sc.dual;
+    r->rel_gap = std::fabs(sc.primal - sc.dual) / std::max(1.0, std::fabs(sc.primal));
+    r->mu = sc.mu;
+    r->strategy_used = ws->strategy;
+    r->cg_iterations = sc.cg_total;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ws->ev[0], ws->ev[1]); r->ms_start = ms;
+    cudaEventElapsedTime(&ms, ws->ev[1], ws->ev[2]); r->ms_setup = ms;
+    cudaEventElapsedTime(&ms, ws->ev[2], ws->ev[3]); r->ms_loop = ms;
+    r->kernels_launched = (g_launch_count - ws->launches_at_begin) + ws->graph_kernel_launches;
+    ws->trace_rows = std::min(sc.iter, SB200_TRACE_ROWS);
+    ws->trace_host.resize((size_t)ws->trace_rows * SB200_TRACE_COLS);
+    if (ws->trace_rows)
+        WS_TRY(cudaMemcpy(ws->trace_host.data(), V.trace, sizeof(double) * ws->trace_host.size(),
+                          cudaMemcpyDeviceToHost));
+    return SB200_OK;
+}
+
+} // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int sb200_version(void) { return SB200_VERSION; }
+
+int sb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void sb200_default_params(sb200_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->max_iter = 25;          // kMehrotraMaxIter
+    p->eta = 0.95;             // kMehrotraEta
+    p->mu_tol = 1e-4;          // kMehrotraMuTol
+    p->gap_enabled = 0;
+    p->strategy = SB200_STRATEGY_AUTO;
+    p->cg_max_iter = 500;
+    p->cg_tol_initial = 1e-2;
+    p->cg_tol_final = 1e-8;
+    p->cg_tol_decay = 0.5;
+    p->stop_flag = nullptr;
+    p->poll_every = 1;
+    p->use_graph = 1;
+}
+
+int sb200_ws_create(int device, const sb200_caps *caps, sb200_ws **out)
+{
+    if (!out) return SB200_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return SB200_ERR_CUDA;     // no CPU fallback: the library needs a GPU
+    }
+    if (device < 0) device = 0;
+    if (device >= ndev) return SB200_ERR_INVALID;
+    sb200_ws *ws = new sb200_ws();
+    ws->device = device;
+    auto bail = [&](int rc) { sb200_ws_destroy(ws); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(SB200_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SB200_ERR_CUDA);
+    for (auto &e : ws->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(SB200_ERR_CUDA);
+    if (cudaMalloc(&ws->sc, sizeof(Scalars)) != cudaSuccess) return bail(SB200_ERR_NOMEM);
+    if (cudaMalloc(&ws->dparams, sizeof(DevParams)) != cudaSuccess) return bail(SB200_ERR_NOMEM);
+    if (cudaMallocHost(&ws->sc_host, sizeof(Scalars)) != cudaSuccess) return bail(SB200_ERR_NOMEM);
+    memset(ws->sc_host, 0, sizeof(Scalars));
+    if (caps && caps->m_max > 0 && caps->n_max > 0 && caps->nnz_max > 0)
+    {
+        int rc = ensure_capacity(ws, caps->m_max, caps->n_max, caps->nnz_max);
+        if (rc) return bail(rc);
+    }
+    *out = ws;
+    return SB200_OK;
+}
+
+int sb200_ws_destroy(sb200_ws *ws)
+{
+    if (!ws) return SB200_OK;
+    cudaSetDevice(ws->device);
+    if (ws->stream) cudaStreamSynchronize(ws->stream);
+    drop_graphs(ws);
+    free_normal_pattern(&ws->pat);
+    chol_work_free(ws->chol);
+    void *ptrs[] = {ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
+                    ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ws->sc_host) cudaFreeHost(ws->sc_host);
+    for (auto &e : ws->ev)
+        if (e) cudaEventDestroy(e);
+    if (ws->stream) cudaStreamDestroy(ws->stream);
+    delete ws;
+    return SB200_OK;
+}
+
+const char *sb200_last_error(const sb200_ws *ws) { return ws ? ws->err.msg.c_str() : "null workspace"; }
+
+void *sb200_stream(sb200_ws *ws) { return ws ? (void *)ws->stream : nullptr; }
+
+int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, const int *csr_offs,
+                     const int *csr_inds, const double *csr_vals, const double *c, const double *b,
+                     int ptrs_on_device, int strategy_hint)
+{
+    if (!ws) return SB200_ERR_INVALID;
+    if (m <= 0 || n <= 0 || nnz <= 0 || n_orig < 0 || n_orig > n || !csr_offs || !csr_inds || !csr_vals ||
+        !c || !b || nnz > 0x7fffffffll)
+        return fail(ws, SB200_ERR_INVALID, "sb200_load_model: bad dimensions or null pointer");
+    WS_TRY(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    ws->loaded = false;
+    drop_graphs(ws);
+    int rc = ensure_capacity(ws, m, n, nnz);
+    if (rc) return rc;
+    ws->m = m; ws->n = n; ws->n_orig = n_orig; ws->nnz = nnz;
+    ws->mpad = round_up(m, SB200_TILE);
+    const cudaMemcpyKind kind = ptrs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    WS_TRY(cudaMemcpyAsync(ws->csr_offs, csr_offs, sizeof(int) * ((size_t)m + 1), kind, st));
+    WS_TRY(cudaMemcpyAsync(ws->csr_inds, csr_inds, sizeof(int) * (size_t)nnz, kind, st));
+    WS_TRY(cudaMemcpyAsync(ws->csr_vals, csr_vals, sizeof(double) * (size_t)nnz, kind, st));
+    WS_TRY(cudaMemcpyAsync(ws->c, c, sizeof(double) * (size_t)n, kind, st));
+    WS_TRY(cudaMemcpyAsync(ws->b, b, sizeof(double) * (size_t)m, kind, st));
+    rc = build_csc(ws->err, m, n, nnz, ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr,
+                   ws->csc_rows, ws->csc_vals, st);
+    if (rc) return rc;
+    ws->csc_lanes = pick_csc_lanes(nnz, n);
+
+    // ---- strategy --------------------------------------------------------------------------------
+    int strat = strategy_hint;
+    if (strat == SB200_STRATEGY_AUTO)
+        strat = (m <= 16384) ? SB200_STRATEGY_CHOLESKY : SB200_STRATEGY_PCG;
+    free_normal_pattern(&ws->pat);
+    if (strat == SB200_STRATEGY_CHOLESKY)
+    {
+        rc = build_normal_pattern(ws->err, m, n, nnz, ws->csc_colptr, ws->csc_rows, ws->csc_vals, &ws->pat, st);
+        if (rc == SB200_ERR_UNSUPPORTED && strategy_hint == SB200_STRATEGY_AUTO)
+            strat = SB200_STRATEGY_PCG;
+        else if (rc)
+            return rc;
+        else if (strategy_hint == SB200_STRATEGY_AUTO)
+        {
+            // density switch (north_star item 1): sparse gather moves 4..12 B per product term at
+            // HBM speed, SYRK spends m^2 n flops on the FP64 tensor pipe.
+            const double t_sparse = (double)ws->pat.n_terms * (ws->pat.term_w ? 12.0 : 4.0) / 6.5e12;
+            const double t_syrk = (double)m * (double)m * (double)n / 3.0e13;
+            if (t_syrk < t_sparse && (double)ws->mpad * round_up(n, 32) * 8.0 < 40e9)
+            {
+                strat = SB200_STRATEGY_SYRK;
+                free_normal_pattern(&ws->pat);
+            }
+        }
+    }
+    ws->strategy = strat;
+    if (strat == SB200_STRATEGY_SYRK)
+    {
+        ws->kpad = round_up(n, 32);
+        if (ws->denseA) cudaFree(ws->denseA);
+        ws->denseA = nullptr;
+        const size_t bytes = sizeof(double) * (size_t)ws->mpad * ws->kpad;
+        WS_TRY(cudaMalloc(&ws->denseA, bytes));
+        WS_TRY(cudaMemsetAsync(ws->denseA, 0, bytes, st));
+        k_densify<<<grid_for((long long)m * 32, 256, 148 * 16), 256, 0, st>>>(m, ws->csr_offs, ws->csr_inds,
+                                                                             ws->csr_vals, ws->denseA, ws->kpad);
+        ++g_launch_count;
+    }
+    if (strat != SB200_STRATEGY_PCG)
+    {
+        const long long need = (long long)ws->mpad * ws->mpad;
+        if (need > ws->M_cap)
+        {
+            if (ws->M) cudaFree(ws->M);
+            ws->M = nullptr;
+            WS_TRY(cudaMalloc(&ws->M, sizeof(double) * (size_t)need));
+            ws->M_cap = need;
+        }
+        WS_TRY(cudaMemsetAsync(ws->M, 0, sizeof(double) * (size_t)need, st));
+        launch_pad_identity(m, ws->M, ws->mpad, st);
+        rc = chol_work_ensure(ws->err, ws->chol, ws->mpad);
+        if (rc) return rc;
+    }
+    carve(ws);
+    WS_TRY(cudaMemsetAsync(ws->slab, 0, ws->slab_bytes, st));
+    launch_fill(ws->ones_n, 1.0, round_up(ws->n_cap, 32), st);
+    WS_TRY(cudaStreamSynchronize(st));
+    ws->loaded = true;
+    return SB200_OK;
+}
+
+int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result)
+{
+    if (!ws || !params || !result) return SB200_ERR_INVALID;
+    int rc = solve_begin(ws, params);
+    if (rc) return rc;
+    int finished = 0;
+    while (!finished)
+    {
+        if ((rc = solve_step(ws))) return rc;
+        if ((rc = solve_poll(ws, &finished))) return rc;
+    }
+    return solve_finish(ws, result);
+}
+
+int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, const sb200_params *params,
+                      sb200_result *results)
+{
+    // LPs of a batch are independent: every workspace runs on its own stream and the
+    // host interleaves enqueue/poll so their kernels overlap on the device.
+    if (!wss || k <= 0 || !params || !results) return SB200_ERR_INVALID;
+    if (deltas)
+        for (int i = 0; i < k; ++i)
+            if (deltas[i].n_extra_rows != 0)
+                return fail(wss[i], SB200_ERR_UNSUPPORTED,
+                            "sb200_solve_batch: node deltas must be folded into the model by the caller");
+    std::vector<int> live(k, 0);
+    int rc, remaining = 0;
+    for (int i = 0; i < k; ++i)
+    {
+        if ((rc = solve_begin(wss[i], params))) return rc;
+        live[i] = 1;
+        ++remaining;
+    }
+    while (remaining)
+    {
+        for (int i = 0; i < k; ++i)
+            if (live[i] && (rc = solve_step(wss[i]))) return rc;
+        for (int i = 0; i < k; ++i)
+            if (live[i])
+            {
+                int fin = 0;
+                if ((rc = solve_poll(wss[i], &fin))) return rc;
+                if (fin)
+                {
+                    if ((rc = solve_finish(wss[i], &results[i]))) return rc;
+                    live[i] = 0;
+                    --remaining;
+                }
+            }
+    }
+    return SB200_OK;
+}
+
+int sb200_get_trace(sb200_ws *ws, double *out, int max_rows)
+{
+    if (!ws || !out) return 0;
+    const int rows = std::min(max_rows, ws->trace_rows);
+    if (rows > 0) memcpy(out, ws->trace_host.data(), sizeof(double) * (size_t)rows * SB200_TRACE_COLS);
+    return rows;
+}
+
+int sb200_get_device_iterates(sb200_ws *ws, void **x, void **y, void **s)
+{
+    if (!ws || !ws->loaded) return SB200_ERR_INVALID;
+    if (x) *x = ws->V.x;
+    if (y) *y = ws->V.y;
+    if (s) *s = ws->V.s;
+    return SB200_OK;
+}
+
+int sb200_model_info(sb200_ws *ws, long long *info, int n_info)
+{
+    if (!ws || !ws->loaded || !info) return SB200_ERR_INVALID;
+    const long long vals[] = {ws->m, ws->n, ws->n_orig, ws->nnz, ws->mpad, ws->strategy, ws->pat.n_pairs,
+                              ws->pat.n_terms, ws->pat.term_w ? 1 : 0, ws->csc_lanes,
+                              ws->iter_graph_kernels, ws->chol.max_coop_grid};
+    const int k = (int)(sizeof vals / sizeof vals[0]);
+    for (int i = 0; i < n_info && i < k; ++i) info[i] = vals[i];
+    return k;
+}
+
+// ---- L0 kernels ------------------------------------------------------------------------------------
+static int l0_done(cudaStream_t st, bool sync)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? SB200_OK : SB200_ERR_CUDA;
+}
+
+int sb200_k_elem_min_mult(const double *d_x, const double *d_s, double *d_out, int n, void *stream)
+{
+    if (n <= 0) return SB200_OK;
+    launch_elem_min_mult(d_x, d_s, d_out, n, (cudaStream_t)stream);
+    return l0_done((cudaStream_t)stream, false);
+}
+
+int sb200_k_corrector_rhs(const double *d_dx, const double *d_ds, double sigma, double mu, double *d_out,
+                          int n, void *stream)
+{
+    if (n <= 0) return SB200_OK;
+    launch_corrector_rhs(d_dx, d_ds, sigma, mu, d_out, n, (cudaStream_t)stream);
+    return l0_done((cudaStream_t)stream, false);
+}
+
+int sb200_k_alpha_max(const double *d_x, const double *d_dx, const double *d_s, const double *d_ds, int n,
+                      double *d_result, double *h_result, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *ord = nullptr;
+    if (cudaMallocAsync(&ord, 16, st) != cudaSuccess) return SB200_ERR_NOMEM;
+    launch_alpha_max(d_x, d_dx, d_s, d_ds, n > 0 ? n : 0, ord, d_result, st);
+    cudaFreeAsync(ord, st);
+    if (h_result)
+    {
+        if (cudaMemcpyAsync(h_result, d_result, 16, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            return SB200_ERR_CUDA;
+        return l0_done(st, true);
+    }
+    return l0_done(st, false);
+}
+
+int sb200_k_spmv_csr(int m, const int *d_offs, const int *d_inds, const double *d_vals, const double *d_x,
+                     double *d_y, double alpha, double beta, void *stream)
+{
+    if (m <= 0) return SB200_OK;
+    launch_spmv_csr(CsrView{m, d_offs, d_inds, d_vals}, d_x, d_y, d_y, alpha, beta, (cudaStream_t)stream);
+    return l0_done((cudaStream_t)stream, false);
+}
+
+int sb200_k_spmv_csc(int n, const int *d_colptr, const int *d_rows, const double *d_vals, const double *d_x,
+                     double *d_y, double alpha, double beta, void *stream)
+{
+    if (n <= 0) return SB200_OK;
+    launch_spmv_csc(CscView{n, d_colptr, d_rows, d_vals, 8}, CSC_PLAIN, d_x, d_y, d_y, alpha, beta, nullptr,
+                    (cudaStream_t)stream);
+    return l0_done((cudaStream_t)stream, false);
+}
+
+int sb200_k_jacobi_diag(int m, const int *d_offs, const int *d_inds, const double *d_vals, const double *d_d,
+                        double *d_diag, void *stream)
+{
+    if (m <= 0) return SB200_OK;
+    launch_jacobi_diag(CsrView{m, d_offs, d_inds, d_vals}, d_d, d_diag, (cudaStream_t)stream);
+    return l0_done((cudaStream_t)stream, false);
+}
+
+static CholWork g_l0_chol;     // scratch of the stand-alone potrf/potrs entry points
+static ErrorSink g_l0_err;
+
+int sb200_k_potrf(int n, double *d_a, int ld, int *d_info, void *stream)
+{
+    if (n <= 0 || ld % SB200_TILE != 0 || ld < n) return SB200_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = chol_work_ensure(g_l0_err, g_l0_chol, ld);
+    if (rc) return rc;
+    if (cudaMemsetAsync(d_info, 0, sizeof(int), st) != cudaSuccess) return SB200_ERR_CUDA;
+    launch_potrf(g_l0_chol, n, d_a, ld, d_info, st);
+    return l0_done(st, false);
+}
+
+int sb200_k_potrs(int n, const double *d_l, int ld, double *d_b, void *stream)
+{
+    if (n <= 0 || ld % SB200_TILE != 0 || ld < n) return SB200_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = chol_work_ensure(g_l0_err, g_l0_chol, ld);
+    if (rc) return rc;
+    launch_potrs(g_l0_chol, n, d_l, ld, d_b, st);
+    return l0_done(st, false);
+}
+
+int sb200_k_syrk(int m, int k, const double *d_a, int lda, const double *d_d, double *d_c, int ld, void *stream)
+{
+    if (m <= 0 || k <= 0 || ld % SB200_TILE != 0 || lda % 32 != 0 || lda < k) return SB200_ERR_INVALID;
+    launch_syrk_dmma(m, k, d_a, lda, d_d, d_c, ld, (cudaStream_t)stream);
+    return l0_done((cudaStream_t)stream, false);
+}
+
+int sb200_assemble_normal(sb200_ws *ws, const double *d_d, double *d_m, int ld)
+{
+    if (!ws || !ws->loaded) return SB200_ERR_INVALID;
+    if (ws->strategy == SB200_STRATEGY_SYRK)
+    {
+        if (ld != ws->mpad) return fail(ws, SB200_ERR_INVALID, "sb200_assemble_normal: ld must equal mpad");
+        launch_syrk_dmma(ws->m, ws->n, ws->denseA, ws->kpad, d_d, d_m, ld, ws->stream);
+    }
+    else if (ws->pat.pair_ptr)
+        launch_assemble_normal(ws->pat, d_d, d_m, ld, ws->stream);
+    else
+        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_assemble_normal: model was loaded for the PCG strategy");
+    return l0_done(ws->stream, true);
+}
+
+} // extern "C"

@@ -1,0 +1,372 @@
+// sb200_assemble.cu - normal-equations assembly M = A diag(d) A'.
+//
+// The reference never forms M: it factors the full (2n+m)^2 KKT matrix
+// (/root/reference/src/sypha_solver.cpp:84-92,113-186) or, on the Krylov branch, applies
+// A D A' matrix-free (/root/reference/src/sypha_solver_krylov.cu:303-329).  north_star item (1)
+// replaces both with an explicit symmetric product.
+//
+// Sparse path (symbolic once per model, numeric once per IPM iteration):
+//   M[i][k] = sum over j in row_i ∩ row_k of a_ij a_kj d_j.
+//   Symbolic: for every column j emit the pairs (i >= k) of its rows keyed by the packed
+//   lower-triangular index, stable radix sort by key -> per-entry lists of column ids (sorted by j,
+//   so the summation order is fixed -> deterministic), prefix sum of the per-entry counts.
+//   Numeric: one thread per matrix entry gathers d over its list: no atomics, no symbolic work,
+//   coalesced writes of M.  Algorithmic bytes per iteration: 4 B (8+4 B when A has non-unit
+//   products) per term + 4 B per entry pointer + 8 B per written entry.
+// Dense path: FP64 tensor-core SYRK C = A diag(d) A' on a dense copy of A (64x64 tiles, DMMA).
+#include "sb200_kernels.cuh"
+#include "sb200_dmma.cuh"
+
+#include <cub/cub.cuh>
+
+namespace sb200 {
+
+// ---------------------------------------------------------------------------------------------
+// CSR -> CSC (device, deterministic: stable sort keeps rows ascending inside each column)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_expand_rows(int m, const int *__restrict__ offs, int *__restrict__ rowid,
+                              unsigned int *__restrict__ pos)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < m; row += gridDim.x * wpb)
+        for (int k = offs[row] + lane; k < offs[row + 1]; k += 32)
+        {
+            rowid[k] = row;
+            pos[k] = (unsigned int)k;
+        }
+}
+__global__ void k_count_cols(long long nnz, const int *__restrict__ inds, int *__restrict__ cnt)
+{
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz;
+         k += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[inds[k]], 1);
+}
+__global__ void k_gather_csc(long long nnz, const unsigned int *__restrict__ perm,
+                             const int *__restrict__ rowid, const double *__restrict__ vals,
+                             int *__restrict__ out_rows, double *__restrict__ out_vals)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nnz;
+         t += (long long)gridDim.x * blockDim.x)
+    {
+        const unsigned int p = perm[t];
+        out_rows[t] = rowid[p];
+        out_vals[t] = vals[p];
+    }
+}
+
+static int bits_for(unsigned long long n)
+{
+    int b = 1;
+    while (b < 64 && (1ull << b) < n) ++b;
+    return b;
+}
+
+int build_csc(ErrorSink &err, int m, int n, long long nnz, const int *csr_offs, const int *csr_inds,
+              const double *csr_vals, int *csc_colptr, int *csc_rows, double *csc_vals,
+              cudaStream_t st)
+{
+    int *rowid = nullptr, *cnt = nullptr;
+    unsigned int *pos = nullptr, *perm = nullptr;
+    int *keys_out = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    SB200_CUDA_TRY(err, cudaMalloc(&rowid, sizeof(int) * (size_t)nnz));
+    SB200_CUDA_TRY(err, cudaMalloc(&pos, sizeof(int) * (size_t)nnz));
+    SB200_CUDA_TRY(err, cudaMalloc(&perm, sizeof(int) * (size_t)nnz));
+    SB200_CUDA_TRY(err, cudaMalloc(&keys_out, sizeof(int) * (size_t)nnz));
+    SB200_CUDA_TRY(err, cudaMalloc(&cnt, sizeof(int) * (size_t)(n + 1)));
+    SB200_CUDA_TRY(err, cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n + 1), st));
+    k_expand_rows<<<grid_for((long long)m * 32, 256, 148 * 16), 256, 0, st>>>(m, csr_offs, rowid, pos);
+    k_count_cols<<<grid_for(nnz, 256, 148 * 16), 256, 0, st>>>(nnz, csr_inds, cnt);
+    const int nb = bits_for((unsigned long long)n);
+    SB200_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, csr_inds, keys_out, pos, perm,
+                                                        nnz, 0, nb, st));
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, csc_colptr, n + 1, st));
+    if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
+    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    size_t tb = tmp_bytes;
+    SB200_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(tmp, tb, csr_inds, keys_out, pos, perm, nnz, 0, nb, st));
+    tb = tmp_bytes;
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, csc_colptr, n + 1, st));
+    k_gather_csc<<<grid_for(nnz, 256, 148 * 16), 256, 0, st>>>(nnz, perm, rowid, csr_vals, csc_rows, csc_vals);
+    g_launch_count += 3;
+    SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+    cudaFree(rowid); cudaFree(pos); cudaFree(perm); cudaFree(keys_out); cudaFree(cnt); cudaFree(tmp);
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// symbolic structure of M
+// ---------------------------------------------------------------------------------------------
+__global__ void k_col_term_counts(int n, const int *__restrict__ colptr, const double *__restrict__ vals,
+                                  unsigned long long *__restrict__ cnt, int *__restrict__ general)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += gridDim.x * blockDim.x)
+    {
+        if (j == n)
+        {
+            cnt[j] = 0;
+            continue;
+        }
+        const int a = colptr[j], e = colptr[j + 1];
+        const unsigned long long c = (unsigned long long)(e - a);
+        cnt[j] = c * (c + 1) / 2;
+        // all products a_ij a_kj are +1 iff the column is all +1 or all -1
+        bool unit = true;
+        if (e > a)
+        {
+            const double v0 = vals[a];
+            unit = (v0 == 1.0 || v0 == -1.0);
+            for (int k = a + 1; k < e && unit; ++k)
+                unit = (vals[k] == v0);
+        }
+        if (!unit) atomicOr(general, 1);
+    }
+}
+
+template <bool GENERAL>
+__global__ void k_emit_terms(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
+                             const double *__restrict__ vals, const unsigned long long *__restrict__ toff,
+                             unsigned int *__restrict__ keys, unsigned int *__restrict__ payload,
+                             unsigned int *__restrict__ colj, double *__restrict__ w,
+                             unsigned int *__restrict__ pair_cnt)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb)
+    {
+        const int a0 = colptr[j];
+        const long long c = colptr[j + 1] - a0;
+        const long long cnt = c * (c + 1) / 2;
+        const unsigned long long base = toff[j];
+        for (long long q = lane; q < cnt; q += 32)
+        {
+            long long a = (long long)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+            while ((a + 1) * (a + 2) / 2 <= q) ++a;
+            while (a * (a + 1) / 2 > q) --a;
+            const long long b = q - a * (a + 1) / 2;
+            const unsigned long long ra = (unsigned long long)rows[a0 + a];   // ra >= rb (rows ascending)
+            const unsigned long long rb = (unsigned long long)rows[a0 + b];
+            const unsigned int key = (unsigned int)(ra * (ra + 1) / 2 + rb);
+            keys[base + q] = key;
+            if (GENERAL)
+            {
+                payload[base + q] = (unsigned int)(base + q);
+                colj[base + q] = (unsigned int)j;
+                w[base + q] = vals[a0 + a] * vals[a0 + b];
+            }
+            else
+                payload[base + q] = (unsigned int)j;
+            atomicAdd(&pair_cnt[key], 1u);
+        }
+    }
+}
+__global__ void k_gather_terms(long long T, const unsigned int *__restrict__ perm,
+                               const unsigned int *__restrict__ colj, const double *__restrict__ w,
+                               unsigned int *__restrict__ term_col, double *__restrict__ term_w)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < T;
+         t += (long long)gridDim.x * blockDim.x)
+    {
+        const unsigned int p = perm[t];
+        term_col[t] = colj[p];
+        term_w[t] = w[p];
+    }
+}
+
+void free_normal_pattern(NormalPattern *p)
+{
+    if (p->pair_ptr) cudaFree(p->pair_ptr);
+    if (p->term_col) cudaFree(p->term_col);
+    if (p->term_w) cudaFree(p->term_w);
+    *p = NormalPattern{};
+}
+
+int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
+                         const int *csc_rows, const double *csc_vals, NormalPattern *out,
+                         cudaStream_t st)
+{
+    (void)nnz;
+    free_normal_pattern(out);
+    if (m > 65535)
+    {
+        err.msg = "build_normal_pattern: m > 65535 (packed pair index would overflow 32 bits)";
+        return SB200_ERR_UNSUPPORTED;
+    }
+    const long long n_pairs = (long long)m * (m + 1) / 2;
+    unsigned long long *cnt = nullptr, *toff = nullptr;
+    int *general_d = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    SB200_CUDA_TRY(err, cudaMalloc(&cnt, sizeof(unsigned long long) * (size_t)(n + 1)));
+    SB200_CUDA_TRY(err, cudaMalloc(&toff, sizeof(unsigned long long) * (size_t)(n + 1)));
+    SB200_CUDA_TRY(err, cudaMalloc(&general_d, sizeof(int)));
+    SB200_CUDA_TRY(err, cudaMemsetAsync(general_d, 0, sizeof(int), st));
+    k_col_term_counts<<<grid_for(n + 1, 256, 148 * 16), 256, 0, st>>>(n, csc_colptr, csc_vals, cnt, general_d);
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, toff, n + 1, st));
+    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, toff, n + 1, st));
+    unsigned long long T = 0;
+    int general = 0;
+    SB200_CUDA_TRY(err, cudaMemcpyAsync(&T, toff + n, sizeof T, cudaMemcpyDeviceToHost, st));
+    SB200_CUDA_TRY(err, cudaMemcpyAsync(&general, general_d, sizeof general, cudaMemcpyDeviceToHost, st));
+    SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+    cudaFree(tmp); tmp = nullptr;
+    cudaFree(cnt); cudaFree(general_d);
+    if (T >= 0xFFFFFFF0ull)
+    {
+        cudaFree(toff);
+        err.msg = "build_normal_pattern: more than 2^32 product terms; use the PCG strategy";
+        return SB200_ERR_UNSUPPORTED;
+    }
+
+    unsigned int *keys = nullptr, *keys_out = nullptr, *payload = nullptr, *payload_out = nullptr;
+    unsigned int *colj = nullptr, *pair_cnt = nullptr;
+    double *w = nullptr;
+    const size_t Ts = (size_t)(T > 0 ? T : 1);
+    SB200_CUDA_TRY(err, cudaMalloc(&keys, 4 * Ts));
+    SB200_CUDA_TRY(err, cudaMalloc(&keys_out, 4 * Ts));
+    SB200_CUDA_TRY(err, cudaMalloc(&payload, 4 * Ts));
+    SB200_CUDA_TRY(err, cudaMalloc(&payload_out, 4 * Ts));
+    SB200_CUDA_TRY(err, cudaMalloc(&pair_cnt, 4 * (size_t)(n_pairs + 1)));
+    SB200_CUDA_TRY(err, cudaMalloc(&out->pair_ptr, 4 * (size_t)(n_pairs + 1)));
+    SB200_CUDA_TRY(err, cudaMemsetAsync(pair_cnt, 0, 4 * (size_t)(n_pairs + 1), st));
+    if (general)
+    {
+        SB200_CUDA_TRY(err, cudaMalloc(&colj, 4 * Ts));
+        SB200_CUDA_TRY(err, cudaMalloc(&w, 8 * Ts));
+        k_emit_terms<true><<<grid_for((long long)n * 32, 256, 148 * 16), 256, 0, st>>>(
+            n, csc_colptr, csc_rows, csc_vals, toff, keys, payload, colj, w, pair_cnt);
+    }
+    else
+        k_emit_terms<false><<<grid_for((long long)n * 32, 256, 148 * 16), 256, 0, st>>>(
+            n, csc_colptr, csc_rows, csc_vals, toff, keys, payload, nullptr, nullptr, pair_cnt);
+    const int nb = bits_for((unsigned long long)n_pairs);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    SB200_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys, keys_out, payload,
+                                                        payload_out, (long long)T, 0, nb, st));
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, pair_cnt, out->pair_ptr,
+                                                      n_pairs + 1, st));
+    tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    size_t tb = tmp_bytes;
+    SB200_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_out, payload, payload_out,
+                                                        (long long)T, 0, nb, st));
+    tb = tmp_bytes;
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tb, pair_cnt, out->pair_ptr, n_pairs + 1, st));
+    if (general)
+    {
+        SB200_CUDA_TRY(err, cudaMalloc(&out->term_col, 4 * Ts));
+        SB200_CUDA_TRY(err, cudaMalloc(&out->term_w, 8 * Ts));
+        k_gather_terms<<<grid_for((long long)T, 256, 148 * 16), 256, 0, st>>>((long long)T, payload_out, colj, w,
+                                                                            out->term_col, out->term_w);
+        SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+        cudaFree(payload_out);
+    }
+    else
+    {
+        SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+        out->term_col = payload_out;      // the sorted payload IS the column list
+        out->term_w = nullptr;
+    }
+    g_launch_count += 3;
+    cudaFree(keys); cudaFree(keys_out); cudaFree(payload); cudaFree(pair_cnt); cudaFree(toff); cudaFree(tmp);
+    if (colj) cudaFree(colj);
+    if (w) cudaFree(w);
+    out->m = m;
+    out->n_pairs = n_pairs;
+    out->n_terms = (long long)T;
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// numeric assembly: one thread per lower-triangular entry
+// ---------------------------------------------------------------------------------------------
+template <bool GENERAL>
+__global__ void __launch_bounds__(256)
+k_assemble_normal(long long n_pairs, const unsigned int *__restrict__ pair_ptr,
+                  const unsigned int *__restrict__ term_col, const double *__restrict__ term_w,
+                  const double *__restrict__ d, double *__restrict__ M, int ld)
+{
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_pairs;
+         p += (long long)gridDim.x * blockDim.x)
+    {
+        const unsigned int a = pair_ptr[p], e = pair_ptr[p + 1];
+        double sum = 0.0;
+        for (unsigned int t = a; t < e; ++t)
+        {
+            const double dj = __ldg(d + term_col[t]);
+            sum += GENERAL ? term_w[t] * dj : dj;
+        }
+        long long i = (long long)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        const long long k = p - i * (i + 1) / 2;
+        M[i * ld + k] = sum;
+    }
+}
+
+void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld, cudaStream_t st)
+{
+    const int grid = grid_for(P.n_pairs, 256, 148 * 64);
+    if (P.term_w)
+        k_assemble_normal<true><<<grid, 256, 0, st>>>(P.n_pairs, P.pair_ptr, P.term_col, P.term_w, d, M, ld);
+    else
+        k_assemble_normal<false><<<grid, 256, 0, st>>>(P.n_pairs, P.pair_ptr, P.term_col, nullptr, d, M, ld);
+    ++g_launch_count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 tensor-core SYRK: C(lower, 64x64 tiles) = A diag(d) A', A dense row-major (rows padded to 64,
+// columns padded to 32 with zeros)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_syrk_dmma(int kpad, const double *__restrict__ A, int lda, const double *__restrict__ d,
+            double *__restrict__ C, int ld)
+{
+    __shared__ __align__(16) double smem[2 * TB * KP];
+    __shared__ double dsh[KC];
+    double(*As)[KP] = reinterpret_cast<double(*)[KP]>(smem);
+    double(*Bs)[KP] = reinterpret_cast<double(*)[KP]>(smem + TB * KP);
+    const int p = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+    while (ti * (ti + 1) / 2 > p) --ti;
+    const int tj = p - ti * (ti + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w >> 1, wn = w & 1, g = lane >> 2, tg = lane & 3;
+    const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kc = 0; kc < kpad; kc += KC)
+    {
+        __syncthreads();
+        if (tid < KC) dsh[tid] = d[kc + tid];
+        __syncthreads();
+        load_tile_64xKC(As, A + r0 * lda + kc, lda, tid, 128, dsh);
+        load_tile_64xKC(Bs, A + c0 * lda + kc, lda, tid, 128, nullptr);
+        __syncthreads();
+        warp_mma_32x32(As, Bs, wm, wn, lane, 1.0, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2 *>(C + (r0 + wm * 32 + i * 8 + g) * ld + c0 + wn * 32 + j * 8 +
+                                         tg * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+void launch_syrk_dmma(int m, int k, const double *a, int lda, const double *d, double *c, int ld,
+                      cudaStream_t st)
+{
+    (void)m;
+    const int T = ld / TB;
+    const int kpad = (k + KC - 1) / KC * KC;
+    k_syrk_dmma<<<T * (T + 1) / 2, 128, 0, st>>>(kpad, a, lda, d, c, ld);
+    ++g_launch_count;
+}
+
+} // namespace sb200

@@ -64,6 +64,10 @@ struct DevParams
     int gap_enabled;
     int gap_window;
     int n_orig;
+    int cg_max_iter;
+    double cg_tol_initial;
+    double cg_tol_final;
+    double cg_tol_decay;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -45,8 +45,7 @@ enum
     CSC_RECOVER = 1,    // ds = resC - w ; dx = (resXS - x ds)/s ; ratio test
     CSC_START_X = 2,    // x = w ; min
     CSC_START_S = 3,    // s = c - w ; min
-    CSC_RESC = 4,       // resC = c - s - w
-    CSC_SCALE_D = 5     // out = d .* w      (PCG: q = D A'p)
+    CSC_RESC = 4        // resC = c - s - w
 };
 
 // ---- sb200_vector.cu -------------------------------------------------------------------------
@@ -56,11 +55,11 @@ void launch_corrector_rhs(const double *dx, const double *ds, double sigma, doub
 void launch_alpha_max(const double *x, const double *dx, const double *s, const double *ds, int n,
                       unsigned long long *d_ord2, double *d_result, cudaStream_t st);
 void launch_reset_scalars(Scalars *sc, cudaStream_t st);
-void launch_init_mu(const IpmVecs &V, const DevParams &P, cudaStream_t st);
+void launch_init_mu(const IpmVecs &V, const DevParams *P, cudaStream_t st);   // P: device pointer
 void launch_prologue(const IpmVecs &V, cudaStream_t st);
 void launch_affine_mu(const IpmVecs &V, cudaStream_t st);
 void launch_corrector(const IpmVecs &V, cudaStream_t st);
-void launch_update(const IpmVecs &V, const DevParams &P, cudaStream_t st);
+void launch_update(const IpmVecs &V, const DevParams *P, cudaStream_t st);    // P: device pointer
 void launch_start_shift1(const IpmVecs &V, cudaStream_t st);
 void launch_start_shift2(const IpmVecs &V, cudaStream_t st);
 void launch_fill(double *p, double v, long long n, cudaStream_t st);
@@ -75,8 +74,7 @@ void launch_spmv_csc(const CscView &A, int mode, const double *v, const double *
 int pick_csc_lanes(long long nnz, int n);
 
 // ---- sb200_chol.cu ---------------------------------------------------------------------------
-void launch_potrf(int n, double *a, int ld, int *info, cudaStream_t st);
-void launch_potrs(int n, const double *l, int ld, double *b, cudaStream_t st);
+// (launch_potrf / launch_potrs: sb200_chol.cuh)
 void launch_pad_identity(int n, double *a, int ld, cudaStream_t st);
 
 // ---- sb200_assemble.cu -----------------------------------------------------------------------

@@ -9,6 +9,7 @@
 //
 // Both kernels are HBM-bound: 12 B per stored entry (8 B value + 4 B index) + the dense vectors.
 #include "sb200_kernels.cuh"
+#include "sb200_pcg.cuh"
 
 namespace sb200 {
 
@@ -79,7 +80,7 @@ k_spmv_csc(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
            IpmVecs V)
 {
     __shared__ double sh[32];
-    if (MODE == CSC_RECOVER || MODE == CSC_SCALE_D)
+    if (MODE == CSC_RECOVER)
         if (V.sc->done) return;
     const int gl = threadIdx.x & (G - 1);
     const int groups_per_block = blockDim.x / G;
@@ -123,8 +124,6 @@ k_spmv_csc(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
             }
             else if (MODE == CSC_RESC)
                 V.resC[col] = V.c[col] - V.s[col] - acc;
-            else if (MODE == CSC_SCALE_D)
-                out[col] = V.d[col] * acc;
         }
     }
     if (MODE == CSC_RECOVER || MODE == CSC_START_X || MODE == CSC_START_S)
@@ -171,7 +170,6 @@ static void launch_csc_g(const CscView &A, int mode, const double *v, const doub
         SB200_CSC_CASE(CSC_START_X)
         SB200_CSC_CASE(CSC_START_S)
         SB200_CSC_CASE(CSC_RESC)
-        SB200_CSC_CASE(CSC_SCALE_D)
     }
 #undef SB200_CSC_CASE
     ++g_launch_count;
@@ -191,6 +189,56 @@ void launch_spmv_csc(const CscView &A, int mode, const double *v, const double *
     case 16: launch_csc_g<16>(A, mode, v, z, out, alpha, beta, V, st); break;
     default: launch_csc_g<32>(A, mode, v, z, out, alpha, beta, V, st); break;
     }
+}
+
+// PCG: q = D A'p (D = I when dscale == nullptr); skipped once the CG solve has finished
+template <int G>
+__global__ void __launch_bounds__(256)
+k_spmv_csc_cg(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
+              const double *__restrict__ vals, const double *__restrict__ p, double *__restrict__ q,
+              const double *__restrict__ dscale, const Scalars *sc)
+{
+    if (sc->cg_done) return;
+    const int gl = threadIdx.x & (G - 1);
+    const int groups_per_block = blockDim.x / G;
+    const int ncols_round = ((n + groups_per_block - 1) / groups_per_block) * groups_per_block;
+    for (int col = blockIdx.x * groups_per_block + threadIdx.x / G; col < ncols_round;
+         col += gridDim.x * groups_per_block)
+    {
+        double acc = 0.0;
+        if (col < n)
+        {
+            const int a = colptr[col], e = colptr[col + 1];
+            for (int k = a + gl; k < e; k += G)
+                acc += vals[k] * __ldg(p + rows[k]);
+        }
+        acc = group_sum<G>(acc);
+        if (gl == 0 && col < n)
+            q[col] = dscale ? dscale[col] * acc : acc;
+    }
+}
+
+void launch_spmv_csc_cg(const CscView &A, const double *p, double *q, const double *dscale,
+                        const Scalars *sc, cudaStream_t st)
+{
+#define SB200_CG_CASE(G)                                                                           \
+    case G:                                                                                        \
+        k_spmv_csc_cg<G><<<grid_for((long long)A.n * G, 256, 148 * 16), 256, 0, st>>>(             \
+            A.n, A.colptr, A.rows, A.vals, p, q, dscale, sc);                                      \
+        break;
+    switch (A.lanes)
+    {
+        SB200_CG_CASE(1)
+        SB200_CG_CASE(2)
+        SB200_CG_CASE(4)
+        SB200_CG_CASE(8)
+        SB200_CG_CASE(16)
+    default:
+        k_spmv_csc_cg<32><<<grid_for((long long)A.n * 32, 256, 148 * 16), 256, 0, st>>>(
+            A.n, A.colptr, A.rows, A.vals, p, q, dscale, sc);
+    }
+#undef SB200_CG_CASE
+    ++g_launch_count;
 }
 
 } // namespace sb200

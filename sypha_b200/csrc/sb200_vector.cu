@@ -135,22 +135,43 @@ void launch_prologue(const IpmVecs &V, cudaStream_t st)
 }
 
 // mu = x.s/n ; arm the loop      (sypha_solver.cpp:458-459, loop test :496)
-__global__ void k_init_mu(IpmVecs V, DevParams P)
+__global__ void k_init_mu(IpmVecs V, const DevParams *__restrict__ Pp)
 {
     __shared__ double sh[32];
-    double acc = 0.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < V.n; j += gridDim.x * blockDim.x)
-        acc += V.x[j] * V.s[j];
+    const DevParams P = *Pp;
+    double acc = 0.0, a_p = 0.0, a_d = 0.0;
+    const int lim = max(V.n, V.m);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < lim; j += gridDim.x * blockDim.x)
+    {
+        if (j < V.n)
+        {
+            acc += V.x[j] * V.s[j];
+            if (j < P.n_orig) a_p += V.x[j] * V.c[j];
+        }
+        if (j < V.m) a_d += V.y[j] * V.b[j];
+    }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) V.partial[blockIdx.x] = acc;
+    a_p = block_sum(a_p, sh);
+    a_d = block_sum(a_d, sh);
+    if (threadIdx.x == 0)
+    {
+        V.partial[blockIdx.x] = acc;
+        V.partial[SB200_MAX_PARTIAL_BLOCKS + blockIdx.x] = a_p;
+        V.partial[2 * SB200_MAX_PARTIAL_BLOCKS + blockIdx.x] = a_d;
+    }
     if (last_block_arrives(&V.sc->ticket[0], gridDim.x))
     {
         double tot = reduce_partials(V.partial, gridDim.x, sh);
+        const double t_p = reduce_partials(V.partial + SB200_MAX_PARTIAL_BLOCKS, gridDim.x, sh);
+        const double t_d = reduce_partials(V.partial + 2 * SB200_MAX_PARTIAL_BLOCKS, gridDim.x, sh);
         if (threadIdx.x == 0)
         {
             Scalars *sc = V.sc;
             const double mu = tot / (double)V.n;
             sc->mu = mu;
+            sc->primal = t_p;
+            sc->dual = t_d;
+            sc->gap = fabs(t_p - t_d) / fmax(1.0, fabs(t_p));
             sc->iter = 0;
             sc->stall = 0;
             sc->best_gap = INFINITY;
@@ -167,9 +188,9 @@ __global__ void k_init_mu(IpmVecs V, DevParams P)
         }
     }
 }
-void launch_init_mu(const IpmVecs &V, const DevParams &P, cudaStream_t st)
+void launch_init_mu(const IpmVecs &V, const DevParams *P, cudaStream_t st)
 {
-    k_init_mu<<<grid_for(V.n, kBlock), kBlock, 0, st>>>(V, P);
+    k_init_mu<<<grid_for(max(V.n, V.m), kBlock), kBlock, 0, st>>>(V, P);
     ++g_launch_count;
 }
 
@@ -227,11 +248,12 @@ void launch_corrector(const IpmVecs &V, cudaStream_t st)
 
 // step, residual scaling, mu / objectives / termination, and the next iteration's prologue
 // (sypha_solver.cpp:693-769 and :505 of the following iteration)
-__global__ void k_update(IpmVecs V, DevParams P)
+__global__ void k_update(IpmVecs V, const DevParams *__restrict__ Pp)
 {
     __shared__ double sh[32];
     Scalars *sc = V.sc;
     if (sc->done) return;
+    const DevParams P = *Pp;
     const double ap = fmin(1.0, P.eta * ord_decode(sc->amax_p));
     const double ad = fmin(1.0, P.eta * ord_decode(sc->amax_d));
     const double fc = -(ad - 1.0), fb = -(ap - 1.0);
@@ -326,7 +348,7 @@ __global__ void k_update(IpmVecs V, DevParams P)
         }
     }
 }
-void launch_update(const IpmVecs &V, const DevParams &P, cudaStream_t st)
+void launch_update(const IpmVecs &V, const DevParams *P, cudaStream_t st)
 {
     k_update<<<grid_for(max(V.n, V.m), kBlock), kBlock, 0, st>>>(V, P);
     ++g_launch_count;

@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's operator interface for the IPM hot path.
+
+Same names, argument meaning and error behaviour as the reference
+(/root/reference/src/sypha_solver_sparse.h:13-51, src/sypha_solver.h:76-108,
+src/sypha_node_sparse.h:26-119), over the C ABI of libsypha_b200.so.  Python only marshals
+buffers; every number is computed by the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+
+# enum SyphaStatus (src/common.h:24-29)
+CODE_SUCCESSFUL, CODE_GENERIC_ERROR, CODE_MODEL_TYPE_NOT_FOUND = range(3)
+# enum SolverTerminationReason (src/sypha_solver_sparse.h:13-20)
+(SOLVER_TERM_CONVERGED, SOLVER_TERM_MAX_ITER, SOLVER_TERM_GAP_STALLED,
+ SOLVER_TERM_INFEASIBLE_OR_NUMERICAL, SOLVER_TERM_TIME_LIMIT) = range(5)
+
+
+class Sb200Error(RuntimeError):
+    """A CUDA / library failure.  The reference treats these as fatal (checkCudaErrors -> exit,
+    src/sypha_cuda_helper.h:19-31); the Python shim raises instead."""
+
+
+@dataclasses.dataclass
+class SolverGapStagnationConfig:            # src/sypha_solver_sparse.h:22-27
+    enabled: bool = False
+    windowIterations: int = 0
+    minImprovementPct: float = 0.0
+
+
+@dataclasses.dataclass
+class SolverExecutionConfig:                # src/sypha_solver_sparse.h:29-36
+    maxIterations: int = 25
+    gapStagnation: SolverGapStagnationConfig = dataclasses.field(default_factory=SolverGapStagnationConfig)
+    bnbNodeOrdinal: int = 0
+    denseSelectionLogEveryNodes: int = 1
+    skipGpuMemorySampling: bool = False
+
+
+@dataclasses.dataclass
+class SolverExecutionResult:                # src/sypha_solver_sparse.h:38-48
+    status: int = CODE_GENERIC_ERROR
+    terminationReason: int = SOLVER_TERM_MAX_ITER
+    iterations: int = 0
+    primalObj: float = 0.0
+    dualObj: float = 0.0
+    relativeGap: float = math.inf
+    primalSolution: Optional[np.ndarray] = None
+    dualSolution: Optional[np.ndarray] = None
+    # extras (not in the reference struct)
+    slackSolution: Optional[np.ndarray] = None
+    mu: float = math.nan
+    msStart: float = 0.0
+    msSetup: float = 0.0
+    msLoop: float = 0.0
+    strategyUsed: int = 0
+    cgIterations: int = 0
+    kernelsLaunched: int = 0
+    trace: Optional[np.ndarray] = None
+
+
+@dataclasses.dataclass
+class SyphaEnvironment:
+    """The parameter surface of src/sypha_environment.h:89-100 that the hot path reads
+    (defaults: src/sypha_environment_defaults.h:14-30)."""
+    mehrotraMaxIter: int = 25
+    mehrotraEta: float = 0.95
+    mehrotraMuTol: float = 1e-4
+    linearSolverStrategy: str = "auto"      # auto | cholesky | syrk | pcg (krylov)
+    krylovMaxCgIter: int = 500
+    krylovCgTolInitial: float = 1e-2
+    krylovCgTolFinal: float = 1e-8
+    krylovCgTolDecayRate: float = 0.5
+    cudaDeviceId: int = 0
+    pollEvery: int = 1
+    useGraph: bool = True
+    stopRequested: Optional[C.c_int] = None     # logger watchdog flag (src/sypha_logger.h:69)
+
+
+class IpmWorkspace:
+    """Persistent device workspace (src/sypha_solver.h:76-105).  Grow-only; reused across LPs."""
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        self.isAllocated = False
+        self.device = 0
+
+    def __del__(self):
+        try:
+            releaseIpmWorkspace(self)
+        except Exception:
+            pass
+
+
+def initializeIpmWorkspace(ws: IpmWorkspace, maxKktNrows: int = 0, maxKktNnz: int = 0, maxNcols: int = 0,
+                           device: int = 0):
+    """src/sypha_solver.h:107.  The sizing arguments are KKT-shaped in the reference
+    (src/sypha_solver_bnb_driver.cpp:620-626: rows 2n+m, nnz 2nnz+3n); recover m, n, nnz."""
+    lib = L.load()
+    caps = None
+    if maxKktNrows > 0 and maxNcols > 0 and maxKktNnz > 0:
+        m_max = maxKktNrows - 2 * maxNcols
+        nnz_max = (maxKktNnz - 3 * maxNcols) // 2
+        if m_max > 0 and nnz_max > 0:
+            caps = L.sb200_caps(m_max, maxNcols, nnz_max)
+    rc = lib.sb200_ws_create(device, C.byref(caps) if caps else None, C.byref(ws.handle))
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_ws_create failed (code {rc}): no CUDA device or out of memory; "
+                         "there is no CPU fallback")
+    ws.isAllocated = True
+    ws.device = device
+
+
+def releaseIpmWorkspace(ws: IpmWorkspace):
+    """src/sypha_solver.h:108."""
+    if ws.isAllocated and ws.handle:
+        L.load().sb200_ws_destroy(ws.handle)
+    ws.handle = C.c_void_p()
+    ws.isAllocated = False
+
+
+class SyphaNodeSparse:
+    """The model container fields the solver reads/writes (src/sypha_node_sparse.h:26-119)."""
+
+    def __init__(self, env: Optional[SyphaEnvironment] = None):
+        self.env = env or SyphaEnvironment()
+        self.ncols = self.nrows = self.ncolsOriginal = self.nnz = 0
+        self.hCsrMatInds = self.hCsrMatOffs = self.hCsrMatVals = None
+        self.hObjDns = self.hRhsDns = None
+        self.hX = self.hY = self.hS = None
+        self.objvalPrim = self.objvalDual = 0.0
+        self.mipGap = math.inf
+        self.iterations = 0
+        self.timeStartSol = self.timePreSol = self.timeSolver = 0.0
+        self._loaded_into = None
+
+    @classmethod
+    def from_csr(cls, m, n, n_orig, offs, inds, vals, c, b, env=None):
+        node = cls(env)
+        node.nrows, node.ncols, node.ncolsOriginal = int(m), int(n), int(n_orig)
+        node.hCsrMatOffs = np.ascontiguousarray(offs, dtype=np.int32)
+        node.hCsrMatInds = np.ascontiguousarray(inds, dtype=np.int32)
+        node.hCsrMatVals = np.ascontiguousarray(vals, dtype=np.float64)
+        node.hObjDns = np.ascontiguousarray(c, dtype=np.float64)
+        node.hRhsDns = np.ascontiguousarray(b, dtype=np.float64)
+        node.nnz = int(node.hCsrMatInds.shape[0])
+        return node
+
+    def copyModelOnDevice(self, workspace: IpmWorkspace, strategy: Optional[str] = None):
+        """src/sypha_node_sparse.cpp:156-198: upload CSR, c, b (and build CSC + symbolic M)."""
+        lib = L.load()
+        strat = L.STRATEGY_NAMES[(strategy or self.env.linearSolverStrategy).lower()]
+        rc = lib.sb200_load_model(
+            workspace.handle, self.nrows, self.ncols, self.ncolsOriginal, self.nnz,
+            self.hCsrMatOffs.ctypes.data, self.hCsrMatInds.ctypes.data, self.hCsrMatVals.ctypes.data,
+            self.hObjDns.ctypes.data, self.hRhsDns.ctypes.data, 0, strat)
+        if rc != L.SB200_OK:
+            raise Sb200Error(f"sb200_load_model failed (code {rc}): "
+                             f"{lib.sb200_last_error(workspace.handle).decode()}")
+        self._loaded_into = workspace
+        return CODE_SUCCESSFUL
+
+
+def _params_from(node: SyphaNodeSparse, config: SolverExecutionConfig) -> L.sb200_params:
+    lib = L.load()
+    p = L.sb200_params()
+    lib.sb200_default_params(C.byref(p))
+    env = node.env
+    # src/sypha_solver.cpp:488
+    p.max_iter = config.maxIterations if config.maxIterations > 0 else env.mehrotraMaxIter
+    p.eta = env.mehrotraEta
+    p.mu_tol = env.mehrotraMuTol
+    g = config.gapStagnation
+    p.gap_enabled = 1 if g.enabled else 0
+    p.gap_window = g.windowIterations
+    p.gap_min_improv_pct = g.minImprovementPct
+    p.cg_max_iter = env.krylovMaxCgIter
+    p.cg_tol_initial = env.krylovCgTolInitial
+    p.cg_tol_final = env.krylovCgTolFinal
+    p.cg_tol_decay = env.krylovCgTolDecayRate
+    p.poll_every = env.pollEvery
+    p.use_graph = 1 if env.useGraph else 0
+    if env.stopRequested is not None:
+        p.stop_flag = C.pointer(env.stopRequested)
+    return p
+
+
+def _fill_result(node, ws, res: L.sb200_result, result: SolverExecutionResult, x, y, s):
+    lib = L.load()
+    result.status = CODE_SUCCESSFUL if res.status == L.SB200_OK else CODE_GENERIC_ERROR
+    result.terminationReason = res.reason
+    result.iterations = res.iterations
+    result.primalObj, result.dualObj, result.relativeGap = res.primal_obj, res.dual_obj, res.rel_gap
+    result.primalSolution, result.dualSolution, result.slackSolution = x, y, s
+    result.mu = res.mu
+    result.msStart, result.msSetup, result.msLoop = res.ms_start, res.ms_setup, res.ms_loop
+    result.strategyUsed = res.strategy_used
+    result.cgIterations = res.cg_iterations
+    result.kernelsLaunched = res.kernels_launched
+    tr = np.zeros((max(res.iterations, 1), L.TRACE_COLS))
+    rows = lib.sb200_get_trace(ws.handle, tr.ctypes.data, tr.shape[0])
+    result.trace = tr[:rows]
+    # node.* outputs, src/sypha_solver.cpp:774-797
+    node.iterations = res.iterations
+    node.objvalPrim, node.objvalDual = res.primal_obj, res.dual_obj
+    node.mipGap = math.inf
+    node.timeStartSol, node.timePreSol, node.timeSolver = res.ms_start / 1e3, res.ms_setup / 1e3, res.ms_loop / 1e3
+
+
+def solver_sparse_mehrotra_run(node: SyphaNodeSparse, config: SolverExecutionConfig,
+                               result: Optional[SolverExecutionResult] = None,
+                               workspace: Optional[IpmWorkspace] = None) -> int:
+    """SyphaStatus solver_sparse_mehrotra_run(node, config, result, workspace)
+    - src/sypha_solver_sparse.h:51.  With ``workspace=None`` everything is allocated and freed
+    inside the call (src/sypha_solver.cpp:197-203, :841-871)."""
+    lib = L.load()
+    own = workspace is None or not workspace.isAllocated
+    ws = workspace
+    if own:
+        ws = IpmWorkspace()
+        initializeIpmWorkspace(ws, device=node.env.cudaDeviceId)
+    try:
+        if node._loaded_into is not ws:
+            node.copyModelOnDevice(ws)
+        p = _params_from(node, config)
+        res = L.sb200_result()
+        x = np.empty(node.ncols)
+        y = np.empty(node.nrows)
+        s = np.empty(node.ncols)
+        res.x_host, res.y_host, res.s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data
+        rc = lib.sb200_solve(ws.handle, C.byref(p), C.byref(res))
+        if rc != L.SB200_OK:
+            raise Sb200Error(f"sb200_solve failed (code {rc}): {lib.sb200_last_error(ws.handle).decode()}")
+        if result is None:
+            result = SolverExecutionResult()
+        _fill_result(node, ws, res, result, x, y, s)
+        return result.status
+    finally:
+        if own:
+            node._loaded_into = None
+            releaseIpmWorkspace(ws)
+
+
+def solver_sparse_mehrotra(node: SyphaNodeSparse) -> int:
+    """Thin wrapper, src/sypha_solver.cpp:25-40."""
+    config = SolverExecutionConfig(maxIterations=node.env.mehrotraMaxIter)
+    result = SolverExecutionResult()
+    status = solver_sparse_mehrotra_run(node, config, result)
+    return status if status != CODE_SUCCESSFUL else result.status
+
+
+def solve_batch(nodes, config: SolverExecutionConfig, workspaces):
+    """Solve independent LPs concurrently (one workspace/stream each) - the B&B node body of
+    src/sypha_solver_bnb_driver.cpp:789-859 batched per GPU."""
+    lib = L.load()
+    k = len(nodes)
+    for node, ws in zip(nodes, workspaces):
+        if node._loaded_into is not ws:
+            node.copyModelOnDevice(ws)
+    p = _params_from(nodes[0], config)
+    handles = (C.c_void_p * k)(*[ws.handle for ws in workspaces])
+    res = (L.sb200_result * k)()
+    bufs = []
+    for i, node in enumerate(nodes):
+        x, y, s = np.empty(node.ncols), np.empty(node.nrows), np.empty(node.ncols)
+        res[i].x_host, res[i].y_host, res[i].s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data
+        bufs.append((x, y, s))
+    rc = lib.sb200_solve_batch(handles, k, None, C.byref(p), res)
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_solve_batch failed (code {rc})")
+    out = []
+    for i, node in enumerate(nodes):
+        r = SolverExecutionResult()
+        _fill_result(node, workspaces[i], res[i], r, *bufs[i])
+        out.append(r)
+    return out

@@ -1,0 +1,166 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the golden fixtures (reference's
+own outputs) and the oracle on the same inputs.
+
+Contract (BASELINE.json north_star): primal/dual objective equal to the reference's to 1e-6 relative,
+iteration count within +-1, complementarity (mu) below the same tolerance."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, node_from_instance
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import sypha_b200 as sb  # noqa: E402
+from oracle import mehrotra as mo  # noqa: E402
+from oracle import scp_io  # noqa: E402
+
+REL = 1e-6      # objective tolerance stated by north_star
+
+
+def run(inst, ws, max_iter=100, strategy="auto", **env_kw):
+    node = node_from_instance(inst, linearSolverStrategy=strategy, **env_kw)
+    res = sb.SolverExecutionResult()
+    st = sb.solver_sparse_mehrotra_run(node, sb.SolverExecutionConfig(maxIterations=max_iter), res, ws)
+    return st, res, node
+
+
+def check_against(res, iters, primal, dual):
+    assert abs(res.iterations - iters) <= 1
+    assert abs(res.primalObj - primal) <= REL * max(1.0, abs(primal))
+    assert abs(res.dualObj - dual) <= REL * max(1.0, abs(dual))
+
+
+SMALL = ["demo00", "scp_demo06", "scp_demo_tiny03", "scp41", "scp42", "scp46", "scp48", "scp49", "scp410",
+         "scp51", "scpclr10", "scpcyc06", "scpa1", "scpb1"]
+LARGE = ["scpnre1", "scpnrf1", "scpnrg1", "scpnrh1", "scpclr13"]
+
+
+@pytest.mark.parametrize("name", SMALL + LARGE)
+def test_golden_parity_cholesky(name, cuda_ws):
+    inst, z = load_golden(name)
+    st, res, node = run(inst, cuda_ws, strategy="cholesky")
+    assert st == sb.CODE_SUCCESSFUL and res.terminationReason == sb.SOLVER_TERM_CONVERGED
+    assert res.iterations == int(z["ref_iters"])        # in practice exact, contract is +-1
+    check_against(res, int(z["ref_iters"]), float(z["ref_primal"]), float(z["ref_dual"]))
+    assert res.mu <= 1e-4
+    # per-iteration trajectory against the oracle's trace stored with the fixture
+    mu_tr = z["oracle_mu_trace"]
+    k = min(len(mu_tr), res.trace.shape[0])
+    assert np.allclose(res.trace[:k, 1], mu_tr[:k], rtol=1e-6)
+    # iterates against the reference's final point
+    assert np.max(np.abs(res.primalSolution - z["ref_x"]) / (1 + np.abs(z["ref_x"]))) < 1e-5
+    assert np.max(np.abs(res.dualSolution - z["ref_y"]) / (1 + np.abs(z["ref_y"]))) < 1e-5
+    # node.* outputs (sypha_solver.cpp:774-797)
+    assert node.iterations == res.iterations and node.objvalPrim == res.primalObj and np.isinf(node.mipGap)
+
+
+@pytest.mark.parametrize("name", ["scp41", "scpclr10", "scpnrf1", "scpclr13"])
+def test_golden_parity_syrk(name, cuda_ws):
+    """dense-ish switch: FP64 tensor-core SYRK assembly + Cholesky (configs[2])."""
+    inst, z = load_golden(name)
+    st, res, _ = run(inst, cuda_ws, strategy="syrk")
+    assert st == sb.CODE_SUCCESSFUL
+    check_against(res, int(z["ref_iters"]), float(z["ref_primal"]), float(z["ref_dual"]))
+
+
+@pytest.mark.parametrize("name", ["scp_demo06", "scp41", "scpcyc06"])
+def test_pcg_parity_tight(name, cuda_ws):
+    """PCG strategy with a tight tolerance tracks the direct solve (parity contract of config 4)."""
+    inst, z = load_golden(name)
+    st, res, _ = run(inst, cuda_ws, strategy="pcg", krylovMaxCgIter=50000, krylovCgTolInitial=1e-9,
+                     krylovCgTolFinal=1e-9, krylovCgTolDecayRate=1.0)
+    assert st == sb.CODE_SUCCESSFUL
+    check_against(res, int(z["ref_iters"]), float(z["ref_primal"]), float(z["ref_dual"]))
+    assert res.cgIterations > 0
+
+
+def test_pcg_reference_cap_is_a_failed_lp(cuda_ws):
+    """With the reference's cap (500) Jacobi-PCG runs out before mu <= 1e-4 and the LP is reported
+    failed, exactly as sypha_solver.cpp:558-566 does."""
+    inst = scp_io.gen_scp(300, 6000, 0.005, 1)
+    st, res, _ = run(inst, cuda_ws, strategy="pcg")
+    o = mo.solve_instance(inst, mo.Params(max_iter=100), "pcg")
+    assert o.status == 1
+    assert st == sb.CODE_GENERIC_ERROR and res.terminationReason == sb.SOLVER_TERM_INFEASIBLE_OR_NUMERICAL
+    assert abs(res.iterations - o.iterations) <= 1
+
+
+def test_default_iteration_cap_binds(cuda_ws):
+    inst, _ = load_golden("scpnre1")
+    st, res, _ = run(inst, cuda_ws, max_iter=0)          # 0 -> env default 25 (solver.cpp:488)
+    o = mo.solve_instance(inst, mo.Params(), "ne")
+    assert res.iterations == 25 and res.terminationReason == sb.SOLVER_TERM_MAX_ITER
+    check_against(res, o.iterations, o.primal, o.dual)
+
+
+def test_gap_stagnation(cuda_ws):
+    inst, _ = load_golden("scp41")
+    node = node_from_instance(inst)
+    cfg = sb.SolverExecutionConfig(maxIterations=100,
+                                   gapStagnation=sb.SolverGapStagnationConfig(True, 2, 60.0))
+    res = sb.SolverExecutionResult()
+    sb.solver_sparse_mehrotra_run(node, cfg, res, cuda_ws)
+    o = mo.solve_instance(inst, mo.Params(max_iter=100, gap_stagnation=True, gap_window=2,
+                                          gap_min_improv_pct=60.0), "ne")
+    assert res.terminationReason == sb.SOLVER_TERM_GAP_STALLED == o.reason
+    assert res.iterations == o.iterations
+    check_against(res, o.iterations, o.primal, o.dual)
+
+
+def test_branch_node_models(cuda_ws):
+    """B&B node LPs: base + appended rows with -1 coefficients (general, non-unit-product path)."""
+    inst, _ = load_golden("scp_demo06")
+    for dec in ([(3, 1)], [(3, 1), (7, 0)], [(0, 0), (1, 0), (2, 1)]):
+        node = scp_io.append_branch_rows(inst, dec)
+        o = mo.solve_instance(node, mo.Params(max_iter=100), "ne")
+        st, res, _ = run(node, cuda_ws)
+        assert (st == sb.CODE_SUCCESSFUL) == (o.status == 0)
+        if o.status == 0:
+            check_against(res, o.iterations, o.primal, o.dual)
+
+
+def test_synthetic_generator_instance(cuda_ws):
+    """SURVEY.md Appendix C check values on the GPU path."""
+    inst = scp_io.gen_scp(1000, 20000, 0.005, 0)
+    st, res, _ = run(inst, cuda_ws)
+    assert st == sb.CODE_SUCCESSFUL
+    check_against(res, 24, 554.166452726, 552.956531973)
+
+
+def test_workspace_none_and_reuse(cuda_ws):
+    inst, z = load_golden("scp49")
+    node = node_from_instance(inst)
+    r1 = sb.SolverExecutionResult()
+    sb.solver_sparse_mehrotra_run(node, sb.SolverExecutionConfig(maxIterations=100), r1, None)
+    st, r2, _ = run(inst, cuda_ws)
+    st, r3, _ = run(inst, cuda_ws)
+    assert r1.primalObj == r2.primalObj == r3.primalObj      # deterministic: bit-equal across runs
+    assert np.array_equal(r2.primalSolution, r3.primalSolution)
+
+
+def test_graph_and_stream_paths_agree(cuda_ws):
+    inst, _ = load_golden("scp42")
+    _, a, _ = run(inst, cuda_ws, useGraph=True)
+    _, b, _ = run(inst, cuda_ws, useGraph=False)
+    _, c, _ = run(inst, cuda_ws, useGraph=True, pollEvery=4)
+    assert a.iterations == b.iterations == c.iterations
+    assert a.primalObj == b.primalObj == c.primalObj and a.dualObj == b.dualObj == c.dualObj
+
+
+def test_batch_of_independent_lps():
+    """solve_batch: independent LPs on their own streams give the same answers as one by one."""
+    names = ["scp41", "scp42", "scp46", "scp48"]
+    insts = [load_golden(n)[0] for n in names]
+    wss = []
+    for _ in names:
+        w = sb.IpmWorkspace()
+        sb.initializeIpmWorkspace(w)
+        wss.append(w)
+    nodes = [node_from_instance(i) for i in insts]
+    out = sb.solve_batch(nodes, sb.SolverExecutionConfig(maxIterations=100), wss)
+    for n, r in zip(names, out):
+        z = load_golden(n)[1]
+        check_against(r, int(z["ref_iters"]), float(z["ref_primal"]), float(z["ref_dual"]))
+    for w in wss:
+        sb.releaseIpmWorkspace(w)

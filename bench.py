@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py - IPM iterations/s and time-to-LP-optimum of the Mehrotra hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one LP solve (starting point + predictor-corrector loop to mu <= 1e-4, max_iter 100,
+eta 0.95 - SURVEY.md 8d) of one synthetic set-covering LP relaxation.  Default workload =
+BASELINE.json configs[1]: scpnrh-shaped (1000 x 10000, 5% density, costs 1..100), five rotating
+instances (like scpnrh1-5) so a step never finds its inputs in L2.  Prints ONE JSON line.
+
+  value : whole-job IPM iterations/s, models resident in HBM (CSR/CSC/symbolic structure loaded)
+  e2e   : the same metric through the reference-facing call with HOST buffers: every step uploads
+          the CSR model (sb200_load_model: H2D + CSC + symbolic), solves and reads x, y, s back
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+--impl reference times the CPU restatement of the reference's own solver (oracle/, NumPy+SciPy with
+all host BLAS threads) on the same workload; /root/reference does not exist on the GPU box.
+N > 1: one process per GPU (torchrun), independent LPs per rank, no data-path collective (the path
+does not shard inside an LP: "weak" scaling, replicas of the LP workload).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+WORKLOADS = {
+    # name: (m, n_orig, density, description)
+    "scpnrh": (1000, 10000, 0.05, "scpnrh-shaped synthetic SCP LP relaxation 1000x10000, 5% density (configs[1])"),
+    "scp4": (200, 1000, 0.02, "scp4x-shaped synthetic SCP LP relaxation 200x1000, 2% density (configs[0])"),
+    "scpnrf": (500, 5000, 0.20, "scpnrf-shaped synthetic SCP LP relaxation 500x5000, 20% density (configs[2])"),
+    "synth5k": (5000, 100000, 0.001, "synthetic SCP 5000x100000, 0.1% density (configs[3] ladder rung)"),
+    "synth50k": (50000, 1000000, 0.001, "synthetic SCP 50000x1000000, 0.1% density (configs[3])"),
+}
+N_INSTANCES = 5
+MAX_ITER = 100
+
+
+def read_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_evt = threading.Event()
+        self.sm, self.maxsm, self.reasons = [], [], set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in out.strip().split(",")]
+                self.sm.append(float(f[0]))
+                self.maxsm.append(float(f[1]))
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_evt.wait(0.2)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.maxsm)),
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def algorithmic_bytes(info, phase):
+    """Algorithmic bytes (or flops) of one launch group, DESIGN.md 'Kernels'."""
+    m, n, nnz, mpad, n_pairs, n_terms, general = (info["m"], info["n"], info["nnz"], info["mpad"],
+                                                  info["n_pairs"], info["n_terms"], info["general"])
+    if phase == "assemble":      # term stream + entry pointers + M written once
+        return n_terms * (12 if general else 4) + n_pairs * 4 + n_pairs * 8
+    if phase == "potrf":         # M read once + L written once (lower triangles)
+        return 2 * 8 * m * (m + 1) // 2
+    if phase == "potrs":         # L read twice (forward + backward)
+        return 2 * 8 * m * (m + 1) // 2
+    if phase == "spmv_csr":
+        return 12 * nnz + 8 * (n + 2 * m)
+    if phase == "spmv_csc_recover":
+        return 12 * nnz + 8 * (m + 6 * n)
+    if phase == "vector":
+        return 8 * 4 * n
+    raise KeyError(phase)
+
+
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    import sypha_b200 as sb
+    from sypha_b200 import _lib as L
+    from sypha_b200.instances import gen_scp
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    m, n0, dens, desc = WORKLOADS[args.workload]
+    strategy = args.strategy
+    models = [gen_scp(m, n0, dens, 1000 * rank + i + 1) for i in range(N_INSTANCES)]
+
+    env = sb.SyphaEnvironment(cudaDeviceId=local_rank, linearSolverStrategy=strategy,
+                              pollEvery=args.poll_every, useGraph=not args.no_graph,
+                              krylovMaxCgIter=args.cg_max_iter, krylovCgTolInitial=args.cg_tol,
+                              krylovCgTolFinal=args.cg_tol, krylovCgTolDecayRate=1.0)
+    cfg = sb.SolverExecutionConfig(maxIterations=MAX_ITER)
+    wss, nodes = [], []
+    for mdl in models:
+        ws = sb.IpmWorkspace()
+        sb.initializeIpmWorkspace(ws, device=local_rank)
+        node = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+        node.copyModelOnDevice(ws)
+        wss.append(ws)
+        nodes.append(node)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(i):
+        res = sb.SolverExecutionResult()
+        st = sb.solver_sparse_mehrotra_run(nodes[i % N_INSTANCES], cfg, res, wss[i % N_INSTANCES])
+        if st != sb.CODE_SUCCESSFUL:
+            raise RuntimeError(f"LP {i} failed: reason {res.terminationReason}")
+        return res
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    results = [step(i) for i in range(args.steps)]
+    barrier()
+    elapsed = time.perf_counter() - t0
+    iters = sum(r.iterations for r in results)
+    launches = sum(r.kernelsLaunched for r in results)
+    dev_ms = sum(r.msStart + r.msSetup + r.msLoop for r in results)
+    loop_ms = sum(r.msLoop for r in results)
+
+    # ---- e2e: host buffers in, host results out, every step ---------------------------------
+    e2e_ws = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(e2e_ws, device=local_rank)
+    pinned = []
+    for mdl in models:
+        arrs = {}
+        for k in ("offs", "inds", "vals", "c", "b"):
+            t = torch.from_numpy(getattr(mdl, k)).pin_memory()
+            arrs[k] = t
+        pinned.append(arrs)
+
+    def e2e_step(i):
+        mdl, a = models[i % N_INSTANCES], pinned[i % N_INSTANCES]
+        node = sb.SyphaNodeSparse(env)
+        node.nrows, node.ncols, node.ncolsOriginal, node.nnz = mdl.m, mdl.n, mdl.n_orig, mdl.nnz
+        node.hCsrMatOffs, node.hCsrMatInds, node.hCsrMatVals = a["offs"].numpy(), a["inds"].numpy(), a["vals"].numpy()
+        node.hObjDns, node.hRhsDns = a["c"].numpy(), a["b"].numpy()
+        res = sb.SolverExecutionResult()
+        sb.solver_sparse_mehrotra_run(node, cfg, res, e2e_ws)      # uploads (model not resident), solves, D2H
+        return res
+
+    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
+    if e2e_steps:
+        e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_res = [e2e_step(i) for i in range(e2e_steps)]
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    e2e_iters = sum(r.iterations for r in e2e_res)
+    mdl0 = models[0]
+    h2d = int(mdl0.offs.nbytes + mdl0.inds.nbytes + mdl0.vals.nbytes + mdl0.c.nbytes + mdl0.b.nbytes)
+    d2h = int(8 * (2 * mdl0.n + mdl0.m))
+    sampler.stop_evt.set()
+    sampler.join(timeout=2)
+
+    # ---- max over ranks / sums ----------------------------------------------------------------
+    if dist:
+        t = torch.tensor([elapsed, e2e_elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed, e2e_elapsed = float(t[0]), float(t[1])
+        c = torch.tensor([iters, launches, e2e_iters], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        iters, launches, e2e_iters = int(c[0]), int(c[1]), int(c[2])
+
+    out = None
+    if rank == 0:
+        # ---- per-phase device timing (CUDA events on the workspace stream) and the roofline ---
+        info_arr = (C.c_longlong * 12)()
+        lib.sb200_model_info(wss[0].handle, info_arr, 12)
+        info = dict(m=info_arr[0], n=info_arr[1], nnz=info_arr[3], mpad=info_arr[4], strategy=info_arr[5],
+                    n_pairs=info_arr[6], n_terms=info_arr[7], general=info_arr[8])
+        peak, peak_src = read_peaks()
+        phases = {}
+        names = {0: "assemble", 1: "potrf", 2: "potrs", 3: "spmv_csr", 4: "spmv_csc_recover", 5: "vector"}
+        per_iter = {"assemble": 1, "potrf": 1, "potrs": 2, "spmv_csr": 2, "spmv_csc_recover": 2, "vector": 3}
+        for pid, nm in ({} if args.no_phases else names).items():
+            ms = C.c_double()
+            if lib.sb200_time_phase(wss[0].handle, pid, 20, C.byref(ms)) == 0:
+                by = algorithmic_bytes(info, nm)
+                phases[nm] = {"ms": ms.value, "algorithmic_bytes": by, "gbs": by / ms.value / 1e6,
+                              "frac_hbm": by / ms.value / 1e6 / peak, "per_iteration": per_iter[nm]}
+        roof = None
+        if phases:
+            dom = max(phases, key=lambda k: phases[k]["ms"] * phases[k]["per_iteration"])
+            ph = phases[dom]
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ph["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": ph["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch_group": ph["ms"], "algorithmic_bytes": ph["algorithmic_bytes"]}
+            if dom in ("potrf",):
+                flops = info["m"] ** 3 / 3.0
+                roof["flops"] = flops
+                roof["tflops"] = flops / ph["ms"] / 1e9
+        out = {
+            "metric": "ipm_iterations_per_sec", "value": iters / elapsed, "unit": "iter/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "instances": N_INSTANCES, "m": m, "n_orig": n0, "density": dens,
+                       "max_iter": MAX_ITER, "eta": 0.95, "mu_tol": 1e-4,
+                       "strategy": {1: "cholesky", 2: "syrk", 3: "pcg"}.get(info["strategy"], "?"),
+                       "l2": f"{N_INSTANCES} rotating instances, working set > 126 MB L2 (no flush needed)",
+                       "poll_every": args.poll_every, "graph": not args.no_graph},
+            "time_to_lp_opt_ms": 1e3 * elapsed / args.steps,
+            "iterations_per_lp": iters / (args.steps * world),
+            "device_ms_per_lp": dev_ms / args.steps, "loop_ms_per_lp": loop_ms / args.steps,
+            "e2e": ({"value": e2e_iters / e2e_elapsed, "unit": "iter/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_elapsed / e2e_steps, "steps": e2e_steps}
+                    if e2e_steps else None),
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "phases": phases,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(models[0], budget_s=args.cpu_budget)
+    for ws in wss + [e2e_ws]:
+        sb.releaseIpmWorkspace(ws)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def to_oracle_instance(mdl):
+    from oracle import scp_io
+    return scp_io.ScpInstance(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, mdl.name)
+
+
+def cpu_baseline(mdl, budget_s=25.0, solver="ne"):
+    """The oracle (CPU port of the reference's solver) on a bounded sample of the same workload."""
+    from oracle import mehrotra as mo
+    inst = to_oracle_instance(mdl)
+    t0 = time.perf_counter()
+    probe = mo.solve_instance(inst, mo.Params(max_iter=MAX_ITER), solver, stop_after=2)
+    t_probe = time.perf_counter() - t0
+    per_iter = max(probe.loop_seconds / max(probe.iterations, 1), 1e-6)
+    cap = int(max(2, min(MAX_ITER, (budget_s - probe.start_seconds) / per_iter)))
+    r = mo.solve_instance(inst, mo.Params(max_iter=MAX_ITER), solver, stop_after=cap)
+    full = r.reason == mo.TERM_CONVERGED
+    secs = r.start_seconds + r.loop_seconds
+    return {"value": r.iterations / secs, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": (f"one {'full' if full else 'truncated'} LP solve of instance 0 ({r.iterations} iterations, "
+                       f"start point {r.start_seconds:.2f} s + loop {r.loop_seconds:.2f} s), NumPy/SciPy oracle "
+                       f"(normal equations + LAPACK Cholesky), BLAS threads = all cores"),
+            "seconds": secs, "probe_seconds": t_probe}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle restatement of the reference's solver, rank 0 only."""
+    if rank != 0:
+        return None
+    from sypha_b200.instances import gen_scp
+    m, n0, dens, desc = WORKLOADS[args.workload]
+    models = [gen_scp(m, n0, dens, i + 1) for i in range(N_INSTANCES)]
+    budget = max(2.0, 170.0 / (args.steps + args.warmup))
+    samples = []
+    for i in range(args.warmup):
+        cpu_baseline(models[i % N_INSTANCES], budget)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        samples.append(cpu_baseline(models[i % N_INSTANCES], budget))
+    elapsed = time.perf_counter() - t0
+    iters_s = sum(s["value"] * s["seconds"] for s in samples) / sum(s["seconds"] for s in samples)
+    return {
+        "impl": "reference", "metric": "ipm_iterations_per_sec", "value": iters_s, "unit": "iter/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "instances": N_INSTANCES, "m": m, "n_orig": n0, "density": dens,
+                   "max_iter": MAX_ITER, "eta": 0.95, "mu_tol": 1e-4},
+        "cpu_baseline": {"value": iters_s, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": samples[0]["sample"] + f"; {args.steps} such steps, {budget:.0f} s budget each"},
+        "e2e": {"value": iters_s, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement (oracle/) of the reference's solver: the reference's CUDA build needs GSL, "
+                "Boost and cuSOLVER/cuSPARSE and does not compile here; its Python prototype cannot travel",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="scpnrh", choices=sorted(WORKLOADS))
+    ap.add_argument("--strategy", default="auto")
+    ap.add_argument("--poll-every", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-phases", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--cg-max-iter", type=int, default=50000)
+    ap.add_argument("--cg-tol", type=float, default=1e-8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        out = run_ours(args, rank, world, local_rank)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -151,6 +151,11 @@ int sb200_get_device_iterates(sb200_ws *ws, void **x, void **y, void **s);
 /* introspection used by bench.py for the roofline arithmetic */
 int sb200_model_info(sb200_ws *ws, long long *info, int n_info);
 void *sb200_stream(sb200_ws *ws);
+/* time one phase of the loop on the resident model with CUDA events on the workspace stream:
+ * phase 0 = normal-matrix assembly, 1 = Cholesky factorisation, 2 = one solve (forward+backward),
+ * 3 = CSR SpMV (rhs), 4 = CSC SpMV + recovery + ratio test, 5 = fused update kernel.
+ * Writes the mean milliseconds per launch group over `reps` runs (after one warm-up). */
+int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out);
 
 /* ---- L0 kernels on caller-owned device buffers ------------------------------------------------ */
 int sb200_k_elem_min_mult(const double *d_x, const double *d_s, double *d_out, int n, void *stream);

@@ -737,6 +737,61 @@ int sb200_model_info(sb200_ws *ws, long long *info, int n_info)
     return k;
 }
 
+int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out)
+{
+    if (!ws || !ws->loaded || !ms_out || reps <= 0) return SB200_ERR_INVALID;
+    if (ws->strategy == SB200_STRATEGY_PCG && (phase == 0 || phase == 1 || phase == 2))
+        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_time_phase: direct-path phase on a PCG model");
+    WS_TRY(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    const IpmVecs &V = ws->V;
+    cudaEvent_t e0, e1;
+    WS_TRY(cudaEventCreate(&e0));
+    WS_TRY(cudaEventCreate(&e1));
+    // a benign state: d = 1, done = 0
+    launch_reset_scalars(ws->sc, st);
+    double total = 0.0;
+    for (int r = -1; r < reps; ++r)
+    {
+        if (phase == 1 || phase == 2)
+        {   // the factorisation is in place: re-assemble (untimed) before every timed potrf
+            if (ws->strategy == SB200_STRATEGY_SYRK)
+            {
+                launch_syrk_dmma(ws->m, ws->n, ws->denseA, ws->kpad, ws->ones_n, ws->M, ws->mpad, st);
+                launch_pad_identity(ws->m, ws->M, ws->mpad, st);
+            }
+            else
+                launch_assemble_normal(ws->pat, ws->ones_n, ws->M, ws->mpad, st);
+            if (phase == 2) launch_potrf(ws->chol, ws->m, ws->M, ws->mpad, &ws->sc->chol_info, st);
+        }
+        WS_TRY(cudaEventRecord(e0, st));
+        switch (phase)
+        {
+        case 0:
+            if (ws->strategy == SB200_STRATEGY_SYRK)
+                launch_syrk_dmma(ws->m, ws->n, ws->denseA, ws->kpad, ws->ones_n, ws->M, ws->mpad, st);
+            else
+                launch_assemble_normal(ws->pat, ws->ones_n, ws->M, ws->mpad, st);
+            break;
+        case 1: launch_potrf(ws->chol, ws->m, ws->M, ws->mpad, &ws->sc->chol_info, st); break;
+        case 2: launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, V.rhs, st); break;
+        case 3: launch_spmv_csr(csr_of(ws), V.t, V.resB, V.rhs, 1.0, 1.0, st); break;
+        case 4: launch_spmv_csc(csc_of(ws), CSC_RECOVER, V.y, nullptr, nullptr, 0, 0, &V, st); break;
+        case 5: launch_affine_mu(V, st); break;
+        default: return fail(ws, SB200_ERR_INVALID, "sb200_time_phase: unknown phase");
+        }
+        WS_TRY(cudaEventRecord(e1, st));
+        WS_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        WS_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 0) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = total / reps;
+    return SB200_OK;
+}
+
 // ---- L0 kernels ------------------------------------------------------------------------------------
 static int l0_done(cudaStream_t st, bool sync)
 {

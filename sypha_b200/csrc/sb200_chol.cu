@@ -7,11 +7,12 @@
 // Layout: row-major, lower triangle, leading dimension ld = m rounded up to 64, identity pad.
 //
 // Factorisation (right-looking, 64-wide panels, 2 launches per panel):
-//   k_trsm_panel : X = A_ik L_kk^-T by row-wise forward substitution (one thread per row)
+//   k_trsm_panel : X = A_ik (L_kk^-1)' as a 64x64x64 FP64 tensor-core GEMM against the pre-inverted
+//                  diagonal block
 //   k_update     : A_ij -= L_ik L_jk'  on 64x64 tiles with FP64 tensor-core MMA
 //                  (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4); the CTA that owns the next diagonal
-//                  tile factors it in shared memory before writing it back (look-ahead), so no
-//                  separate potrf launch sits on the critical path.
+//                  tile factors AND inverts it in shared memory before writing it back (look-ahead),
+//                  so no separate potrf launch sits on the critical path.
 // Solves (one launch each, data-flow): every 64-row block is owned by one CTA which accumulates
 //   its right-hand side as the blocks it depends on are published through release/acquire flags,
 //   then multiplies by the pre-inverted 64x64 diagonal block.  All CTAs are co-resident
@@ -24,37 +25,281 @@ namespace sb200 {
 
 static constexpr int LP = TB + 1;    // padded stride of the potrf tile
 
+// dynamic shared-memory layout of the kernels that factor a diagonal tile (bytes)
+static constexpr int SM_LS = 0;                                   // L tile (aliases the MMA staging buffers)
+static constexpr int SM_MMA_BYTES = 2 * TB * KP * 8;              // 36864
+static constexpr int SM_LI = SM_MMA_BYTES;                        // inverse tile
+static constexpr int SM_T = SM_LI + TB * LP * 8;                  // scratch of the inverse (<= 1024 doubles)
+static constexpr int SM_P = SM_T + 1024 * 8;                      // double-buffered 64x4 panel
+static constexpr int SM_D = SM_P + 2 * 256 * 8;                   // 4x4 inverse of the current diagonal block
+static constexpr int SM_FLAG = SM_D + 32 * 8;                     // (D is double buffered)
+static constexpr int SM_TOTAL = SM_FLAG + 16;
+static constexpr int NT_TILE = 288;                               // threads of the tile factorisation
+
 // ---------------------------------------------------------------------------------------------
-// potrf of a 64x64 tile held in shared memory (lower), 128 threads.  Returns 0 or the 1-based
-// local index of the first non-positive pivot (same value in every thread).
+// Cholesky + inverse of a 64x64 tile in shared memory, 288 threads (see the thread -> block map).
+//   Threads with ty >= tx keep the 4x4 block (rows 4ty..,
+//   cols 4tx..) of the lower triangle of A in registers.  Threads with ty < tx ("mirror" threads,
+//   idle in a plain Cholesky) keep block (row-block tx, col-block ty) of the running inverse.
+//   16 block-column steps, 2 barriers each:
+//     diag thread jb : factor its 4x4 block (4 dependent rsqrt), W = its 4x4 inverse -> smem
+//     -- barrier --
+//     panel threads (tx == jb, ty > jb)      : L_ij = A_ij W'            -> panel buffer (transposed)
+//     mirror threads of inverse row-block jb : X_j,: = W R_j,:           -> inverse-row buffer
+//     -- barrier --
+//     trailing threads (tx > jb)             : A_ik -= L_ij L_kj'
+//     mirror threads of row-blocks i > jb    : R_i,: -= L_ij X_j,:
+//   (right-looking forward substitution on the identity, R starts as I).
+// On exit Ls = L (upper zeroed), Li = L^-1 (upper zero).  Returns 0 or the 1-based local index of
+// the first non-positive pivot.
 // ---------------------------------------------------------------------------------------------
-__device__ int potrf_tile64(double (*Ls)[LP], int tid)
+#ifdef SB200_TILE_TIMING
+__device__ long long g_tile_timing[64];
+#define TT(i) do { if (tid == 0) g_tile_timing[i] = clock64(); } while (0)
+__device__ long long g_tile_trace[16][9][8];
+#define TACC(i) do { const long long now__ = clock64(); tacc__[i - 40] += now__ - tprev__; tprev__ = now__; \
+                     if ((tid & 31) == 0) g_tile_trace[jb][tid >> 5][i - 40] = now__; } while (0)
+#else
+#define TT(i) do { } while (0)
+#define TACC(i) do { } while (0)
+#endif
+
+__device__ int potrf_inv_tile64(unsigned char *smem, int tid)
 {
-    int fail = 0;
-    const int i = tid & 63, h = tid >> 6;
-    for (int j = 0; j < TB; ++j)
+    TT(0);
+    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
+    double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LI);
+    double *P = reinterpret_cast<double *>(smem + SM_P);     // [2][4][64]  panel, transposed: P[k][row]
+    double *XR = reinterpret_cast<double *>(smem + SM_T);    // [2][4][64]  inverse rows:      XR[r][col]
+    double *D2 = reinterpret_cast<double *>(smem + SM_D);   // [2][16]
+    int *sflag = reinterpret_cast<int *>(smem + SM_FLAG);
+
+    // Thread -> block map (288 threads): warp 0 lanes 0..15 own the diagonal blocks and nothing else, so
+    // the serial chain (update diag block -> 4 dependent rsqrt) never waits behind off-diagonal work
+    // of its own warp; threads 32..151 own the 120 strictly-lower blocks, 152..271 the 120 mirror
+    // (inverse) blocks; the rest idle.
+    int ty = -1, tx = 100;                 // idle: fails every role test below
+    if (tid < 16)
+        ty = tx = tid;
+    else if (tid >= 32 && tid < 272)
     {
-        __syncthreads();
-        const double diag = Ls[j][j];
-        if (!(diag > 0.0) && fail == 0) fail = j + 1;
-        const double r = sqrt(diag);
-        const double inv = 1.0 / r;
-        __syncthreads();
-        if (h == 0)
+        const int q = (tid - 32) % 120;
+        int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
+        while (i * (i - 1) / 2 > q) --i;
+        while ((i + 1) * i / 2 <= q) ++i;
+        const int j = q - i * (i - 1) / 2;          // i > j
+        if (tid < 152) { ty = i; tx = j; }          // lower block (i, j)
+        else           { ty = j; tx = i; }          // mirror of (i, j)
+    }
+    const bool valid = ty >= 0;
+    const bool lower = valid && ty >= tx;
+    // lower threads: a = A block (ty, tx).  mirror threads: a = inverse/residual block (tx, ty).
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            a[r][c] = lower ? Ls[4 * ty + r][4 * tx + c] : 0.0;
+    if (tid == 0) *sflag = 0;
+    TT(1);
+#ifdef SB200_TILE_TIMING
+    long long tprev__ = clock64();
+    long long tacc__[5] = {0, 0, 0, 0, 0};
+#endif
+
+    for (int jb = 0; jb < 16; ++jb)
+    {
+        double *Pb = P + (jb & 1) * 256;
+        double *Xb = XR + (jb & 1) * 256;
+        double *D = D2 + (jb & 1) * 16;
+        if (ty == jb && tx == jb)
         {
-            if (i == j) Ls[j][j] = r;
-            else if (i > j) Ls[i][j] *= inv;
+#ifdef SB200_TILE_TIMING
+            const long long tq0 = clock64();
+#endif
+            double inv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+                const double d = a[c][c];
+                if (!(d > 0.0)) atomicCAS(sflag, 0, 4 * jb + c + 1);
+                inv[c] = rsqrt(d);
+                a[c][c] = d * inv[c];
+#pragma unroll
+                for (int r = c + 1; r < 4; ++r)
+                    a[r][c] *= inv[c];
+#pragma unroll
+                for (int c2 = c + 1; c2 < 4; ++c2)
+#pragma unroll
+                    for (int r = c2; r < 4; ++r)
+                        a[r][c2] -= a[r][c] * a[c2][c];
+            }
+            a[0][1] = a[0][2] = a[0][3] = a[1][2] = a[1][3] = a[2][3] = 0.0;
+            // W = inverse of the 4x4 lower block
+            const double w00 = inv[0], w11 = inv[1], w22 = inv[2], w33 = inv[3];
+            const double w10 = -a[1][0] * w00 * w11;
+            const double w21 = -a[2][1] * w11 * w22;
+            const double w32 = -a[3][2] * w22 * w33;
+            const double w20 = -(a[2][0] * w00 + a[2][1] * w10) * w22;
+            const double w31 = -(a[3][1] * w11 + a[3][2] * w21) * w33;
+            const double w30 = -(a[3][0] * w00 + a[3][1] * w10 + a[3][2] * w20) * w33;
+            D[0] = w00; D[1] = 0.0; D[2] = 0.0; D[3] = 0.0;
+            D[4] = w10; D[5] = w11; D[6] = 0.0; D[7] = 0.0;
+            D[8] = w20; D[9] = w21; D[10] = w22; D[11] = 0.0;
+            D[12] = w30; D[13] = w31; D[14] = w32; D[15] = w33;
+#ifdef SB200_TILE_TIMING
+            g_tile_timing[16 + jb] = clock64() - tq0;
+#endif
         }
+        TACC(40);
         __syncthreads();
-        if (i > j)
+        TACC(41);
+        if (tx == jb && ty != jb)
         {
-            const double lij = Ls[i][j];
-            for (int k = j + 1 + h; k <= i; k += 2)
-                Ls[i][k] -= lij * Ls[k][j];
+            double w[16];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+            {
+                const double2 v = *reinterpret_cast<const double2 *>(&D[2 * q]);
+                w[2 * q] = v.x;
+                w[2 * q + 1] = v.y;
+            }
+            if (ty > jb)
+            {   // panel: L_ij = A_ij W'
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                {
+                    const double a0 = a[r][0], a1 = a[r][1], a2 = a[r][2], a3 = a[r][3];
+                    a[r][0] = a0 * w[0];
+                    a[r][1] = a0 * w[4] + a1 * w[5];
+                    a[r][2] = a0 * w[8] + a1 * w[9] + a2 * w[10];
+                    a[r][3] = a0 * w[12] + a1 * w[13] + a2 * w[14] + a3 * w[15];
+                }
+            }
+            else
+            {   // mirror, inverse row-block jb, column-block ty < jb: X = W R (R complete through jb-1)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    const double r0 = a[0][c], r1 = a[1][c], r2 = a[2][c], r3 = a[3][c];
+                    a[0][c] = w[0] * r0;
+                    a[1][c] = w[4] * r0 + w[5] * r1;
+                    a[2][c] = w[8] * r0 + w[9] * r1 + w[10] * r2;
+                    a[3][c] = w[12] * r0 + w[13] * r1 + w[14] * r2 + w[15] * r3;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                {
+                    *reinterpret_cast<double2 *>(&Xb[r * 64 + 4 * ty]) = make_double2(a[r][0], a[r][1]);
+                    *reinterpret_cast<double2 *>(&Xb[r * 64 + 4 * ty + 2]) = make_double2(a[r][2], a[r][3]);
+                }
+            }
+        }
+        if (tx == jb && ty >= jb)
+        {   // column block jb of L, transposed: Pb[c][row]
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+                *reinterpret_cast<double2 *>(&Pb[c * 64 + 4 * ty]) = make_double2(a[0][c], a[1][c]);
+                *reinterpret_cast<double2 *>(&Pb[c * 64 + 4 * ty + 2]) = make_double2(a[2][c], a[3][c]);
+            }
+        }
+        TACC(42);
+        __syncthreads();
+        TACC(43);
+        if (valid && tx > jb)
+        {
+            // pr[k][r] = L[4*tx+r][4*jb+k]   (row-block tx of the panel; for lower threads tx is the
+            // column-block, for mirror threads tx is the inverse row-block - same panel rows)
+            double pt[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const double2 v0 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * tx]);
+                const double2 v1 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * tx + 2]);
+                pt[k][0] = v0.x; pt[k][1] = v0.y; pt[k][2] = v1.x; pt[k][3] = v1.y;
+            }
+            if (lower)
+            {   // A_(ty,tx) -= L_(ty,jb) L_(tx,jb)'
+                double pr[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const double2 v0 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * ty]);
+                    const double2 v1 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * ty + 2]);
+                    pr[k][0] = v0.x; pr[k][1] = v0.y; pr[k][2] = v1.x; pr[k][3] = v1.y;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            a[r][c] -= pr[k][r] * pt[k][c];
+            }
+            else if (ty <= jb)
+            {   // mirror: R_(tx,ty) -= L_(tx,jb) X_(jb,ty);  X_(jb,jb) = W
+                double xv[4][4];
+                if (ty == jb)
+                {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        xv[q >> 2][q & 3] = D[q];
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const double2 v0 = *reinterpret_cast<const double2 *>(&Xb[k * 64 + 4 * ty]);
+                        const double2 v1 = *reinterpret_cast<const double2 *>(&Xb[k * 64 + 4 * ty + 2]);
+                        xv[k][0] = v0.x; xv[k][1] = v0.y; xv[k][2] = v1.x; xv[k][3] = v1.y;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            a[r][c] -= pt[k][r] * xv[k][c];
+            }
+        }
+        TACC(44);
+        // the diagonal thread's inverse block and the finished inverse row go to Li after the loop
+        if (ty == jb && tx == jb)
+        {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    Li[4 * jb + r][4 * jb + c] = D[4 * r + c];
         }
     }
+    TT(2);
+#ifdef SB200_TILE_TIMING
+    if (tid == SB200_TILE_TIMING) for (int q = 0; q < 5; ++q) g_tile_timing[40 + q] = tacc__[q];
+#endif
+    // write back: lower threads -> L blocks; mirror threads -> inverse block (tx, ty) and zero the
+    // upper blocks (ty, tx) of both matrices
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+        {
+            if (lower)
+                Ls[4 * ty + r][4 * tx + c] = a[r][c];
+            else if (valid)
+            {
+                Ls[4 * ty + r][4 * tx + c] = 0.0;
+                Li[4 * ty + r][4 * tx + c] = 0.0;
+                Li[4 * tx + r][4 * ty + c] = a[r][c];
+            }
+        }
     __syncthreads();
-    return fail;
+    TT(3);
+    TT(4);
+    return *sflag;
 }
 
 __device__ __forceinline__ void report_fail(int *info, int fail, int base)
@@ -63,75 +308,79 @@ __device__ __forceinline__ void report_fail(int *info, int fail, int base)
         atomicCAS(info, 0, base + fail);
 }
 
-// first diagonal tile
-__global__ void __launch_bounds__(128) k_potrf_first(double *__restrict__ A, int ld, int *info)
+// write L (lower) back to the matrix and L^-1 to the inverse store
+__device__ __forceinline__ void store_factored_tile(const unsigned char *smem, double *__restrict__ Atile, int ld,
+                                                    double *__restrict__ linv_k, int tid)
 {
-    __shared__ double Ls[TB][LP];
+    const double(*Ls)[LP] = reinterpret_cast<const double(*)[LP]>(smem + SM_LS);
+    const double(*Li)[LP] = reinterpret_cast<const double(*)[LP]>(smem + SM_LI);
+    for (int idx = tid; idx < TB * TB; idx += NT_TILE)
+    {
+        const int r = idx >> 6, c = idx & 63;
+        if (c <= r) Atile[(size_t)r * ld + c] = Ls[r][c];
+        linv_k[idx] = Li[r][c];
+    }
+}
+
+// first diagonal tile
+__global__ void __launch_bounds__(NT_TILE) k_potrf_first(double *__restrict__ A, int ld, double *__restrict__ linv,
+                                                         int *info)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LS);
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < TB * TB; idx += 128)
+    for (int idx = tid; idx < TB * TB; idx += NT_TILE)
     {
         const int r = idx >> 6, c = idx & 63;
         Ls[r][c] = A[(size_t)r * ld + c];
     }
-    const int fail = potrf_tile64(Ls, tid);
-    for (int idx = tid; idx < TB * TB; idx += 128)
-    {
-        const int r = idx >> 6, c = idx & 63;
-        if (c <= r) A[(size_t)r * ld + c] = Ls[r][c];
-    }
+    __syncthreads();
+    const int fail = potrf_inv_tile64(dyn_smem, tid);
+    store_factored_tile(dyn_smem, A, ld, linv, tid);
     report_fail(info, fail, 0);
 }
 
-// X = A_ik L_kk^-T for every tile row i > k: one CTA per tile, one thread per row
-__global__ void __launch_bounds__(64) k_trsm_panel(double *__restrict__ A, int ld, int k)
-{
-    __shared__ double Ls[TB][LP];
-    __shared__ double invd[TB];
-    const int tid = threadIdx.x;
-    const size_t k0 = (size_t)k * TB;
-    const size_t row = ((size_t)k + 1 + blockIdx.x) * TB + tid;
-    for (int idx = tid; idx < TB * TB; idx += 64)
-    {
-        const int r = idx >> 6, c = idx & 63;
-        Ls[r][c] = A[(k0 + r) * ld + k0 + c];
-    }
-    double a[TB];
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(A + row * ld + k0);
-#pragma unroll
-        for (int c = 0; c < TB / 2; ++c)
-        {
-            const double2 v = src[c];
-            a[2 * c] = v.x;
-            a[2 * c + 1] = v.y;
-        }
-    }
-    __syncthreads();
-    invd[tid] = 1.0 / Ls[tid][tid];
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < TB; ++c)
-    {
-        const double xc = a[c] * invd[c];
-        a[c] = xc;
-#pragma unroll
-        for (int c2 = c + 1; c2 < TB; ++c2)
-            a[c2] -= xc * Ls[c2][c];
-    }
-    {
-        double2 *dst = reinterpret_cast<double2 *>(A + row * ld + k0);
-#pragma unroll
-        for (int c = 0; c < TB / 2; ++c)
-            dst[c] = make_double2(a[2 * c], a[2 * c + 1]);
-    }
-}
-
-// trailing update with look-ahead potrf of the next diagonal tile
-__global__ void __launch_bounds__(128) k_update(double *__restrict__ A, int ld, int k, int T, int *info)
+// X = A_ik L_kk^-T = A_ik (L_kk^-1)' for every tile row i > k: one CTA per 64x64 tile, DMMA GEMM
+__global__ void __launch_bounds__(128) k_trsm_panel(double *__restrict__ A, int ld, int k,
+                                                    const double *__restrict__ linv)
 {
     __shared__ __align__(16) double smem[2 * TB * KP];
     double(*As)[KP] = reinterpret_cast<double(*)[KP]>(smem);
     double(*Bs)[KP] = reinterpret_cast<double(*)[KP]>(smem + TB * KP);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w >> 1, wn = w & 1, g = lane >> 2, tg = lane & 3;
+    const size_t r0 = ((size_t)k + 1 + blockIdx.x) * TB, k0 = (size_t)k * TB;
+    const double *Lk = linv + (size_t)k * TB * TB;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int kc = 0; kc < TB; kc += KC)
+    {
+        __syncthreads();
+        load_tile_64xKC(As, A + r0 * ld + k0 + kc, ld, tid, 128, nullptr);
+        load_tile_64xKC(Bs, Lk + kc, TB, tid, 128, nullptr);
+        __syncthreads();
+        warp_mma_32x32(As, Bs, wm, wn, lane, 1.0, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2 *>(A + (r0 + wm * 32 + i * 8 + g) * ld + k0 + wn * 32 + j * 8 + tg * 2) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// trailing update with look-ahead factorisation (+ inverse) of the next diagonal tile
+__global__ void __launch_bounds__(NT_TILE) k_update(double *__restrict__ A, int ld, int k, int T,
+                                                    double *__restrict__ linv, int *info)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double(*As)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem);
+    double(*Bs)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem + TB * KP * 8);
 
     // decode (ti, tj), tj <= ti, both relative to k+1
     const int p = blockIdx.x;
@@ -143,94 +392,66 @@ __global__ void __launch_bounds__(128) k_update(double *__restrict__ A, int ld, 
     if (ti >= T) return;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wm = w >> 1, wn = w & 1;
+    const int row0 = (w >> 2) * 32, col0 = (w & 3) * 16;     // 8 warps: 2 x 4, warp tile 32 x 16
     const int g = lane >> 2, tg = lane & 3;
     const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB, k0 = (size_t)k * TB;
 
-    double acc[4][4][2];
+    const bool mma_warp = w < 8;           // warp 8 only takes part in the tile factorisation
+    double acc[4][2][2];
+    if (mma_warp)
+    {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-            const double2 v = *reinterpret_cast<const double2 *>(
-                A + (r0 + wm * 32 + i * 8 + g) * ld + c0 + wn * 32 + j * 8 + tg * 2);
-            acc[i][j][0] = v.x;
-            acc[i][j][1] = v.y;
-        }
+            for (int j = 0; j < 2; ++j)
+            {
+                const double2 v = *reinterpret_cast<const double2 *>(
+                    A + (r0 + row0 + i * 8 + g) * ld + c0 + col0 + j * 8 + tg * 2);
+                acc[i][j][0] = v.x;
+                acc[i][j][1] = v.y;
+            }
+    }
 #pragma unroll
     for (int kc = 0; kc < TB; kc += KC)
     {
         __syncthreads();
-        load_tile_64xKC(As, A + r0 * ld + k0 + kc, ld, tid, 128, nullptr);
-        load_tile_64xKC(Bs, A + c0 * ld + k0 + kc, ld, tid, 128, nullptr);
+        load_tile_64xKC(As, A + r0 * ld + k0 + kc, ld, tid, NT_TILE, nullptr);
+        load_tile_64xKC(Bs, A + c0 * ld + k0 + kc, ld, tid, NT_TILE, nullptr);
         __syncthreads();
-        warp_mma_32x32(As, Bs, wm, wn, lane, -1.0, acc);
+        if (mma_warp) warp_mma<4, 2>(As, Bs, row0, col0, lane, -1.0, acc);
     }
 
     if (ri == 0 && rj == 0)
-    {   // next diagonal tile: factor it before it goes back to memory
+    {   // next diagonal tile: factor + invert it before it goes back to memory
         __syncthreads();
-        double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem);   // 64*65 <= 2*64*36
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-            {
-                const int r = wm * 32 + i * 8 + g, c = wn * 32 + j * 8 + tg * 2;
-                Ls[r][c] = acc[i][j][0];
-                Ls[r][c + 1] = acc[i][j][1];
-            }
-        const int fail = potrf_tile64(Ls, tid);
-        for (int idx = tid; idx < TB * TB; idx += 128)
+        double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LS);
+        if (mma_warp)
         {
-            const int r = idx >> 6, c = idx & 63;
-            if (c <= r) A[(r0 + r) * ld + c0 + c] = Ls[r][c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                {
+                    const int r = row0 + i * 8 + g, c = col0 + j * 8 + tg * 2;
+                    Ls[r][c] = acc[i][j][0];
+                    Ls[r][c + 1] = acc[i][j][1];
+                }
         }
+        __syncthreads();
+        const int fail = potrf_inv_tile64(dyn_smem, tid);
+        store_factored_tile(dyn_smem, A + r0 * ld + c0, ld, linv + (size_t)ti * TB * TB, tid);
         report_fail(info, fail, (int)r0);
         return;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<double2 *>(A + (r0 + wm * 32 + i * 8 + g) * ld + c0 + wn * 32 + j * 8 +
-                                         tg * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
-}
-
-// inverse of every 64x64 diagonal block of L (lower), one CTA per block, one thread per column.
-// Column c of the inverse is built in registers-by-row order into Z (thread c owns column c of Z).
-__global__ void __launch_bounds__(64) k_invert_diag(const double *__restrict__ L, int ld,
-                                                    double *__restrict__ linv)
-{
-    extern __shared__ double sm_inv[];
-    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(sm_inv);
-    double(*Z)[LP] = reinterpret_cast<double(*)[LP]>(sm_inv + TB * LP);
-    const int tid = threadIdx.x;
-    const size_t k0 = (size_t)blockIdx.x * TB;
-    for (int idx = tid; idx < TB * TB; idx += 64)
+    if (mma_warp)
     {
-        const int r = idx >> 6, c = idx & 63;
-        Ls[r][c] = L[(k0 + r) * ld + k0 + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2 *>(A + (r0 + row0 + i * 8 + g) * ld + c0 + col0 + j * 8 + tg * 2) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
     }
-    __syncthreads();
-    const int c = tid;
-    for (int i = 0; i < TB; ++i)
-    {
-        double sum = 0.0;
-        if (i >= c)
-        {
-            sum = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k)
-                sum -= Ls[i][k] * Z[k][c];
-            sum /= Ls[i][i];
-        }
-        Z[i][c] = sum;
-    }
-    __syncthreads();
-    double *out = linv + (size_t)blockIdx.x * TB * TB;
-    for (int idx = tid; idx < TB * TB; idx += 64)
-        out[idx] = Z[idx >> 6][idx & 63];
 }
 
 __global__ void k_pad_identity(int n, double *__restrict__ A, int ld)
@@ -477,8 +698,8 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad)
     SB200_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_trsv_bwd, 256, 0));
     const int occ = occ_f < occ_b ? occ_f : occ_b;
     W.max_coop_grid = sms * (occ < 1 ? 1 : occ);
-    SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(2 * TB * LP * sizeof(double))));
+    SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_potrf_first, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     return SB200_OK;
 }
 void chol_work_free(CholWork &W)
@@ -492,17 +713,15 @@ void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t
 {
     (void)n;
     const int T = ld / TB;
-    k_potrf_first<<<1, 128, 0, st>>>(a, ld, info);
+    k_potrf_first<<<1, NT_TILE, SM_TOTAL, st>>>(a, ld, W.linv, info);
     ++g_launch_count;
     for (int k = 0; k + 1 < T; ++k)
     {
         const int rem = T - 1 - k;
-        k_trsm_panel<<<rem, 64, 0, st>>>(a, ld, k);
-        k_update<<<rem * (rem + 1) / 2, 128, 0, st>>>(a, ld, k, T, info);
+        k_trsm_panel<<<rem, 128, 0, st>>>(a, ld, k, W.linv);
+        k_update<<<rem * (rem + 1) / 2, NT_TILE, SM_TOTAL, st>>>(a, ld, k, T, W.linv, info);
         g_launch_count += 2;
     }
-    k_invert_diag<<<T, 64, 2 * TB * LP * sizeof(double), st>>>(a, ld, W.linv);
-    ++g_launch_count;
 }
 
 static cudaError_t launch_coop(const void *fn, int grid, int block, void **args, cudaStream_t st)

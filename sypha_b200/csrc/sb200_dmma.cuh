@@ -21,27 +21,33 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
-// acc(32x32 warp tile) += sign * As(rows wm*32.., KC) * Bs(rows wn*32.., KC)'
-__device__ __forceinline__ void warp_mma_32x32(const double (*As)[KP], const double (*Bs)[KP], int wm,
-                                               int wn, int lane, double sign, double acc[4][4][2])
+// acc((MI*8) x (NJ*8) warp tile at row0/col0) += sign * As(rows row0.., KC) * Bs(rows col0.., KC)'
+template <int MI, int NJ>
+__device__ __forceinline__ void warp_mma(const double (*As)[KP], const double (*Bs)[KP], int row0, int col0,
+                                         int lane, double sign, double acc[MI][NJ][2])
 {
     const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
     for (int kk = 0; kk < KC; kk += 4)
     {
-        double a[4], b[4];
+        double a[MI], b[NJ];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            a[i] = sign * As[wm * 32 + i * 8 + g][kk + tg];
-            b[i] = Bs[wn * 32 + i * 8 + g][kk + tg];
-        }
+        for (int i = 0; i < MI; ++i)
+            a[i] = sign * As[row0 + i * 8 + g][kk + tg];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < NJ; ++j)
+            b[j] = Bs[col0 + j * 8 + g][kk + tg];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
                 dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+}
+__device__ __forceinline__ void warp_mma_32x32(const double (*As)[KP], const double (*Bs)[KP], int wm,
+                                               int wn, int lane, double sign, double acc[4][4][2])
+{
+    warp_mma<4, 4>(As, Bs, wm * 32, wn * 32, lane, sign, acc);
 }
 
 // cooperative load of a 64 x KC block (row-major, leading dim ld) into padded shared memory,

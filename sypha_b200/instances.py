@@ -1,0 +1,77 @@
+"""Set-covering LP instances for the host side of the path: the OR-Library text format of the
+reference's reader (/root/reference/src/model_reader.cpp:90-174: ``m n``, n costs, then per row
+``k idx_1..idx_k`` 1-based; standard form A = [A0 | -I], b = 1, c = [c0; 0]) and the synthetic
+generator used by bench.py (SURVEY.md Appendix C shape: k = round(n*density) random columns per row,
+no empty columns, integer costs 1..100)."""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+
+@dataclasses.dataclass
+class ScpModel:
+    m: int
+    n: int
+    n_orig: int
+    offs: np.ndarray     # int32 [m+1]
+    inds: np.ndarray     # int32 [nnz]
+    vals: np.ndarray     # float64 [nnz]
+    c: np.ndarray        # float64 [n]
+    b: np.ndarray        # float64 [m]
+    name: str = ""
+
+    @property
+    def nnz(self):
+        return int(self.inds.shape[0])
+
+
+def _standard_form(m, n, row_cols, row_cnt, costs, name):
+    """row_cols: concatenated 0-based column ids, row_cnt[m]: entries per row."""
+    cnt = np.asarray(row_cnt, dtype=np.int64)
+    offs = np.zeros(m + 1, dtype=np.int64)
+    offs[1:] = np.cumsum(cnt + 1)
+    inds = np.empty(offs[-1], dtype=np.int32)
+    vals = np.ones(offs[-1], dtype=np.float64)
+    dst = np.arange(len(row_cols), dtype=np.int64) + np.repeat(np.arange(m, dtype=np.int64), cnt)
+    inds[dst] = row_cols
+    inds[offs[1:] - 1] = n + np.arange(m, dtype=np.int32)      # surplus column, last in its row
+    vals[offs[1:] - 1] = -1.0
+    c = np.concatenate([np.asarray(costs, dtype=np.float64), np.zeros(m)])
+    return ScpModel(m, n + m, n, offs.astype(np.int32), inds, vals, c, np.ones(m), name)
+
+
+def read_scp(path) -> ScpModel:
+    tok = np.array(open(path).read().split(), dtype=np.int64)
+    m, n = int(tok[0]), int(tok[1])
+    costs = tok[2:2 + n].astype(np.float64)
+    pos, cols, cnt = 2 + n, [], []
+    for _ in range(m):
+        k = int(tok[pos])
+        cols.append(tok[pos + 1:pos + 1 + k] - 1)
+        cnt.append(k)
+        pos += 1 + k
+    return _standard_form(m, n, np.concatenate(cols), cnt, costs, str(path))
+
+
+def gen_scp(m, n, density, seed) -> ScpModel:
+    r = np.random.default_rng(seed)
+    k = max(1, int(round(n * density)))
+    cols = r.integers(0, n, size=(m, k), dtype=np.int64)
+    cols.sort(axis=1)
+    keep = np.ones((m, k), dtype=bool)
+    keep[:, 1:] = cols[:, 1:] != cols[:, :-1]
+    rows = np.repeat(np.arange(m, dtype=np.int64), k).reshape(m, k)[keep]
+    cols = cols[keep]
+    present = np.zeros(n, dtype=bool)
+    present[cols] = True
+    empty = np.nonzero(~present)[0]
+    if len(empty):
+        rows = np.concatenate([rows, r.integers(0, m, len(empty))])
+        cols = np.concatenate([cols, empty])
+        order = np.lexsort((cols, rows))
+        rows, cols = rows[order], cols[order]
+    cnt = np.bincount(rows, minlength=m)
+    costs = r.integers(1, 101, n).astype(np.float64)
+    return _standard_form(m, n, cols, cnt, costs, f"gen_scp({m},{n},{density},{seed})")

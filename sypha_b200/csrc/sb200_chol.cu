@@ -20,287 +20,9 @@
 #include "sb200_kernels.cuh"
 #include "sb200_chol.cuh"
 #include "sb200_dmma.cuh"
+#include "sb200_tile64.cuh"
 
 namespace sb200 {
-
-static constexpr int LP = TB + 1;    // padded stride of the potrf tile
-
-// dynamic shared-memory layout of the kernels that factor a diagonal tile (bytes)
-static constexpr int SM_LS = 0;                                   // L tile (aliases the MMA staging buffers)
-static constexpr int SM_MMA_BYTES = 2 * TB * KP * 8;              // 36864
-static constexpr int SM_LI = SM_MMA_BYTES;                        // inverse tile
-static constexpr int SM_T = SM_LI + TB * LP * 8;                  // scratch of the inverse (<= 1024 doubles)
-static constexpr int SM_P = SM_T + 1024 * 8;                      // double-buffered 64x4 panel
-static constexpr int SM_D = SM_P + 2 * 256 * 8;                   // 4x4 inverse of the current diagonal block
-static constexpr int SM_FLAG = SM_D + 32 * 8;                     // (D is double buffered)
-static constexpr int SM_TOTAL = SM_FLAG + 16;
-static constexpr int NT_TILE = 288;                               // threads of the tile factorisation
-
-// ---------------------------------------------------------------------------------------------
-// Cholesky + inverse of a 64x64 tile in shared memory, 288 threads (see the thread -> block map).
-//   Threads with ty >= tx keep the 4x4 block (rows 4ty..,
-//   cols 4tx..) of the lower triangle of A in registers.  Threads with ty < tx ("mirror" threads,
-//   idle in a plain Cholesky) keep block (row-block tx, col-block ty) of the running inverse.
-//   16 block-column steps, 2 barriers each:
-//     diag thread jb : factor its 4x4 block (4 dependent rsqrt), W = its 4x4 inverse -> smem
-//     -- barrier --
-//     panel threads (tx == jb, ty > jb)      : L_ij = A_ij W'            -> panel buffer (transposed)
-//     mirror threads of inverse row-block jb : X_j,: = W R_j,:           -> inverse-row buffer
-//     -- barrier --
-//     trailing threads (tx > jb)             : A_ik -= L_ij L_kj'
-//     mirror threads of row-blocks i > jb    : R_i,: -= L_ij X_j,:
-//   (right-looking forward substitution on the identity, R starts as I).
-// On exit Ls = L (upper zeroed), Li = L^-1 (upper zero).  Returns 0 or the 1-based local index of
-// the first non-positive pivot.
-// ---------------------------------------------------------------------------------------------
-#ifdef SB200_TILE_TIMING
-__device__ long long g_tile_timing[64];
-#define TT(i) do { if (tid == 0) g_tile_timing[i] = clock64(); } while (0)
-__device__ long long g_tile_trace[16][9][8];
-#define TACC(i) do { const long long now__ = clock64(); tacc__[i - 40] += now__ - tprev__; tprev__ = now__; \
-                     if ((tid & 31) == 0) g_tile_trace[jb][tid >> 5][i - 40] = now__; } while (0)
-#else
-#define TT(i) do { } while (0)
-#define TACC(i) do { } while (0)
-#endif
-
-__device__ int potrf_inv_tile64(unsigned char *smem, int tid)
-{
-    TT(0);
-    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
-    double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LI);
-    double *P = reinterpret_cast<double *>(smem + SM_P);     // [2][4][64]  panel, transposed: P[k][row]
-    double *XR = reinterpret_cast<double *>(smem + SM_T);    // [2][4][64]  inverse rows:      XR[r][col]
-    double *D2 = reinterpret_cast<double *>(smem + SM_D);   // [2][16]
-    int *sflag = reinterpret_cast<int *>(smem + SM_FLAG);
-
-    // Thread -> block map (288 threads): warp 0 lanes 0..15 own the diagonal blocks and nothing else, so
-    // the serial chain (update diag block -> 4 dependent rsqrt) never waits behind off-diagonal work
-    // of its own warp; threads 32..151 own the 120 strictly-lower blocks, 152..271 the 120 mirror
-    // (inverse) blocks; the rest idle.
-    int ty = -1, tx = 100;                 // idle: fails every role test below
-    if (tid < 16)
-        ty = tx = tid;
-    else if (tid >= 32 && tid < 272)
-    {
-        const int q = (tid - 32) % 120;
-        int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
-        while (i * (i - 1) / 2 > q) --i;
-        while ((i + 1) * i / 2 <= q) ++i;
-        const int j = q - i * (i - 1) / 2;          // i > j
-        if (tid < 152) { ty = i; tx = j; }          // lower block (i, j)
-        else           { ty = j; tx = i; }          // mirror of (i, j)
-    }
-    const bool valid = ty >= 0;
-    const bool lower = valid && ty >= tx;
-    // lower threads: a = A block (ty, tx).  mirror threads: a = inverse/residual block (tx, ty).
-    double a[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            a[r][c] = lower ? Ls[4 * ty + r][4 * tx + c] : 0.0;
-    if (tid == 0) *sflag = 0;
-    TT(1);
-#ifdef SB200_TILE_TIMING
-    long long tprev__ = clock64();
-    long long tacc__[5] = {0, 0, 0, 0, 0};
-#endif
-
-    for (int jb = 0; jb < 16; ++jb)
-    {
-        double *Pb = P + (jb & 1) * 256;
-        double *Xb = XR + (jb & 1) * 256;
-        double *D = D2 + (jb & 1) * 16;
-        if (ty == jb && tx == jb)
-        {
-#ifdef SB200_TILE_TIMING
-            const long long tq0 = clock64();
-#endif
-            double inv[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-            {
-                const double d = a[c][c];
-                if (!(d > 0.0)) atomicCAS(sflag, 0, 4 * jb + c + 1);
-                inv[c] = rsqrt(d);
-                a[c][c] = d * inv[c];
-#pragma unroll
-                for (int r = c + 1; r < 4; ++r)
-                    a[r][c] *= inv[c];
-#pragma unroll
-                for (int c2 = c + 1; c2 < 4; ++c2)
-#pragma unroll
-                    for (int r = c2; r < 4; ++r)
-                        a[r][c2] -= a[r][c] * a[c2][c];
-            }
-            a[0][1] = a[0][2] = a[0][3] = a[1][2] = a[1][3] = a[2][3] = 0.0;
-            // W = inverse of the 4x4 lower block
-            const double w00 = inv[0], w11 = inv[1], w22 = inv[2], w33 = inv[3];
-            const double w10 = -a[1][0] * w00 * w11;
-            const double w21 = -a[2][1] * w11 * w22;
-            const double w32 = -a[3][2] * w22 * w33;
-            const double w20 = -(a[2][0] * w00 + a[2][1] * w10) * w22;
-            const double w31 = -(a[3][1] * w11 + a[3][2] * w21) * w33;
-            const double w30 = -(a[3][0] * w00 + a[3][1] * w10 + a[3][2] * w20) * w33;
-            D[0] = w00; D[1] = 0.0; D[2] = 0.0; D[3] = 0.0;
-            D[4] = w10; D[5] = w11; D[6] = 0.0; D[7] = 0.0;
-            D[8] = w20; D[9] = w21; D[10] = w22; D[11] = 0.0;
-            D[12] = w30; D[13] = w31; D[14] = w32; D[15] = w33;
-#ifdef SB200_TILE_TIMING
-            g_tile_timing[16 + jb] = clock64() - tq0;
-#endif
-        }
-        TACC(40);
-        __syncthreads();
-        TACC(41);
-        if (tx == jb && ty != jb)
-        {
-            double w[16];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-            {
-                const double2 v = *reinterpret_cast<const double2 *>(&D[2 * q]);
-                w[2 * q] = v.x;
-                w[2 * q + 1] = v.y;
-            }
-            if (ty > jb)
-            {   // panel: L_ij = A_ij W'
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                {
-                    const double a0 = a[r][0], a1 = a[r][1], a2 = a[r][2], a3 = a[r][3];
-                    a[r][0] = a0 * w[0];
-                    a[r][1] = a0 * w[4] + a1 * w[5];
-                    a[r][2] = a0 * w[8] + a1 * w[9] + a2 * w[10];
-                    a[r][3] = a0 * w[12] + a1 * w[13] + a2 * w[14] + a3 * w[15];
-                }
-            }
-            else
-            {   // mirror, inverse row-block jb, column-block ty < jb: X = W R (R complete through jb-1)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                {
-                    const double r0 = a[0][c], r1 = a[1][c], r2 = a[2][c], r3 = a[3][c];
-                    a[0][c] = w[0] * r0;
-                    a[1][c] = w[4] * r0 + w[5] * r1;
-                    a[2][c] = w[8] * r0 + w[9] * r1 + w[10] * r2;
-                    a[3][c] = w[12] * r0 + w[13] * r1 + w[14] * r2 + w[15] * r3;
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                {
-                    *reinterpret_cast<double2 *>(&Xb[r * 64 + 4 * ty]) = make_double2(a[r][0], a[r][1]);
-                    *reinterpret_cast<double2 *>(&Xb[r * 64 + 4 * ty + 2]) = make_double2(a[r][2], a[r][3]);
-                }
-            }
-        }
-        if (tx == jb && ty >= jb)
-        {   // column block jb of L, transposed: Pb[c][row]
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-            {
-                *reinterpret_cast<double2 *>(&Pb[c * 64 + 4 * ty]) = make_double2(a[0][c], a[1][c]);
-                *reinterpret_cast<double2 *>(&Pb[c * 64 + 4 * ty + 2]) = make_double2(a[2][c], a[3][c]);
-            }
-        }
-        TACC(42);
-        __syncthreads();
-        TACC(43);
-        if (valid && tx > jb)
-        {
-            // pr[k][r] = L[4*tx+r][4*jb+k]   (row-block tx of the panel; for lower threads tx is the
-            // column-block, for mirror threads tx is the inverse row-block - same panel rows)
-            double pt[4][4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                const double2 v0 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * tx]);
-                const double2 v1 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * tx + 2]);
-                pt[k][0] = v0.x; pt[k][1] = v0.y; pt[k][2] = v1.x; pt[k][3] = v1.y;
-            }
-            if (lower)
-            {   // A_(ty,tx) -= L_(ty,jb) L_(tx,jb)'
-                double pr[4][4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                {
-                    const double2 v0 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * ty]);
-                    const double2 v1 = *reinterpret_cast<const double2 *>(&Pb[k * 64 + 4 * ty + 2]);
-                    pr[k][0] = v0.x; pr[k][1] = v0.y; pr[k][2] = v1.x; pr[k][3] = v1.y;
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            a[r][c] -= pr[k][r] * pt[k][c];
-            }
-            else if (ty <= jb)
-            {   // mirror: R_(tx,ty) -= L_(tx,jb) X_(jb,ty);  X_(jb,jb) = W
-                double xv[4][4];
-                if (ty == jb)
-                {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                        xv[q >> 2][q & 3] = D[q];
-                }
-                else
-                {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                    {
-                        const double2 v0 = *reinterpret_cast<const double2 *>(&Xb[k * 64 + 4 * ty]);
-                        const double2 v1 = *reinterpret_cast<const double2 *>(&Xb[k * 64 + 4 * ty + 2]);
-                        xv[k][0] = v0.x; xv[k][1] = v0.y; xv[k][2] = v1.x; xv[k][3] = v1.y;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            a[r][c] -= pt[k][r] * xv[k][c];
-            }
-        }
-        TACC(44);
-        // the diagonal thread's inverse block and the finished inverse row go to Li after the loop
-        if (ty == jb && tx == jb)
-        {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    Li[4 * jb + r][4 * jb + c] = D[4 * r + c];
-        }
-    }
-    TT(2);
-#ifdef SB200_TILE_TIMING
-    if (tid == SB200_TILE_TIMING) for (int q = 0; q < 5; ++q) g_tile_timing[40 + q] = tacc__[q];
-#endif
-    // write back: lower threads -> L blocks; mirror threads -> inverse block (tx, ty) and zero the
-    // upper blocks (ty, tx) of both matrices
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-        {
-            if (lower)
-                Ls[4 * ty + r][4 * tx + c] = a[r][c];
-            else if (valid)
-            {
-                Ls[4 * ty + r][4 * tx + c] = 0.0;
-                Li[4 * ty + r][4 * tx + c] = 0.0;
-                Li[4 * tx + r][4 * ty + c] = a[r][c];
-            }
-        }
-    __syncthreads();
-    TT(3);
-    TT(4);
-    return *sflag;
-}
 
 __device__ __forceinline__ void report_fail(int *info, int fail, int base)
 {

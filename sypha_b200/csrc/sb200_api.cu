@@ -317,7 +317,7 @@ int ensure_iter_graph(sb200_ws *ws)
 }
 
 // ---- solve state machine ------------------------------------------------------------------------
-int solve_begin(sb200_ws *ws, const sb200_params *p)
+int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
 {
     if (!ws->loaded) return fail(ws, SB200_ERR_INVALID, "sb200_solve: no model loaded");
     WS_TRY(cudaSetDevice(ws->device));
@@ -363,6 +363,12 @@ int solve_begin(sb200_ws *ws, const sb200_params *p)
     launch_spmv_csc(At, CSC_START_S, V.y, nullptr, nullptr, 0, 0, &V, st);   // s~ = c - A' y~
     launch_start_shift1(V, st);
     launch_start_shift2(V, st);
+    if (res)
+    {   // node.hX / hY / hS = starting point (sypha_solver.cpp:72-78)
+        if (res->x0_host) WS_TRY(cudaMemcpyAsync(res->x0_host, V.x, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
+        if (res->y0_host) WS_TRY(cudaMemcpyAsync(res->y0_host, V.y, sizeof(double) * ws->m, cudaMemcpyDeviceToHost, st));
+        if (res->s0_host) WS_TRY(cudaMemcpyAsync(res->s0_host, V.s, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
+    }
     WS_TRY(cudaEventRecord(ws->ev[1], st));
 
     // ---- initial residuals and mu (sypha_solver.cpp:375-459) ------------------------------------
@@ -659,7 +665,7 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
 int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result)
 {
     if (!ws || !params || !result) return SB200_ERR_INVALID;
-    int rc = solve_begin(ws, params);
+    int rc = solve_begin(ws, params, result);
     if (rc) return rc;
     int finished = 0;
     while (!finished)
@@ -685,7 +691,7 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     int rc, remaining = 0;
     for (int i = 0; i < k; ++i)
     {
-        if ((rc = solve_begin(wss[i], params))) return rc;
+        if ((rc = solve_begin(wss[i], params, &results[i]))) return rc;
         live[i] = 1;
         ++remaining;
     }

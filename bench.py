@@ -341,6 +341,9 @@ def main():
     ap.add_argument("--cg-tol", type=float, default=1e-8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly ONE JSON line: libraries (NCCL banner, ...) are diverted to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -351,8 +354,9 @@ def main():
         if args.warmup < 3:
             args.warmup = 3
         out = run_ours(args, rank, world, local_rank)
+    sys.stdout.flush()
     if out is not None:
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -44,6 +44,9 @@ int main()
         long long t[64];
         cudaMemcpyFromSymbol(t, g_tile_timing, sizeof t);
         printf("rep %d: kernel %.2f us; factor %lld cycles, inverse %lld cycles\n", rep, ms * 1000, t[1] - t[0], t[2] - t[1]);
+        for (int kb = 0; kb < 4; kb++)
+            printf("   panel %d: diag16 %lld  rows-below %lld  trailing %lld\n", kb, t[9 + 4 * kb] - t[8 + 4 * kb],
+                   t[10 + 4 * kb] - t[9 + 4 * kb], (kb < 3 ? t[12 + 4 * kb] : t[1]) - t[10 + 4 * kb]);
     }
     std::vector<double> L(64 * 64), Li(64 * 64);
     cudaMemcpy(L.data(), dA, 64 * 64 * 8, cudaMemcpyDeviceToHost);

@@ -440,11 +440,11 @@ int solve_finish(sb200_ws *ws, sb200_result *r)
 
     int reason = sc.reason;
     int trsv_err = 0;
-    if (ws->chol.ctl) WS_TRY(cudaMemcpy(&trsv_err, ws->chol.ctl + 4, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ws->chol.ctl) WS_TRY(cudaMemcpy(&trsv_err, ws->chol.ctl + 8, sizeof(int), cudaMemcpyDeviceToHost));
     if (trsv_err)
     {
-        cudaMemset(ws->chol.ctl + 4, 0, sizeof(int));
-        return fail(ws, SB200_ERR_CUDA, "triangular-solve data-flow wait timed out (CTAs not co-resident?)");
+        cudaMemset(ws->chol.ctl + 8, 0, sizeof(int));
+        return fail(ws, SB200_ERR_CUDA, "data-flow wait timed out in the factorisation / triangular solves");
     }
     bool numerical = sc.numerical != 0 || sc.chol_info != 0;
     // sypha_solver.cpp:775-778: anything but a failure / gap stall is re-labelled from mu

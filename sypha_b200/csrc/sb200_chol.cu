@@ -6,21 +6,26 @@
 //
 // Layout: row-major, lower triangle, leading dimension ld = m rounded up to 64, identity pad.
 //
-// Factorisation (right-looking, 64-wide panels, 2 launches per panel):
+// Default factorisation: k_potrf_df, ONE data-flow launch (left-looking 64x64 tile tasks, see below).
+// The earlier right-looking panel version is kept behind SB200_POTRF=panel for A/B measurements
+// (right-looking, 64-wide panels, 2 launches per panel):
 //   k_trsm_panel : X = A_ik (L_kk^-1)' as a 64x64x64 FP64 tensor-core GEMM against the pre-inverted
 //                  diagonal block
 //   k_update     : A_ij -= L_ik L_jk'  on 64x64 tiles with FP64 tensor-core MMA
 //                  (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4); the CTA that owns the next diagonal
 //                  tile factors AND inverts it in shared memory before writing it back (look-ahead),
 //                  so no separate potrf launch sits on the critical path.
-// Solves (one launch each, data-flow): every 64-row block is owned by one CTA which accumulates
-//   its right-hand side as the blocks it depends on are published through release/acquire flags,
-//   then multiplies by the pre-inverted 64x64 diagonal block.  All CTAs are co-resident
-//   (cooperative launch); spins are bounded and raise an error flag instead of hanging.
+// Solves (k_trsv_df, one launch for forward + backward, data-flow): every 128-row block is a task
+//   which accumulates its right-hand side as the blocks it depends on are published through
+//   release/acquire flags, then multiplies by the pre-inverted 128x128 diagonal block.  Tasks are
+//   claimed in dependency order, so no co-residency is required; spins are bounded and raise an error
+//   flag instead of hanging.
 #include "sb200_kernels.cuh"
 #include "sb200_chol.cuh"
 #include "sb200_dmma.cuh"
 #include "sb200_tile64.cuh"
+
+#include <cstdlib>
 
 namespace sb200 {
 
@@ -196,7 +201,7 @@ void launch_pad_identity(int n, double *a, int ld, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------------
-// data-flow triangular solves
+// device-side synchronisation shared by the data-flow kernels
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
@@ -208,33 +213,99 @@ __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// thread 0 spins (bounded), then the block synchronises
-__device__ __forceinline__ void wait_flag(const int *flag, int epoch, int *err)
+__device__ __forceinline__ int ld_volatile(const int *p)
 {
-    if (threadIdx.x == 0)
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: spin until *flag == epoch.  Bounded: a wait that never completes raises *err (every
+// other wait of the launch then falls through) instead of hanging the device.
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polls with relaxed loads (no L1 invalidation per poll) and fences once on success.
+__device__ __forceinline__ void spin_until(const int *flag, int epoch, int *err)
+{
+    int spins = 0;
+    if (ld_relaxed(flag) == epoch)
     {
-        long long spins = 0;
-        while (ld_acquire(flag) != epoch)
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        return;
+    }
+    while (ld_relaxed(flag) != epoch)
+    {
+        ++spins;
+        if ((spins & 255) == 0)
         {
-            if (++spins > (1ll << 22))
+            if (ld_volatile(err)) break;
+            if (spins > (1 << 21))
             {
                 atomicExch(err, 1);
                 break;
             }
         }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// all threads of the block wrote global data; publish it under `flag`.  The block barrier orders the
+// other threads' writes before thread 0's release store (release is cumulative) - no extra fence.
+__device__ __forceinline__ void publish(int *flag, int epoch, int publisher = 0)
+{
     __syncthreads();
+    if (threadIdx.x == publisher) st_release(flag, epoch);
 }
 
-struct TrsvCtl
+#ifdef SB200_DF_TIMING
+__device__ unsigned long long g_df_time[8192][12];
+__device__ __forceinline__ unsigned long long df_now()
 {
-    int *flags;        // [T]
-    int *epoch;        // device counter: flags carry *epoch+1 when published in this launch
-    unsigned *exits;   // CTAs that finished (last one bumps *epoch)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DFT(task, slot) do { if (threadIdx.x == 0 && (task) < 8192) g_df_time[task][slot] = df_now(); } while (0)
+#else
+#define DFT(task, slot) do { } while (0)
+#endif
+
+// A/B switches measured with scripts/df_timeline.cu on B200 (m = 1024, potrf us; baseline 354):
+//   SB200_V_RSQ (tile64.cuh) branch-free rsqrt on the pivot chain .............. 321
+//   SB200_V_ST   vectorised D1 stores ............................................ 347
+//   SB200_V_LJ   L_jj staged through registers (spills when combined) ............ 349
+//   SB200_V_PUB  publish of tile (j, j-1) deferred past the diagonal update ...... 357
+#ifndef SB200_V_LJ
+#define SB200_V_LJ 0
+#endif
+#ifndef SB200_V_PUB
+#define SB200_V_PUB 0
+#endif
+#ifndef SB200_V_ST
+#define SB200_V_ST 1
+#endif
+
+// control block of one data-flow kernel family: [0] epoch, [1] next task, [2] exit count
+struct DfCtl
+{
+    int *epoch;
+    unsigned *next_task;
+    unsigned *exits;
     int *err;
 };
-
-__device__ __forceinline__ void trsv_epilogue(const TrsvCtl &C)
+// claim the next task (dynamic, in list order: every dependency of a claimed task is owned by a
+// running CTA, so no co-residency requirement and no deadlock)
+__device__ __forceinline__ int claim_task(const DfCtl &C, int *s_task)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) *s_task = (int)atomicAdd(C.next_task, 1u);
+    __syncthreads();
+    return *s_task;
+}
+// last CTA out re-arms the counters and opens the next epoch (=> graph-replayable)
+__device__ __forceinline__ void df_epilogue(const DfCtl &C)
 {
     __syncthreads();
     if (threadIdx.x == 0)
@@ -244,241 +315,770 @@ __device__ __forceinline__ void trsv_epilogue(const TrsvCtl &C)
         if (t == gridDim.x - 1)
         {
             *C.exits = 0u;
+            *C.next_task = 0u;
             __threadfence();
             atomicAdd(C.epoch, 1);
         }
     }
 }
 
-// forward: L y = b, in place.  256 threads: (row = t>>2, q = t&3), q splits the 64 columns.
-__global__ void __launch_bounds__(256)
-k_trsv_fwd(const double *__restrict__ L, int ld, const double *__restrict__ linv, double *b, int T,
-           TrsvCtl C)
+// ---------------------------------------------------------------------------------------------
+// data-flow Cholesky: ONE launch, left-looking per 64x64 tile.
+//
+// Task list (column-major): chain(j), [pair-inverse((j-1)/2) when j is odd], tile(i,j) for i >= j+2.
+// tile(i,j):  acc = A_ij - sum_{k<j} L_ik L_jk'   (waits on the two tiles of column k, in k order);
+//             wait D1(j); X = acc L_jj^-T by block substitution with the 16x16 inverses (each warp owns
+//             8 rows, no block barrier); write L_ij; publish
+// chain(j):   the sub-diagonal tile (j, j-1) AND the diagonal tile (j, j) in one CTA: both accumulate
+//             over k < j-1 while waiting; on D1(j-1) the CTA substitutes (j, j-1), publishes it, applies
+//             it to the diagonal tile straight from shared memory, factors the tile, inverts its four
+//             16x16 diagonal blocks, writes L_jj and those blocks, publishes D1(j); then assembles the
+//             full 64x64 inverse (needed by the solves only) and publishes D2
+// pair-inverse(b): [W0 0; -W1 L10 W0  W1] = inverse of the 128x128 diagonal block - what the
+//             triangular solves multiply by (8 hops at m = 1000 instead of 16).
+// The critical path per 64 columns is  factor -> ONE hop -> substitution -> 64^3 DMMA update (no 64x64
+// inverse, no kernel boundary, no second hand-off on it).
+// ---------------------------------------------------------------------------------------------
+struct PotrfDf
 {
-    __shared__ double rs[TB];
-    const int tid = threadIdx.x, row = tid >> 2, q = tid & 3;
-    const int epoch = *C.epoch + 1;
-    for (int i = blockIdx.x; i < T; i += gridDim.x)
+    double *A;
+    int ld, T;
+    double *linv;        // [T][64][64]
+    double *linv128;     // [(T+1)/2][128][128]
+    const int2 *tasks;   // x = i | type << 16, y = j
+    int ntasks;
+    int *tile_flag;      // [T*T]: tile (i,j) final (diag: D1)
+    int *d2_flag;        // [T]
+    int *pair_flag;      // [(T+1)/2]
+    int *info;
+};
+enum { TASK_TILE = 0, TASK_PAIR = 1, TASK_CHAIN = 2 };
+
+__device__ __forceinline__ void ldcg_tile_chunk(double (*S)[KP], const double *g, size_t ld, int tid)
+{   // 64 x KC block, bypassing L1 (the tile was written by another SM during this launch)
+    for (int idx = tid; idx < TB * (KC / 2); idx += NT_TILE)
     {
-        const size_t grow = (size_t)i * TB + row;
-        // pre-inverted diagonal block row (lower part only matters)
-        double li[16];
-        {
-            const double2 *src = reinterpret_cast<const double2 *>(linv + ((size_t)i * TB + row) * TB + q * 16);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-            {
-                const double2 v = src[j];
-                li[2 * j] = v.x;
-                li[2 * j + 1] = v.y;
-            }
-        }
-        double acc = 0.0;
-        double cur[16];
-        if (i > 0)
-        {
-            const double2 *src = reinterpret_cast<const double2 *>(L + grow * ld + q * 16);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-            {
-                const double2 v = src[j];
-                cur[2 * j] = v.x;
-                cur[2 * j + 1] = v.y;
-            }
-        }
-        for (int k = 0; k < i; ++k)
-        {
-            double nxt[16];
-            if (k + 1 < i)
-            {
-                const double2 *src =
-                    reinterpret_cast<const double2 *>(L + grow * ld + (size_t)(k + 1) * TB + q * 16);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                {
-                    const double2 v = src[j];
-                    nxt[2 * j] = v.x;
-                    nxt[2 * j + 1] = v.y;
-                }
-            }
-            wait_flag(C.flags + k, epoch, C.err);
-            const double *yk = b + (size_t)k * TB + q * 16;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                acc -= cur[j] * __ldcg(yk + j);
-            if (k + 1 < i)
-            {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    cur[j] = nxt[j];
-            }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        __syncthreads();
-        if (q == 0) rs[row] = __ldcg(b + grow) + acc;
-        __syncthreads();
-        double yv = 0.0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            yv += li[j] * rs[q * 16 + j];
-        yv += __shfl_xor_sync(0xffffffffu, yv, 1);
-        yv += __shfl_xor_sync(0xffffffffu, yv, 2);
-        if (q == 0) b[grow] = yv;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release(C.flags + i, epoch);
+        const int r = idx / (KC / 2), c2 = (idx % (KC / 2)) * 2;
+        *reinterpret_cast<double2 *>(&S[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(g + (size_t)r * ld + c2));
     }
-    trsv_epilogue(C);
 }
 
-// backward: L' x = y, in place.  256 threads: (col = t&63, q = t>>6), q splits the 64 rows.
-__global__ void __launch_bounds__(256)
-k_trsv_bwd(const double *__restrict__ L, int ld, const double *__restrict__ linv, double *b, int T,
-           TrsvCtl C)
+// pair-inverse; operands staged in the two big shared-memory regions (stride XP)
+__device__ void pair_inverse_128(unsigned char *smem, const double *__restrict__ Atile10, int ld,
+                                 const double *__restrict__ W0g, const double *__restrict__ W1g,
+                                 double *__restrict__ out, int tid)
 {
-    __shared__ double xs[TB];
-    __shared__ double red[4][TB];
-    const int tid = threadIdx.x, col = tid & 63, q = tid >> 6;
-    const int epoch = *C.epoch + 1;
-    for (int ii = blockIdx.x; ii < T; ii += gridDim.x)
+    double(*S0)[XP] = reinterpret_cast<double(*)[XP]>(smem + SM_LS);
+    double(*S1)[XP] = reinterpret_cast<double(*)[XP]>(smem + SM_LI);
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const bool half = (Atile10 == nullptr);    // odd tile count: the pair is [W0 0; 0 I]
+    for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
     {
-        const int i = T - 1 - ii;
-        // column `col` of Linv_ii' = row-slice of Linv_ii: rows q*16.., column col
-        double li[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            li[j] = linv[((size_t)i * TB + q * 16 + j) * TB + col];
-        double acc = 0.0;
-        double cur[16];
-        if (i < T - 1)
+        const int r = idx >> 5, c2 = (idx & 31) * 2;
+        const double2 w0 = __ldcg(reinterpret_cast<const double2 *>(W0g + r * TB + c2));
+        *reinterpret_cast<double2 *>(&S1[r][c2]) = w0;
+        *reinterpret_cast<double2 *>(out + (size_t)r * 128 + c2) = w0;
+        *reinterpret_cast<double2 *>(out + (size_t)r * 128 + 64 + c2) = make_double2(0.0, 0.0);
+        if (!half)
+            *reinterpret_cast<double2 *>(&S0[r][c2]) =
+                __ldcg(reinterpret_cast<const double2 *>(Atile10 + (size_t)r * ld + c2));
+        else
         {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                cur[j] = L[((size_t)(T - 1) * TB + q * 16 + j) * ld + (size_t)i * TB + col];
+            *reinterpret_cast<double2 *>(out + (size_t)(64 + r) * 128 + c2) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2 *>(out + (size_t)(64 + r) * 128 + 64 + c2) =
+                make_double2(r == c2 ? 1.0 : 0.0, r == c2 + 1 ? 1.0 : 0.0);
         }
-        for (int k = T - 1; k > i; --k)
-        {
-            double nxt[16];
-            if (k - 1 > i)
-            {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    nxt[j] = L[((size_t)(k - 1) * TB + q * 16 + j) * ld + (size_t)i * TB + col];
-            }
-            wait_flag(C.flags + k, epoch, C.err);
-            if (tid < TB) xs[tid] = __ldcg(b + (size_t)k * TB + tid);
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                acc -= cur[j] * xs[q * 16 + j];
-            if (k - 1 > i)
-            {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    cur[j] = nxt[j];
-            }
-            __syncthreads();
-        }
-        red[q][col] = acc;
-        __syncthreads();
-        if (tid < TB)
-            xs[tid] = __ldcg(b + (size_t)i * TB + tid) + red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-        __syncthreads();
-        double xv = 0.0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            xv += li[j] * xs[q * 16 + j];
-        __syncthreads();
-        red[q][col] = xv;
-        __syncthreads();
-        if (tid < TB)
-            b[(size_t)i * TB + tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release(C.flags + i, epoch);
     }
-    trsv_epilogue(C);
+    if (half) return;
+    __syncthreads();
+    // Tm = L10 W0 : warp w owns rows 8w..8w+7; W0 is lower triangular => k >= column block start
+    double acc[8][2];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+    {
+        double c0 = 0.0, c1 = 0.0;
+        for (int kk = 8 * nb; kk < TB; kk += 4)
+            dmma_8x8x4(c0, c1, S0[8 * warp + g][kk + tg], S1[kk + tg][8 * nb + g]);
+        acc[nb][0] = c0;
+        acc[nb][1] = c1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+        *reinterpret_cast<double2 *>(&S0[8 * warp + g][8 * nb + 2 * tg]) = make_double2(acc[nb][0], acc[nb][1]);
+    for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
+    {
+        const int r = idx >> 5, c2 = (idx & 31) * 2;
+        const double2 w1 = __ldcg(reinterpret_cast<const double2 *>(W1g + r * TB + c2));
+        *reinterpret_cast<double2 *>(&S1[r][c2]) = w1;
+        *reinterpret_cast<double2 *>(out + (size_t)(64 + r) * 128 + 64 + c2) = w1;
+    }
+    __syncthreads();
+    // X = -W1 Tm : W1 lower triangular => k <= row block end
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+    {
+        double c0 = 0.0, c1 = 0.0;
+        for (int kk = 0; kk < 8 * warp + 8; kk += 4)
+            dmma_8x8x4(c0, c1, -S1[8 * warp + g][kk + tg], S0[kk + tg][8 * nb + g]);
+        *reinterpret_cast<double2 *>(out + (size_t)(64 + 8 * warp + g) * 128 + 8 * nb + 2 * tg) = make_double2(c0, c1);
+    }
+}
+
+// acc (warp tile 32x16 of the 8-warp 2x4 grid) -= X(rows) X(cols)' with both operands in one
+// shared-memory tile of stride XP (full K = 64)
+__device__ __forceinline__ void warp_mma_xx(const double (*Xs)[XP], int row0, int col0, int lane, double acc[4][2][2])
+{
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll 4
+    for (int kk = 0; kk < TB; kk += 4)
+    {
+        double a[4], b[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            a[i] = -Xs[row0 + i * 8 + g][kk + tg];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            b[j] = Xs[col0 + j * 8 + g][kk + tg];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+// X = acc L_jj^-T for tile (ti, tj): block substitution with the 16x16 inverses of L_jj (each warp owns
+// 8 rows - no block barrier inside), result written to the matrix and left in Xs (stride XP).
+// Waits for D1(tj).  All threads must call; ends WITHOUT a barrier (publish() provides it).
+__device__ __forceinline__ void trsm_tile(unsigned char *dyn_smem, const PotrfDf &P, const DfCtl &C, int epoch,
+                                          int ti, int tj, const double acc[4][2][2], int t_dbg = 8191)
+{
+    double(*Xs)[XP] = reinterpret_cast<double(*)[XP]>(dyn_smem + SM_LS);
+    double(*Lj)[XP] = reinterpret_cast<double(*)[XP]>(dyn_smem + SM_LI);
+    double(*Wd)[16][17] = reinterpret_cast<double(*)[16][17]>(dyn_smem + SM_T);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int row0 = (w >> 2) * 32, col0 = (w & 3) * 16, g = lane >> 2, tg = lane & 3;
+    const int T = P.T, ld = P.ld;
+    const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2 *>(&Xs[row0 + i * 8 + g][col0 + j * 8 + tg * 2]) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+    if (tid == 0) spin_until(P.tile_flag + tj * T + tj, epoch, C.err);
+    __syncthreads();
+    DFT(t_dbg, 8);
+    const double *Ljj = P.A + c0 * ld + c0;
+    const double *Wj = P.linv + (size_t)tj * TB * TB;
+#if SB200_V_LJ
+    {   // issue every load first (one L2 round trip), then stage
+        double2 lv[8];
+        double wv[4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+            const int idx = tid + u * NT_TILE, r = idx >> 5, c2 = (idx & 31) * 2;
+            if (c2 <= r)      // the strictly-upper part of L_jj is never read
+                lv[u] = __ldcg(reinterpret_cast<const double2 *>(Ljj + (size_t)r * ld + c2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const int idx = tid + u * NT_TILE, b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+            wv[u] = __ldcg(Wj + (size_t)(16 * b + r) * TB + 16 * b + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+            const int idx = tid + u * NT_TILE, r = idx >> 5, c2 = (idx & 31) * 2;
+            if (c2 <= r) *reinterpret_cast<double2 *>(&Lj[r][c2]) = lv[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const int idx = tid + u * NT_TILE, b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+            Wd[b][r][c] = wv[u];
+        }
+    }
+    __syncthreads();
+#else
+    for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
+    {
+        const int r = idx >> 5, c2 = (idx & 31) * 2;
+        if (c2 <= r)      // the strictly-upper part of L_jj is never read (stale memory there)
+            *reinterpret_cast<double2 *>(&Lj[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(Ljj + (size_t)r * ld + c2));
+    }
+    for (int idx = tid; idx < 4 * 16 * 16; idx += NT_TILE)
+    {
+        const int b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+        Wd[b][r][c] = __ldcg(Wj + (size_t)(16 * b + r) * TB + 16 * b + c);
+    }
+    __syncthreads();
+#endif
+    DFT(t_dbg, 9);
+    const int R = 8 * w;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+        double cc[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+        {
+            const double2 v = *reinterpret_cast<const double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]);
+            cc[nb][0] = v.x;
+            cc[nb][1] = v.y;
+        }
+        for (int kk = 0; kk < 16 * b; kk += 4)
+        {
+            const double a = -Xs[R + g][kk + tg];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+                dmma_8x8x4(cc[nb][0], cc[nb][1], a, Lj[16 * b + 8 * nb + g][kk + tg]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+            *reinterpret_cast<double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]) = make_double2(cc[nb][0], cc[nb][1]);
+        __syncwarp();
+        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int kk = 0; kk < 16; kk += 4)
+        {
+            const double a = Xs[R + g][16 * b + kk + tg];
+            if (kk < 8) dmma_8x8x4(o[0][0], o[0][1], a, Wd[b][g][kk + tg]);     // W lower: k <= n
+            dmma_8x8x4(o[1][0], o[1][1], a, Wd[b][8 + g][kk + tg]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+            *reinterpret_cast<double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]) = make_double2(o[nb][0], o[nb][1]);
+        __syncwarp();
+    }
+    // each warp writes its own 8 rows (coalesced 512 B rows)
+    DFT(t_dbg, 10);
+    double *Atile = P.A + r0 * ld + c0;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr)
+        *reinterpret_cast<double2 *>(Atile + (size_t)(R + rr) * ld + 2 * lane) =
+            *reinterpret_cast<const double2 *>(&Xs[R + rr][2 * lane]);
+}
+
+__global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ int s_task;
+    double(*As)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem);
+    double(*Bs)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem + TB * KP * 8);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int row0 = (w >> 2) * 32, col0 = (w & 3) * 16;     // 8 warps: 2 x 4, warp tile 32 x 16
+    const int g = lane >> 2, tg = lane & 3;
+    const int T = P.T, ld = P.ld;
+    const int epoch = ld_volatile(C.epoch) + 1;
+
+    auto load_acc = [&](double acc[4][2][2], size_t r0, size_t c0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+            {
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(
+                    P.A + (r0 + row0 + i * 8 + g) * ld + c0 + col0 + j * 8 + tg * 2));
+                acc[i][j][0] = v.x;
+                acc[i][j][1] = v.y;
+            }
+    };
+
+    for (;;)
+    {
+        const int t = claim_task(C, &s_task);
+        if (t >= P.ntasks) break;
+        const int2 task = P.tasks[t];
+        const int type = task.x >> 16, ti = task.x & 0xffff, tj = task.y;
+        DFT(t, 0);
+
+        if (type == TASK_PAIR)
+        {
+            const int j0 = 2 * tj, j1 = j0 + 1;
+            if (tid == 0)
+            {
+                spin_until(P.d2_flag + j0, epoch, C.err);
+                if (j1 < T)
+                {
+                    spin_until(P.d2_flag + j1, epoch, C.err);
+                    spin_until(P.tile_flag + j1 * T + j0, epoch, C.err);
+                }
+            }
+            __syncthreads();
+            pair_inverse_128(dyn_smem, j1 < T ? P.A + (size_t)j1 * TB * ld + (size_t)j0 * TB : nullptr, ld,
+                             P.linv + (size_t)j0 * TB * TB, P.linv + (size_t)j1 * TB * TB,
+                             P.linv128 + (size_t)tj * 128 * 128, tid);
+            publish(P.pair_flag + tj, epoch);
+            DFT(t, 3);
+            continue;
+        }
+
+        if (type == TASK_TILE)
+        {   // ---- regular off-diagonal tile (ti >= tj + 2): left-looking accumulation, then X = acc L_jj^-T
+            const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
+            double acc[4][2][2];
+            load_acc(acc, r0, c0);
+            for (int k = 0; k < tj; ++k)
+            {
+                if (tid == 0)
+                {
+                    spin_until(P.tile_flag + ti * T + k, epoch, C.err);
+                    spin_until(P.tile_flag + tj * T + k, epoch, C.err);
+                }
+                const size_t k0 = (size_t)k * TB;
+#pragma unroll
+                for (int kc = 0; kc < TB; kc += KC)
+                {
+                    __syncthreads();
+                    ldcg_tile_chunk(As, P.A + r0 * ld + k0 + kc, ld, tid);
+                    ldcg_tile_chunk(Bs, P.A + c0 * ld + k0 + kc, ld, tid);
+                    __syncthreads();
+                    warp_mma<4, 2>(As, Bs, row0, col0, lane, -1.0, acc);
+                }
+            }
+            __syncthreads();
+            DFT(t, 1);
+            trsm_tile(dyn_smem, P, C, epoch, ti, tj, acc);
+            publish(P.tile_flag + ti * T + tj, epoch);
+            DFT(t, 3);
+            continue;
+        }
+
+        // ---- chain task j: sub-diagonal tile (j, j-1) and diagonal tile (j, j) in one CTA, so the only
+        //      hand-off on the critical path per 64 columns is D1(j-1) -> here ------------------------
+        const int j = tj, jm = tj - 1;
+        const size_t c0 = (size_t)j * TB;
+        double acc2[4][2][2];
+        load_acc(acc2, c0, c0);
+        if (j > 0)
+        {
+            const size_t cm = (size_t)jm * TB;
+            double acc1[4][2][2];
+            load_acc(acc1, c0, cm);
+            for (int k = 0; k < jm; ++k)
+            {
+                if (tid == 0)
+                {
+                    spin_until(P.tile_flag + j * T + k, epoch, C.err);
+                    spin_until(P.tile_flag + jm * T + k, epoch, C.err);
+                }
+                const size_t k0 = (size_t)k * TB;
+#pragma unroll
+                for (int kc = 0; kc < TB; kc += KC)
+                {
+                    __syncthreads();
+                    ldcg_tile_chunk(As, P.A + c0 * ld + k0 + kc, ld, tid);
+                    ldcg_tile_chunk(Bs, P.A + cm * ld + k0 + kc, ld, tid);
+                    __syncthreads();
+                    warp_mma<4, 2>(As, Bs, row0, col0, lane, -1.0, acc1);
+                    warp_mma<4, 2>(As, As, row0, col0, lane, -1.0, acc2);
+                }
+            }
+            __syncthreads();
+            DFT(t, 1);
+#if SB200_V_PUB
+            trsm_tile(dyn_smem, P, C, epoch, j, jm, acc1, t);
+            __syncthreads();                                    // Xs complete
+            DFT(t, 4);
+            warp_mma_xx(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), row0, col0, lane, acc2);
+            // tile (j, j-1) is published after the update and by a thread of warp 1: the release fence
+            // then overlaps the pivot chain (warp 0) instead of delaying it; its consumers have a whole
+            // tile factorisation of slack
+            publish(P.tile_flag + j * T + jm, epoch, 32);
+#else
+            trsm_tile(dyn_smem, P, C, epoch, j, jm, acc1, t);
+            publish(P.tile_flag + j * T + jm, epoch);           // barrier inside: Xs complete
+            DFT(t, 4);
+            warp_mma_xx(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), row0, col0, lane, acc2);
+            __syncthreads();
+#endif
+            DFT(t, 5);
+        }
+        {   // ---- diagonal tile ----------------------------------------------------------------------
+            double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LS);
+            double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LI);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+                {
+                    const int r = row0 + i * 8 + g, c = col0 + jj * 8 + tg * 2;
+                    Ls[r][c] = acc2[i][jj][0];
+                    Ls[r][c + 1] = acc2[i][jj][1];
+                }
+            __syncthreads();
+            const int fail = potrf_tile64_factor(dyn_smem, tid);
+            DFT(t, 6);
+            DFT(t, 7);
+            double *Atile = P.A + c0 * ld + c0;
+            double *linv_j = P.linv + (size_t)j * TB * TB;
+#if SB200_V_ST
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+            {   // lower triangle of L (the element right of an even diagonal entry is the tile's zero)
+                const int idx = tid + u * NT_TILE, r = idx >> 5, c2 = (idx & 31) * 2;
+                if (c2 <= r)
+                    *reinterpret_cast<double2 *>(Atile + (size_t)r * ld + c2) = make_double2(Ls[r][c2], Ls[r][c2 + 1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+            {   // the four 16x16 diagonal inverses (the strictly-upper blocks of linv stay zero from allocation)
+                const int idx = tid + u * NT_TILE, b = idx >> 7, r = 16 * b + ((idx >> 3) & 15), c2 = 16 * b + (idx & 7) * 2;
+                *reinterpret_cast<double2 *>(linv_j + r * TB + c2) = make_double2(Li[r][c2], Li[r][c2 + 1]);
+            }
+#else
+            for (int idx = tid; idx < TB * TB; idx += NT_TILE)
+            {
+                const int r = idx >> 6, c = idx & 63;
+                if (c <= r) Atile[(size_t)r * ld + c] = Ls[r][c];
+                if ((r >> 4) == (c >> 4)) linv_j[idx] = Li[r][c];      // diagonal 16-blocks (upper blocks stay zero)
+            }
+#endif
+            report_fail(P.info, fail, (int)c0);
+            DFT(t, 11);
+            publish(P.tile_flag + j * T + j, epoch);                   // D1
+            DFT(t, 2);
+            tile64_inv_assemble(dyn_smem, tid);
+            for (int idx = tid; idx < TB * TB; idx += NT_TILE)
+            {
+                const int r = idx >> 6, c = idx & 63;
+                if ((r >> 4) > (c >> 4)) linv_j[idx] = Li[r][c];
+            }
+            publish(P.d2_flag + j, epoch);                            // D2
+            DFT(t, 3);
+        }
+    }
+    df_epilogue(C);
+}
+
+// pair inverses after the panel-launch factorisation (A/B path): one CTA per 128x128 diagonal block
+__global__ void __launch_bounds__(NT_TILE) k_pair_inverse(const double *__restrict__ A, int ld, int T,
+                                                          const double *__restrict__ linv,
+                                                          double *__restrict__ linv128)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const int b = blockIdx.x, j0 = 2 * b, j1 = j0 + 1;
+    pair_inverse_128(dyn_smem, j1 < T ? A + (size_t)j1 * TB * ld + (size_t)j0 * TB : nullptr, ld,
+                     linv + (size_t)j0 * TB * TB, linv + (size_t)(j1 < T ? j1 : j0) * TB * TB,
+                     linv128 + (size_t)b * 128 * 128, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// data-flow triangular solves: ONE launch for L y = b and L' x = y, 128-row blocks.
+// Tasks 0..T2-1 are the forward blocks (ascending), T2..2T2-1 the backward blocks (descending); a block
+// accumulates its right-hand side as the blocks it depends on arrive, then multiplies by the
+// pre-inverted 128x128 diagonal block held in shared memory.
+// Hand-off without flags or fences: every published value travels as one aligned 16-byte
+// {value, epoch tag} store; the consumer polls the pair itself (relaxed 128-bit loads) until the tag
+// is this launch's epoch, so a hop costs one store -> L2 -> load round trip.
+// ---------------------------------------------------------------------------------------------
+static constexpr int NT_TRSV = 512;
+static constexpr int WP = 132;                                   // row stride of the inverse block in smem
+static constexpr int TRSV_SMEM = 128 * WP * 8;
+
+struct TrsvDf
+{
+    const double *L;
+    int ld, T2;
+    const double *linv128;
+    double *b;
+    double2 *fwd_val, *bwd_val;      // [T2*128] tagged y / x
+};
+
+__device__ __forceinline__ void st_tagged(double2 *p, double v, double tag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(tag) : "memory");
+}
+__device__ __forceinline__ double2 ld_tagged(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void trsv_load_w(double (*Ws)[WP], const double *__restrict__ Wg, int tid)
+{
+    for (int idx = tid; idx < 128 * 64; idx += NT_TRSV)
+    {
+        const int r = idx >> 6, c2 = (idx & 63) * 2;
+        *reinterpret_cast<double2 *>(&Ws[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(Wg + (size_t)r * 128 + c2));
+    }
+}
+// warp 0 polls the 128 tagged values of block k into dst (padded by one per 32), then the block syncs
+__device__ __forceinline__ void trsv_fetch(double *dst, const double2 *src, double tag, int *err, int tid)
+{
+    if (tid < 32)
+    {
+        double2 v0, v1, v2, v3;
+        int spins = 0;
+        for (;;)
+        {
+            v0 = ld_tagged(src + tid);
+            v1 = ld_tagged(src + tid + 32);
+            v2 = ld_tagged(src + tid + 64);
+            v3 = ld_tagged(src + tid + 96);
+            if (v0.y == tag && v1.y == tag && v2.y == tag && v3.y == tag) break;
+            if ((++spins & 255) == 0)
+            {
+                if (ld_volatile(err)) break;
+                if (spins > (1 << 21))
+                {
+                    atomicExch(err, 1);
+                    break;
+                }
+            }
+        }
+        dst[tid] = v0.x;
+        dst[tid + 33] = v1.x;
+        dst[tid + 66] = v2.x;
+        dst[tid + 99] = v3.x;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ int s_task;
+    __shared__ double ys[2][132];
+    __shared__ double rs[128];
+    double(*Ws)[WP] = reinterpret_cast<double(*)[WP]>(dyn_smem);
+    const int tid = threadIdx.x, e = tid >> 2, q = tid & 3;
+    const int ld = P.ld, T2 = P.T2;
+    const int epoch = ld_volatile(C.epoch) + 1;
+    const double tag = (double)epoch;
+
+    for (;;)
+    {
+        const int t = claim_task(C, &s_task);
+        if (t >= 2 * T2) break;
+        DFT(4096 + t, 0);
+        const bool fwd = t < T2;
+        const int i = fwd ? t : 2 * T2 - 1 - t;
+        const int ge = i * 128 + e;                 // this thread's row (forward) / column (backward)
+        trsv_load_w(Ws, P.linv128 + (size_t)i * 128 * 128, tid);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double cur[32];
+        if (fwd)
+        {   // ---- L y = b: thread (row e, q) owns columns q*32..q*32+31 of every block of its row ------
+            const bool rv = ge < ld;
+            auto load_cur = [&](int k) {
+                const double2 *src = reinterpret_cast<const double2 *>(P.L + (size_t)ge * ld + (size_t)k * 128 + q * 32);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                {
+                    const double2 v = rv ? __ldcg(src + j) : make_double2(0.0, 0.0);
+                    cur[2 * j] = v.x;
+                    cur[2 * j + 1] = v.y;
+                }
+            };
+            if (i > 0) load_cur(0);
+            for (int k = 0; k < i; ++k)
+            {
+                const double *yk = ys[k & 1] + q * 33;
+                trsv_fetch(ys[k & 1], P.fwd_val + (size_t)k * 128, tag, C.err, tid);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                {
+                    a0 -= cur[j] * yk[j];
+                    a1 -= cur[j + 1] * yk[j + 1];
+                    a2 -= cur[j + 2] * yk[j + 2];
+                    a3 -= cur[j + 3] * yk[j + 3];
+                }
+                if (k + 1 < i) load_cur(k + 1);
+            }
+            DFT(4096 + t, 1);
+            double acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0) rs[e] = (rv ? __ldcg(P.b + ge) : 0.0) + acc;
+            __syncthreads();
+            a0 = a1 = a2 = a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)          // columns interleaved over q: conflict-free with WP % 16 == 4
+            {
+                a0 += Ws[e][4 * j + q] * rs[4 * j + q];
+                a1 += Ws[e][4 * j + 4 + q] * rs[4 * j + 4 + q];
+                a2 += Ws[e][4 * j + 8 + q] * rs[4 * j + 8 + q];
+                a3 += Ws[e][4 * j + 12 + q] * rs[4 * j + 12 + q];
+            }
+            double yv = (a0 + a1) + (a2 + a3);
+            yv += __shfl_xor_sync(0xffffffffu, yv, 1);
+            yv += __shfl_xor_sync(0xffffffffu, yv, 2);
+            if (q == 0) st_tagged(P.fwd_val + ge, yv, tag);
+        }
+        else
+        {   // ---- L' x = y: thread (column e, q) owns rows 4j+q of every block below ---------------------
+            auto load_cur = [&](int k) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                {
+                    const int gr = k * 128 + 4 * j + q;
+                    cur[j] = gr < ld ? __ldcg(P.L + (size_t)gr * ld + ge) : 0.0;
+                }
+            };
+            if (i < T2 - 1) load_cur(T2 - 1);
+            for (int k = T2 - 1; k > i; --k)
+            {
+                const double *xk = ys[k & 1];
+                trsv_fetch(ys[k & 1], P.bwd_val + (size_t)k * 128, tag, C.err, tid);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                {
+                    a0 -= cur[j] * xk[4 * j + q + (j >> 3)];
+                    a1 -= cur[j + 1] * xk[4 * j + 4 + q + (j >> 3)];
+                    a2 -= cur[j + 2] * xk[4 * j + 8 + q + (j >> 3)];
+                    a3 -= cur[j + 3] * xk[4 * j + 12 + q + (j >> 3)];
+                }
+                if (k - 1 > i) load_cur(k - 1);
+            }
+            DFT(4096 + t, 1);
+            double acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            // y_i (tagged forward result of the same rows)
+            trsv_fetch(ys[i & 1], P.fwd_val + (size_t)i * 128, tag, C.err, tid);
+            if (q == 0) rs[e] = ys[i & 1][e + (e >> 5)] + acc;
+            __syncthreads();
+            a0 = a1 = a2 = a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+            {
+                a0 += Ws[4 * j + q][e] * rs[4 * j + q];
+                a1 += Ws[4 * j + 4 + q][e] * rs[4 * j + 4 + q];
+                a2 += Ws[4 * j + 8 + q][e] * rs[4 * j + 8 + q];
+                a3 += Ws[4 * j + 12 + q][e] * rs[4 * j + 12 + q];
+            }
+            double xv = (a0 + a1) + (a2 + a3);
+            xv += __shfl_xor_sync(0xffffffffu, xv, 1);
+            xv += __shfl_xor_sync(0xffffffffu, xv, 2);
+            if (q == 0)
+            {
+                st_tagged(P.bwd_val + ge, xv, tag);
+                if (ge < ld) P.b[ge] = xv;
+            }
+        }
+        DFT(4096 + t, 3);
+    }
+    df_epilogue(C);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static int build_task_list(ErrorSink &err, CholWork &W, int T)
+{
+    std::vector<int2> tasks;
+    for (int j = 0; j < T; ++j)
+    {
+        tasks.push_back(make_int2(j | (TASK_CHAIN << 16), j));      // tile (j, j-1) + diagonal tile j
+        if (j & 1) tasks.push_back(make_int2(TASK_PAIR << 16, j >> 1));
+        else if (j == T - 1) tasks.push_back(make_int2(TASK_PAIR << 16, j >> 1));    // odd tile count
+        for (int i = j + 2; i < T; ++i)
+            tasks.push_back(make_int2(i | (TASK_TILE << 16), j));
+    }
+    if (W.tasks) cudaFree(W.tasks);
+    W.tasks = nullptr;
+    SB200_CUDA_TRY(err, cudaMalloc(&W.tasks, sizeof(int2) * tasks.size()));
+    SB200_CUDA_TRY(err, cudaMemcpy(W.tasks, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice));
+    W.ntasks = (int)tasks.size();
+    W.tasks_T = T;
+    return SB200_OK;
+}
+
 int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad)
 {
     const int T = n_pad / TB;
-    if (T <= W.t_cap) return SB200_OK;
-    chol_work_free(W);
-    SB200_CUDA_TRY(err, cudaMalloc(&W.linv, sizeof(double) * (size_t)T * TB * TB));
-    SB200_CUDA_TRY(err, cudaMalloc(&W.ctl, sizeof(int) * (size_t)(2 * T + 16)));
-    SB200_CUDA_TRY(err, cudaMemset(W.ctl, 0, sizeof(int) * (size_t)(2 * T + 16)));
-    W.t_cap = T;
-    int dev = 0, sms = 0, occ_f = 0, occ_b = 0;
-    SB200_CUDA_TRY(err, cudaGetDevice(&dev));
-    SB200_CUDA_TRY(err, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SB200_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_trsv_fwd, 256, 0));
-    SB200_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_trsv_bwd, 256, 0));
-    const int occ = occ_f < occ_b ? occ_f : occ_b;
-    W.max_coop_grid = sms * (occ < 1 ? 1 : occ);
-    SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_potrf_first, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    if (T > 0xffff) { err.msg = "chol_work_ensure: matrix too large"; return SB200_ERR_UNSUPPORTED; }
+    if (T > W.t_cap)
+    {
+        chol_work_free(W);
+        const int T2 = (T + 1) / 2;
+        const size_t nflags = (size_t)T * T + T + 3 * (size_t)T2 + 32;
+        SB200_CUDA_TRY(err, cudaMalloc(&W.linv, sizeof(double) * (size_t)T * TB * TB));
+        SB200_CUDA_TRY(err, cudaMemset(W.linv, 0, sizeof(double) * (size_t)T * TB * TB));
+        SB200_CUDA_TRY(err, cudaMalloc(&W.linv128, sizeof(double) * (size_t)T2 * 128 * 128));
+        SB200_CUDA_TRY(err, cudaMalloc(&W.tagged, sizeof(double2) * (size_t)T2 * 128 * 2));
+        SB200_CUDA_TRY(err, cudaMemset(W.tagged, 0, sizeof(double2) * (size_t)T2 * 128 * 2));
+        SB200_CUDA_TRY(err, cudaMalloc(&W.ctl, sizeof(int) * nflags));
+        SB200_CUDA_TRY(err, cudaMemset(W.ctl, 0, sizeof(int) * nflags));
+        W.t_cap = T;
+        int dev = 0;
+        SB200_CUDA_TRY(err, cudaGetDevice(&dev));
+        SB200_CUDA_TRY(err, cudaDeviceGetAttribute(&W.sms, cudaDevAttrMultiProcessorCount, dev));
+        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_potrf_first, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_potrf_df, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_pair_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_trsv_df, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+        int occ = 0;
+        SB200_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_potrf_df, NT_TILE, SM_TOTAL));
+        W.potrf_occ = occ < 1 ? 1 : occ;
+        const char *mode = getenv("SB200_POTRF");
+        W.panel_mode = (mode && std::string(mode) == "panel") ? 1 : 0;
+    }
+    if (T != W.tasks_T) return build_task_list(err, W, T);
     return SB200_OK;
 }
 void chol_work_free(CholWork &W)
 {
     if (W.linv) cudaFree(W.linv);
+    if (W.linv128) cudaFree(W.linv128);
     if (W.ctl) cudaFree(W.ctl);
+    if (W.tagged) cudaFree(W.tagged);
+    if (W.tasks) cudaFree(W.tasks);
     W = CholWork{};
 }
 
+// ctl layout (ints): [0..2] potrf epoch/next/exits, [4..6] trsv epoch/next/exits, [8] err,
+// [32 ..) tile flags T*T, D2 flags T, pair flags T2, fwd flags T2, bwd flags T2   (T = t_cap)
 void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t st)
 {
     (void)n;
-    const int T = ld / TB;
-    k_potrf_first<<<1, NT_TILE, SM_TOTAL, st>>>(a, ld, W.linv, info);
-    ++g_launch_count;
-    for (int k = 0; k + 1 < T; ++k)
+    const int T = ld / TB, T2 = (T + 1) / 2;
+    if (W.panel_mode)
     {
-        const int rem = T - 1 - k;
-        k_trsm_panel<<<rem, 128, 0, st>>>(a, ld, k, W.linv);
-        k_update<<<rem * (rem + 1) / 2, NT_TILE, SM_TOTAL, st>>>(a, ld, k, T, W.linv, info);
-        g_launch_count += 2;
+        k_potrf_first<<<1, NT_TILE, SM_TOTAL, st>>>(a, ld, W.linv, info);
+        ++g_launch_count;
+        for (int k = 0; k + 1 < T; ++k)
+        {
+            const int rem = T - 1 - k;
+            k_trsm_panel<<<rem, 128, 0, st>>>(a, ld, k, W.linv);
+            k_update<<<rem * (rem + 1) / 2, NT_TILE, SM_TOTAL, st>>>(a, ld, k, T, W.linv, info);
+            g_launch_count += 2;
+        }
+        k_pair_inverse<<<T2, NT_TILE, SM_TOTAL, st>>>(a, ld, T, W.linv, W.linv128);
+        ++g_launch_count;
+        return;
     }
-}
-
-static cudaError_t launch_coop(const void *fn, int grid, int block, void **args, cudaStream_t st)
-{
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelExC(&cfg, fn, args);
+    int *ctl = W.ctl, *flags = W.ctl + 32;
+    const size_t tc = (size_t)W.t_cap;
+    PotrfDf P{a, ld, T, W.linv, W.linv128, W.tasks, W.ntasks, flags, flags + tc * tc, flags + tc * tc + tc, info};
+    DfCtl C{ctl + 0, reinterpret_cast<unsigned *>(ctl + 1), reinterpret_cast<unsigned *>(ctl + 2), ctl + 8};
+    const int cap = W.sms * W.potrf_occ;
+    const int grid = W.ntasks < cap ? W.ntasks : cap;
+    k_potrf_df<<<grid, NT_TILE, SM_TOTAL, st>>>(P, C);
+    ++g_launch_count;
 }
 
 void launch_potrs(CholWork &W, int n, const double *l, int ld, double *b, cudaStream_t st)
 {
     (void)n;
-    int T = ld / TB;
-    const int grid = T < W.max_coop_grid ? T : W.max_coop_grid;
-    int *ctl = W.ctl;
-    TrsvCtl Cf{ctl + 16, ctl + 0, reinterpret_cast<unsigned *>(ctl + 1), ctl + 4};
-    TrsvCtl Cb{ctl + 16 + W.t_cap, ctl + 2, reinterpret_cast<unsigned *>(ctl + 3), ctl + 4};
-    const double *linv = W.linv;
-    {
-        void *args[] = {(void *)&l, (void *)&ld, (void *)&linv, (void *)&b, (void *)&T, (void *)&Cf};
-        launch_coop((const void *)k_trsv_fwd, grid, 256, args, st);
-    }
-    {
-        void *args[] = {(void *)&l, (void *)&ld, (void *)&linv, (void *)&b, (void *)&T, (void *)&Cb};
-        launch_coop((const void *)k_trsv_bwd, grid, 256, args, st);
-    }
-    g_launch_count += 2;
+    const int T = ld / TB, T2 = (T + 1) / 2;
+    int *ctl = W.ctl, *flags = W.ctl + 32;
+    const size_t tc = (size_t)W.t_cap, tc2 = (tc + 1) / 2;
+    (void)flags;
+    TrsvDf P{l, ld, T2, W.linv128, b, W.tagged, W.tagged + tc2 * 128};
+    DfCtl C{ctl + 4, reinterpret_cast<unsigned *>(ctl + 5), reinterpret_cast<unsigned *>(ctl + 6), ctl + 8};
+    const int grid = 2 * T2 < W.sms ? 2 * T2 : W.sms;
+    k_trsv_df<<<grid, NT_TRSV, TRSV_SMEM, st>>>(P, C);
+    ++g_launch_count;
 }
 
 } // namespace sb200

@@ -6,9 +6,15 @@ namespace sb200 {
 
 struct CholWork
 {
-    double *linv = nullptr;     // [T][64][64] inverses of the diagonal blocks of L
-    int *ctl = nullptr;         // epochs, exit tickets, error flag, then 2*T publish flags
+    double *linv = nullptr;     // [T][64][64] inverses of the 64x64 diagonal blocks of L
+    double *linv128 = nullptr;  // [ceil(T/2)][128][128] inverses of the 128x128 diagonal blocks
+    double2 *tagged = nullptr;  // [2][ceil(T/2)*128] {value, epoch tag}: forward / backward solve hand-off
+    int *ctl = nullptr;         // epochs, task counters, error flag, then the publish flags
+    int2 *tasks = nullptr;      // task list of the data-flow factorisation for tasks_T tiles
+    int ntasks = 0, tasks_T = 0;
     int t_cap = 0;
+    int sms = 148, potrf_occ = 1;
+    int panel_mode = 0;         // SB200_POTRF=panel: the two-launches-per-panel factorisation (A/B)
     int max_coop_grid = 148;
 };
 

@@ -21,15 +21,19 @@ static constexpr int LP = TB + 1;    // padded row stride of the tile in shared 
 static constexpr int SM_LS = 0;                                   // L tile (aliases the MMA staging buffers)
 static constexpr int SM_MMA_BYTES = 2 * TB * KP * 8;              // 36864
 static constexpr int SM_LI = SM_MMA_BYTES;                        // inverse tile
-static constexpr int SM_T = SM_LI + TB * LP * 8;                  // 32x32 scratch of the inverse
-static constexpr int SM_INVD = SM_T + 1024 * 8;                   // 64 reciprocal pivots
+static constexpr int XP = TB + 4;                                 // row stride of DMMA-fragment-friendly tiles
+static constexpr int SM_LI_BYTES = TB * XP * 8;                   // 34816 (>= TB*LP*8)
+static constexpr int SM_T = SM_LI + SM_LI_BYTES;                  // 32x32 scratch of the inverse / 4 x 16x17 blocks
+static constexpr int SM_INVD = SM_T + 1088 * 8;                   // 64 reciprocal pivots
 static constexpr int SM_FLAG = SM_INVD + 64 * 8;
 static constexpr int SM_TOTAL = SM_FLAG + 16;
 static constexpr int NT_TILE = 256;                               // threads of the tile factorisation
 
 #ifdef SB200_TILE_TIMING
+// stamped by thread 32 (warp 1): a stamp inside warp 0 leaves the pivot-chain warp diverged and makes
+// every shuffle take its slow path (measured: 19.6k instead of 3.6k cycles per 16x16 block)
 __device__ long long g_tile_timing[64];
-#define TT(i) do { if (tid == 0) g_tile_timing[i] = clock64(); } while (0)
+#define TT(i) do { if (tid == 32) g_tile_timing[i] = clock64(); } while (0)
 #else
 #define TT(i) do { } while (0)
 #endif
@@ -60,96 +64,190 @@ __device__ __forceinline__ void dmma_block_nt_sub(const double *A, const double 
     C[g * ldc + 2 * tg + 1] = c1;
 }
 
-// Returns 0 or the 1-based local index of the first non-positive pivot (same value in all threads).
-// On exit Ls = L (upper zeroed), Li = L^-1 (upper zero).
-__device__ int potrf_inv_tile64(unsigned char *smem, int tid)
+// 1/sqrt(x) for a normal positive double: MUFU seed (about 20 bits) + one third-order correction
+// y0 (1 + e/2 + 3e^2/8), e = 1 - x y0^2 - the same arithmetic as CUDA's rsqrt() without its
+// special-case branch, which costs more than the arithmetic on the serial pivot chain (isolated
+// 16x16 block on B200: 3630 -> 2420 cycles).  Non-positive / non-finite pivots are caught by the
+// caller's d > 0 test; the garbage this returns for them never reaches a reported result.
+__device__ __forceinline__ double rsqrt_pivot(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-(y0 * y0), x, 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+
+#ifndef SB200_V_RSQ
+#define SB200_V_RSQ 1
+#endif
+#ifndef SB200_V_TRAIL
+#define SB200_V_TRAIL 0      // 1 = three interleaved blocks per warp: measured SLOWER (354 -> 395 us at m = 1024)
+#endif
+#if SB200_V_RSQ
+#define SB200_RSQ(x) rsqrt_pivot(x)
+#else
+#define SB200_RSQ(x) rsqrt(x)
+#endif
+
+// Factor: returns 0 or the 1-based local index of the first non-positive pivot (same value in all
+// threads).  On exit Ls = L (upper zeroed) and the four 16x16 diagonal blocks of Li hold the inverses
+// of the diagonal blocks of L (the strictly-upper 16x16 blocks of Li are cleared).
+//
+// Per 16-column panel:
+//   1. ONE warp factors the 16x16 diagonal block: lanes 0..15 hold its rows in registers, column c of
+//      L is broadcast through shared memory, and the pivot chain dg -> shfl -> rsqrt -> l is issued one
+//      column ahead of the bulk update (measured on B200: shfl 26, rsqrt 67, DFMA 8 cycles).  Lanes
+//      16..31 run the SAME instruction stream on the columns of the identity, which yields W = L_dd^-1
+//      at no extra latency.
+//   2. the rows below become X = A W' on the tensor pipe (one 8-row block per warp) instead of a
+//      16-step substitution;
+//   3. the trailing lower triangle is updated with unrolled 8x8x16 DMMA blocks.
+__device__ int potrf_tile64_factor(unsigned char *smem, int tid)
 {
     TT(0);
     double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
     double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LI);
-    double *Tb = reinterpret_cast<double *>(smem + SM_T);        // 32x32 scratch; also the 16x16 column buffer
-    double *invd = reinterpret_cast<double *>(smem + SM_INVD);
+    double *Tb = reinterpret_cast<double *>(smem + SM_T);        // the 16x16 column buffer of the diagonal block
     int *sflag = reinterpret_cast<int *>(smem + SM_FLAG);
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
     if (tid == 0) *sflag = 0;
+    // clear the strictly-upper 16x16 blocks of Li: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    for (int idx = tid; idx < 6 * 256; idx += NT_TILE)
+    {
+        const int blk = idx >> 8, e = idx & 255;
+        const int bi = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
+        const int bj = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
+        Li[16 * bi + (e >> 4)][16 * bj + (e & 15)] = 0.0;
+    }
 
+#pragma unroll 1
     for (int kb = 0; kb < 4; ++kb)
     {
         const int c0 = 16 * kb;
         __syncthreads();
+        TT(8 + 4 * kb);
         if (warp == 0)
-        {   // ---- 16x16 diagonal block: lane r holds row c0+r (lanes 16..31 duplicate 0..15) ----
-            // Column c of L is broadcast through shared memory (Cb); the pivot chain
-            // shfl(dg) -> rsqrt -> l -> dg is issued one column ahead of the bulk update.
+        {
             const int r = lane & 15;
+            const bool inv_lane = lane >= 16;          // lanes 16..31: column r of W = L_dd^-1
             double(*Cb)[17] = reinterpret_cast<double(*)[17]>(Tb);
             double a[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                a[j] = Ls[c0 + r][c0 + j];
+                a[j] = inv_lane ? (j == r ? 1.0 : 0.0) : Ls[c0 + r][c0 + j];
             double dg = a[0];
 #pragma unroll
             for (int j = 1; j < 16; ++j)
                 dg = (r == j) ? a[j] : dg;             // this lane's own diagonal entry
             int bad = 0;
             double d = __shfl_sync(0xffffffffu, dg, 0);
-            double inv = rsqrt(d);
+            double inv = SB200_RSQ(d);
 #pragma unroll
             for (int c = 0; c < 16; ++c)
             {
                 if (!(d > 0.0) && bad == 0) bad = c0 + c + 1;
-                const double l = (r == c) ? d * inv : a[c] * inv;     // L[r][c], meaningful for r >= c
+                // rows: L[r][c] (meaningful for r >= c);  inverse lanes: z_c = z[c] / L[c][c]
+                const double l = (!inv_lane && r == c) ? d * inv : a[c] * inv;
                 a[c] = l;
                 dg -= l * l;
-                Cb[c][r] = l;
-                if (lane == c) invd[c0 + c] = inv;
+                if (!inv_lane) Cb[c][r] = l;
                 if (c < 15)
                 {   // next pivot: long-latency chain started before this column's bulk update
                     d = __shfl_sync(0xffffffffu, dg, c + 1);
-                    inv = rsqrt(d);
+                    inv = SB200_RSQ(d);
                 }
                 __syncwarp();
 #pragma unroll
                 for (int c2 = c + 1; c2 < 16; ++c2)
-                    a[c2] -= l * Cb[c][c2];            // L[c2][c] (broadcast read)
+                    a[c2] -= l * Cb[c][c2];            // L[c2][c] (broadcast read); inverse lanes: z[c2] -= L[c2][c] z_c
             }
-            if (lane < 16)
+            if (!inv_lane)
             {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     Ls[c0 + r][c0 + j] = (j <= r) ? a[j] : 0.0;
             }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    Li[c0 + j][c0 + r] = a[j];         // W[j][r]; zero above the diagonal by construction
+            }
             if (lane == 0 && bad) atomicCAS(sflag, 0, bad);
         }
         __syncthreads();
+        TT(9 + 4 * kb);
         const int nrows = 48 - c0;
-        if (tid < nrows)
-        {   // ---- panel: rows below, X L_dd' = A  (one thread per row) -------------------------
-            const int row = c0 + 16 + tid;
-            double x[16];
+        if (8 * warp < nrows)
+        {   // ---- rows below: X = A W' (W lower triangular: k <= n), one 8-row block per warp ----------
+            const int R = c0 + 16 + 8 * warp;
+            double af[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                x[j] = Ls[row][c0 + j];
+            for (int kk = 0; kk < 4; ++kk)
+                af[kk] = Ls[R + g][c0 + 4 * kk + tg];
+            double x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
+            for (int kk = 0; kk < 4; ++kk)
             {
-                const double xc = x[c] * invd[c0 + c];
-                x[c] = xc;
-#pragma unroll
-                for (int c2 = c + 1; c2 < 16; ++c2)
-                    x[c2] -= xc * Ls[c0 + c2][c0 + c];
+                if (kk < 2) dmma_8x8x4(x00, x01, af[kk], Li[c0 + g][c0 + 4 * kk + tg]);
+                dmma_8x8x4(x10, x11, af[kk], Li[c0 + 8 + g][c0 + 4 * kk + tg]);
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                Ls[row][c0 + j] = x[j];
+            __syncwarp();
+            Ls[R + g][c0 + 2 * tg] = x00;
+            Ls[R + g][c0 + 2 * tg + 1] = x01;
+            Ls[R + g][c0 + 8 + 2 * tg] = x10;
+            Ls[R + g][c0 + 8 + 2 * tg + 1] = x11;
         }
-        else if (tid >= 64 && tid < 64 + 16 && kb < 3)
+        else if (kb < 3 && warp == 7)
         {   // meanwhile: zero the part of the block row right of the diagonal block
-            const int rr = c0 + (tid - 64);
-            for (int j = c0 + 16; j < TB; ++j)
-                Ls[rr][j] = 0.0;
+            for (int idx = lane; idx < 16 * (48 - c0); idx += 32)
+                Ls[c0 + idx / (48 - c0)][c0 + 16 + idx % (48 - c0)] = 0.0;
         }
         __syncthreads();
+        TT(10 + 4 * kb);
+#if SB200_V_TRAIL
+        {   // ---- trailing update on the tensor pipe: 8x8 blocks of the lower triangle; a warp owns up to
+            //      three blocks (q = warp, warp+8, warp+16) and interleaves their independent DMMA chains
+            const int r0 = c0 + 16, nb = nrows >> 3, nblk = nb * (nb + 1) / 2;
+            double af[3][4], bf[3][4], u[3][2];
+            double *Cp[3];
+            bool act[3];
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+            {
+                const int q = warp + 8 * v;
+                act[v] = q < nblk;
+                int bi = 0;
+                while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
+                const int bj = q - bi * (bi + 1) / 2;
+                Cp[v] = &Ls[r0 + 8 * bi + g][r0 + 8 * bj + 2 * tg];
+                if (act[v])
+                {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                    {
+                        af[v][kk] = -Ls[r0 + 8 * bi + g][c0 + 4 * kk + tg];
+                        bf[v][kk] = Ls[r0 + 8 * bj + g][c0 + 4 * kk + tg];
+                    }
+                    u[v][0] = Cp[v][0];
+                    u[v][1] = Cp[v][1];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                    if (act[v]) dmma_8x8x4(u[v][0], u[v][1], af[v][kk], bf[v][kk]);
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+                if (act[v])
+                {
+                    Cp[v][0] = u[v][0];
+                    Cp[v][1] = u[v][1];
+                }
+        }
+    }
+#else
         {   // ---- trailing update on the tensor pipe: 8x8 blocks of the lower triangle, round-robin
             const int r0 = c0 + 16, nb = nrows >> 3, nblk = nb * (nb + 1) / 2;
             for (int q = warp; q < nblk; q += 8)
@@ -158,15 +256,37 @@ __device__ int potrf_inv_tile64(unsigned char *smem, int tid)
                 while (bi * (bi + 1) / 2 > q) --bi;
                 while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
                 const int bj = q - bi * (bi + 1) / 2;
-                dmma_block_nt_sub(&Ls[r0 + 8 * bi][c0], &Ls[r0 + 8 * bj][c0], LP, &Ls[r0 + 8 * bi][r0 + 8 * bj], LP,
-                                  16, lane);
+                double af[4], bf[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                {
+                    af[kk] = -Ls[r0 + 8 * bi + g][c0 + 4 * kk + tg];
+                    bf[kk] = Ls[r0 + 8 * bj + g][c0 + 4 * kk + tg];
+                }
+                double *Cp = &Ls[r0 + 8 * bi + g][r0 + 8 * bj + 2 * tg];
+                double u0 = Cp[0], u1 = Cp[1];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    dmma_8x8x4(u0, u1, af[kk], bf[kk]);
+                Cp[0] = u0;
+                Cp[1] = u1;
             }
         }
     }
+#endif
     __syncthreads();
     TT(1);
+    return *sflag;
+}
 
-    // ---- inverse: four 16x16 triangular inverses, lane j of warp b computes column j -------------
+// The four 16x16 diagonal blocks of Li = L^-1 (lane j of warp b computes column j of block b); the
+// strictly-upper 16x16 blocks of Li are cleared.  Ends with a block barrier.
+__device__ void tile64_inv16(unsigned char *smem, int tid)
+{
+    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
+    double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LI);
+    double *invd = reinterpret_cast<double *>(smem + SM_INVD);
+    const int lane = tid & 31, warp = tid >> 5;
     if (warp < 4 && lane < 16)
     {
         const int b0 = 16 * warp, j = lane;
@@ -200,6 +320,16 @@ __device__ int potrf_inv_tile64(unsigned char *smem, int tid)
         }
     }
     __syncthreads();
+}
+
+// Off-diagonal blocks of Li from the 16x16 diagonal inverses: two levels of
+// inv([A 0; C D]) = [A^-1 0; -D^-1 C A^-1  D^-1].  Ends with a block barrier.
+__device__ void tile64_inv_assemble(unsigned char *smem, int tid)
+{
+    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
+    double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LI);
+    double *Tb = reinterpret_cast<double *>(smem + SM_T);
+    const int lane = tid & 31, warp = tid >> 5;
     // level 16 -> 32: two independent pairs p; T = L21 W11, X21 = -W22 T.  8 blocks of 8x8 -> 8 warps.
     {
         const int p = warp >> 2, bi = (warp >> 1) & 1, bj = warp & 1, o = 32 * p;
@@ -224,7 +354,14 @@ __device__ int potrf_inv_tile64(unsigned char *smem, int tid)
     }
     __syncthreads();
     TT(2);
-    return *sflag;
+}
+
+// factor + full inverse (the panel-launch path and the stand-alone tile kernel)
+__device__ int potrf_inv_tile64(unsigned char *smem, int tid)
+{
+    const int fail = potrf_tile64_factor(smem, tid);     // also leaves the 16x16 diagonal inverses in Li
+    tile64_inv_assemble(smem, tid);
+    return fail;
 }
 
 } // namespace sb200

@@ -153,9 +153,16 @@ int sb200_model_info(sb200_ws *ws, long long *info, int n_info);
 void *sb200_stream(sb200_ws *ws);
 /* time one phase of the loop on the resident model with CUDA events on the workspace stream:
  * phase 0 = normal-matrix assembly, 1 = Cholesky factorisation, 2 = one solve (forward+backward),
- * 3 = CSR SpMV (rhs), 4 = CSC SpMV + recovery + ratio test, 5 = fused update kernel.
+ * 3 = CSR SpMV (rhs), 4 = CSC SpMV + recovery + ratio test, 5 = fused update kernel,
+ * 6 = one whole CG iteration, 7 = its A'p product, 8 = its A q product (PCG strategy only).
  * Writes the mean milliseconds per launch group over `reps` runs (after one warm-up). */
 int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out);
+
+/* y = A x (transpose = 0, x length n, y length m) or y = A' x (transpose = 1) on the RESIDENT model, with
+ * whatever representation the workspace built for it (value-carrying CSR/CSC, or the +/-1 pattern staged
+ * through shared memory for PCG-strategy models).  Device pointers; runs on the workspace stream and
+ * synchronises.  Replaces cusparseSpMV on node.matDescr (src/sypha_solver.cpp:419,450). */
+int sb200_ws_spmv(sb200_ws *ws, int transpose, const double *d_x, double *d_y);
 
 /* ---- L0 kernels on caller-owned device buffers ------------------------------------------------ */
 int sb200_k_elem_min_mult(const double *d_x, const double *d_s, double *d_out, int n, void *stream);

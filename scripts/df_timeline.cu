@@ -76,8 +76,13 @@ int main(int argc, char **argv)
     for (int t = 0; t < 2 * T2; t++) s0 = std::min(s0, tm[4096 + t][0]);
     printf("# trsv tasks: t claim acc_done done (us)\n");
     for (int t = 0; t < 2 * T2 && t < 64; t++)
-        printf("trsv %3d  %8.2f %8.2f %8.2f\n", t, (tm[4096 + t][0] - s0) * 1e-3, (tm[4096 + t][1] - s0) * 1e-3,
+    {
+        printf("trsv %3d  %8.2f %8.2f %8.2f", t, (tm[4096 + t][0] - s0) * 1e-3, (tm[4096 + t][1] - s0) * 1e-3,
                (tm[4096 + t][3] - s0) * 1e-3);
+        if (t >= T2) printf("   last-x seen %8.2f  y_i seen %8.2f  W done %8.2f", (tm[4096 + t][4] - s0) * 1e-3,
+                            (tm[4096 + t][5] - s0) * 1e-3, (tm[4096 + t][6] - s0) * 1e-3);
+        printf("\n");
+    }
 #ifdef SB200_TILE_TIMING
     {
         long long tt[64];

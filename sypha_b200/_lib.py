@@ -67,6 +67,7 @@ SYMBOLS = {
     "sb200_model_info": (_i, [_vp, C.POINTER(_ll), _i]),
     "sb200_stream": (_vp, [_vp]),
     "sb200_time_phase": (_i, [_vp, _i, _i, C.POINTER(_d)]),
+    "sb200_ws_spmv": (_i, [_vp, _i, _vp, _vp]),
     "sb200_k_elem_min_mult": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sb200_k_corrector_rhs": (_i, [_vp, _vp, _d, _d, _vp, _i, _vp]),
     "sb200_k_alpha_max": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 using namespace sb200;
@@ -41,6 +42,7 @@ struct sb200_ws
     long long nnz_cap = 0;
 
     NormalPattern pat;
+    BlockedPattern blk_rows, blk_cols;    // PCG strategy on a +/-1 matrix: shared-memory-staged products
     double *denseA = nullptr;     // SYRK strategy: dense row-major copy of A, mpad x kpad
     int kpad = 0;
     double *M = nullptr;          // mpad x mpad
@@ -163,10 +165,14 @@ void carve(sb200_ws *ws)
     V.dy = (ws->strategy == SB200_STRATEGY_PCG) ? ws->cg_x : V.rhs;
 }
 
-CsrView csr_of(const sb200_ws *ws) { return CsrView{ws->m, ws->csr_offs, ws->csr_inds, ws->csr_vals}; }
+CsrView csr_of(const sb200_ws *ws)
+{
+    return CsrView{ws->m, ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->blk_rows.ptr ? &ws->blk_rows : nullptr};
+}
 CscView csc_of(const sb200_ws *ws)
 {
-    return CscView{ws->n, ws->csc_colptr, ws->csc_rows, ws->csc_vals, ws->csc_lanes};
+    return CscView{ws->n, ws->csc_colptr, ws->csc_rows, ws->csc_vals, ws->csc_lanes,
+                   ws->blk_cols.ptr ? &ws->blk_cols : nullptr};
 }
 
 __global__ void k_densify(int m, const int *__restrict__ offs, const int *__restrict__ inds,
@@ -557,6 +563,8 @@ int sb200_ws_destroy(sb200_ws *ws)
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     drop_graphs(ws);
     free_normal_pattern(&ws->pat);
+    free_blocked(&ws->blk_rows);
+    free_blocked(&ws->blk_cols);
     chol_work_free(ws->chol);
     void *ptrs[] = {ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
                     ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams};
@@ -627,6 +635,26 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
         }
     }
     ws->strategy = strat;
+    free_blocked(&ws->blk_rows);
+    free_blocked(&ws->blk_cols);
+    if (strat == SB200_STRATEGY_PCG)
+    {   // +/-1 matrix => pattern-only, shared-memory-staged products (sb200_blocked.cu)
+        const char *off = getenv("SB200_BLOCKED");
+        if (!(off && off[0] == '0'))
+        {
+            rc = build_blocked(ws->err, m, n, nnz, ws->csr_offs, ws->csr_inds, ws->csr_vals, blocked_nb_for_rows(n), true,
+                               &ws->blk_rows, st);
+            if (rc == SB200_OK)
+                rc = build_blocked(ws->err, n, m, nnz, ws->csc_colptr, ws->csc_rows, ws->csc_vals, blocked_nb_for_cols(m),
+                                   false, &ws->blk_cols, st);
+            if (rc != SB200_OK)
+            {
+                free_blocked(&ws->blk_rows);
+                free_blocked(&ws->blk_cols);
+                if (rc != SB200_ERR_UNSUPPORTED) return rc;      // general coefficients: value-carrying kernels
+            }
+        }
+    }
     if (strat == SB200_STRATEGY_SYRK)
     {
         ws->kpad = round_up(n, 32);
@@ -737,7 +765,9 @@ int sb200_model_info(sb200_ws *ws, long long *info, int n_info)
     if (!ws || !ws->loaded || !info) return SB200_ERR_INVALID;
     const long long vals[] = {ws->m, ws->n, ws->n_orig, ws->nnz, ws->mpad, ws->strategy, ws->pat.n_pairs,
                               ws->pat.n_terms, ws->pat.term_w ? 1 : 0, ws->csc_lanes,
-                              ws->iter_graph_kernels, ws->chol.max_coop_grid};
+                              ws->iter_graph_kernels, ws->chol.max_coop_grid, ws->blk_rows.ptr ? 1 : 0,
+                              ws->blk_rows.nblk, ws->blk_cols.nblk, (long long)ws->blk_rows.n_chunks,
+                              (long long)ws->blk_cols.n_chunks};
     const int k = (int)(sizeof vals / sizeof vals[0]);
     for (int i = 0; i < n_info && i < k; ++i) info[i] = vals[i];
     return k;
@@ -756,6 +786,15 @@ int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out)
     WS_TRY(cudaEventCreate(&e1));
     // a benign state: d = 1, done = 0
     launch_reset_scalars(ws->sc, st);
+    if (phase >= 6 && phase <= 8 && ws->strategy == SB200_STRATEGY_PCG)
+    {   // CG state for rhs = b, D = I, tolerance never met
+        PcgVecs C{ws->m, V.rhs, ws->cg_diag, ws->cg_x, ws->cg_r, ws->cg_z, ws->cg_p, ws->cg_Ap, ws->cg_q, ws->ones_n,
+                  V.partial};
+        WS_TRY(cudaMemsetAsync(V.rhs, 0, sizeof(double) * ws->mpad, st));
+        WS_TRY(cudaMemcpyAsync(V.rhs, ws->b, sizeof(double) * ws->m, cudaMemcpyDeviceToDevice, st));
+        launch_jacobi_diag(csr_of(ws), ws->ones_n, ws->cg_diag, st);
+        launch_cg_init(C, ws->sc, ws->dparams, 1e-300, 0, st);
+    }
     double total = 0.0;
     for (int r = -1; r < reps; ++r)
     {
@@ -784,6 +823,24 @@ int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out)
         case 3: launch_spmv_csr(csr_of(ws), V.t, V.resB, V.rhs, 1.0, 1.0, st); break;
         case 4: launch_spmv_csc(csc_of(ws), CSC_RECOVER, V.y, nullptr, nullptr, 0, 0, &V, st); break;
         case 5: launch_affine_mu(V, st); break;
+        case 6:
+        case 7:
+        case 8:
+        {   // PCG strategy: one CG iteration / its A'p product / its A q product on a never-converging solve
+            if (ws->strategy != SB200_STRATEGY_PCG)
+                return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_time_phase: CG phase on a direct-strategy model");
+            PcgVecs C{ws->m, V.rhs, ws->cg_diag, ws->cg_x, ws->cg_r, ws->cg_z, ws->cg_p, ws->cg_Ap, ws->cg_q,
+                      ws->ones_n, V.partial};
+            if (phase == 6)
+                launch_cg_iteration(csr_of(ws), csc_of(ws), C, V, ws->dparams, 1 << 30, st);
+            else if (phase == 7)
+                launch_spmv_csc_cg(csc_of(ws), C.p, C.q, C.dscale, ws->sc, st);
+            else if (csr_of(ws).blk)
+                launch_blk_cg_matvec(*csr_of(ws).blk, C, ws->sc, st);
+            else
+                launch_spmv_csr(csr_of(ws), C.q, nullptr, C.Ap, 1.0, 0.0, st);
+            break;
+        }
         default: return fail(ws, SB200_ERR_INVALID, "sb200_time_phase: unknown phase");
         }
         WS_TRY(cudaEventRecord(e1, st));
@@ -795,6 +852,19 @@ int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_out = total / reps;
+    return SB200_OK;
+}
+
+int sb200_ws_spmv(sb200_ws *ws, int transpose, const double *d_x, double *d_y)
+{
+    if (!ws || !ws->loaded || !d_x || !d_y) return SB200_ERR_INVALID;
+    WS_TRY(cudaSetDevice(ws->device));
+    if (transpose)
+        launch_spmv_csc(csc_of(ws), CSC_PLAIN, d_x, d_y, d_y, 1.0, 0.0, nullptr, ws->stream);
+    else
+        launch_spmv_csr(csr_of(ws), d_x, d_y, d_y, 1.0, 0.0, ws->stream);
+    WS_TRY(cudaGetLastError());
+    WS_TRY(cudaStreamSynchronize(ws->stream));
     return SB200_OK;
 }
 

@@ -928,6 +928,7 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
             {
                 const double *xk = ys[k & 1];
                 trsv_fetch(ys[k & 1], P.bwd_val + (size_t)k * 128, tag, C.err, tid);
+                DFT(4096 + t, 4);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                 {
@@ -944,6 +945,7 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
             // y_i (tagged forward result of the same rows)
             trsv_fetch(ys[i & 1], P.fwd_val + (size_t)i * 128, tag, C.err, tid);
+            DFT(4096 + t, 5);
             if (q == 0) rs[e] = ys[i & 1][e + (e >> 5)] + acc;
             __syncthreads();
             a0 = a1 = a2 = a3 = 0.0;
@@ -956,6 +958,7 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
                 a3 += Ws[4 * j + 12 + q][e] * rs[4 * j + 12 + q];
             }
             double xv = (a0 + a1) + (a2 + a3);
+            DFT(4096 + t, 6);
             xv += __shfl_xor_sync(0xffffffffu, xv, 1);
             xv += __shfl_xor_sync(0xffffffffu, xv, 2);
             if (q == 0)

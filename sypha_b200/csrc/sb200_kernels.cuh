@@ -22,12 +22,26 @@ struct IpmVecs
     double *trace;            // [SB200_TRACE_ROWS][SB200_TRACE_COLS]
 };
 
+// Pattern-only, vector-blocked copy of a +/-1 matrix (sb200_blocked.cu): entries ordered by
+// (block of the dense vector, major), 2 bytes each = 15-bit index local to the block + sign bit.
+struct BlockedPattern
+{
+    int majors = 0, minors = 0;     // rows x cols for the A v copy, cols x rows for the A' v copy
+    int nb = 0, nblk = 0;           // vector block size (doubles) and number of blocks
+    long long nnz = 0;
+    unsigned n_chunks = 0;          // 16-byte chunks (8 entries) stored; every segment is a whole number of chunks
+    unsigned *ptr = nullptr;        // [nblk * majors + 1] segment bounds in chunks
+    unsigned short *ent = nullptr;  // [8 * n_chunks]; the pad of a segment's last chunk points at the zero slot
+    double *partial = nullptr;      // [nblk][majors] per-block sums (A v copy only)
+};
+
 struct CsrView
 {
     int m;
     const int *offs;
     const int *inds;
     const double *vals;
+    const BlockedPattern *blk = nullptr;   // host pointer; set => the blocked kernels are used
 };
 struct CscView
 {
@@ -36,6 +50,7 @@ struct CscView
     const int *rows;
     const double *vals;
     int lanes;                // lanes per column used by the kernels (power of two <= 32)
+    const BlockedPattern *blk = nullptr;
 };
 
 // CSC epilogue modes
@@ -72,6 +87,18 @@ void launch_jacobi_diag(const CsrView &A, const double *d, double *diag, cudaStr
 void launch_spmv_csc(const CscView &A, int mode, const double *v, const double *z, double *out,
                      double alpha, double beta, const IpmVecs *V, cudaStream_t st);
 int pick_csc_lanes(long long nnz, int n);
+
+// ---- sb200_blocked.cu ------------------------------------------------------------------------
+int build_blocked(ErrorSink &err, int majors, int minors, long long nnz, const int *mptr, const int *midx,
+                  const double *vals, int nb, bool with_partials, BlockedPattern *out, cudaStream_t st);
+void free_blocked(BlockedPattern *p);
+int blocked_nb_for_rows(int n);
+int blocked_nb_for_cols(int m);
+void launch_blk_spmv_rows(const BlockedPattern &B, const double *x, const double *z, double *out, double alpha,
+                          double beta, cudaStream_t st);
+void launch_blk_jacobi_diag(const BlockedPattern &B, const double *d, double *diag, cudaStream_t st);
+void launch_blk_spmv_cols(const BlockedPattern &B, int mode, const double *v, const double *z, double *out,
+                          double alpha, double beta, const IpmVecs *V, cudaStream_t st);
 
 // ---- sb200_chol.cu ---------------------------------------------------------------------------
 // (launch_potrf / launch_potrs: sb200_chol.cuh)

@@ -189,10 +189,16 @@ void launch_cg_iteration(const CsrView &A, const CscView &At, const PcgVecs &C, 
 {
     // q = D A'p : CSC gather with the scale epilogue; V.d holds D; early exit on cg_done
     launch_spmv_csc_cg(At, C.p, C.q, C.dscale, V.sc, st);
-    k_cg_matvec<<<grid_for((long long)A.m * 32, 256), 256, 0, st>>>(A, C, V.sc);
+    if (A.blk)
+        launch_blk_cg_matvec(*A.blk, C, V.sc, st);
+    else
+    {
+        k_cg_matvec<<<grid_for((long long)A.m * 32, 256), 256, 0, st>>>(A, C, V.sc);
+        ++g_launch_count;
+    }
     k_cg_update<<<grid_for(C.m, kBlock), kBlock, 0, st>>>(C, V.sc, P, max_iter_override);
     k_cg_direction<<<grid_for(C.m, kBlock), kBlock, 0, st>>>(C, V.sc);
-    g_launch_count += 3;
+    g_launch_count += 2;
 }
 
 void launch_cg_check(Scalars *sc, cudaStream_t st)

@@ -22,6 +22,10 @@ void launch_cg_init(const PcgVecs &C, Scalars *sc, const DevParams *P, double fi
 void launch_cg_iteration(const CsrView &A, const CscView &At, const PcgVecs &C, const IpmVecs &V,
                          const DevParams *P, int max_iter_override, cudaStream_t st);
 void launch_cg_check(Scalars *sc, cudaStream_t st);
+// sb200_blocked.cu: the two products of a CG iteration on the blocked pattern
+void launch_blk_cg_matvec(const BlockedPattern &B, const PcgVecs &C, Scalars *sc, cudaStream_t st);
+void launch_blk_cg_cols(const BlockedPattern &B, const double *p, double *q, const double *dscale, const Scalars *sc,
+                        cudaStream_t st);
 void launch_spmv_csc_cg(const CscView &A, const double *p, double *q, const double *dscale,
                         const Scalars *sc, cudaStream_t st);
 

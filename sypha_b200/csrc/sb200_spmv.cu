@@ -48,12 +48,14 @@ k_spmv_csr(int m, const int *__restrict__ offs, const int *__restrict__ inds,
 void launch_spmv_csr(const CsrView &A, const double *x, const double *z, double *out, double alpha,
                      double beta, cudaStream_t st)
 {
+    if (A.blk) return launch_blk_spmv_rows(*A.blk, x, z, out, alpha, beta, st);
     const int grid = grid_for((long long)A.m * 32, 256, 148 * 16);
     k_spmv_csr<0><<<grid, 256, 0, st>>>(A.m, A.offs, A.inds, A.vals, x, z, out, alpha, beta);
     ++g_launch_count;
 }
 void launch_jacobi_diag(const CsrView &A, const double *d, double *diag, cudaStream_t st)
 {
+    if (A.blk) return launch_blk_jacobi_diag(*A.blk, d, diag, st);
     const int grid = grid_for((long long)A.m * 32, 256, 148 * 16);
     k_spmv_csr<1><<<grid, 256, 0, st>>>(A.m, A.offs, A.inds, A.vals, d, nullptr, diag, 1.0, 0.0);
     ++g_launch_count;
@@ -178,6 +180,7 @@ static void launch_csc_g(const CscView &A, int mode, const double *v, const doub
 void launch_spmv_csc(const CscView &A, int mode, const double *v, const double *z, double *out,
                      double alpha, double beta, const IpmVecs *Vp, cudaStream_t st)
 {
+    if (A.blk) return launch_blk_spmv_cols(*A.blk, mode, v, z, out, alpha, beta, Vp, st);
     IpmVecs V{};
     if (Vp) V = *Vp;
     switch (A.lanes)
@@ -221,6 +224,7 @@ k_spmv_csc_cg(int n, const int *__restrict__ colptr, const int *__restrict__ row
 void launch_spmv_csc_cg(const CscView &A, const double *p, double *q, const double *dscale,
                         const Scalars *sc, cudaStream_t st)
 {
+    if (A.blk) return launch_blk_cg_cols(*A.blk, p, q, dscale, sc, st);
 #define SB200_CG_CASE(G)                                                                           \
     case G:                                                                                        \
         k_spmv_csc_cg<G><<<grid_for((long long)A.n * G, 256, 148 * 16), 256, 0, st>>>(             \

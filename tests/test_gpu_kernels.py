@@ -163,3 +163,74 @@ def test_syrk_dmma(lib, shape):
     got = Cd.cpu().numpy()
     il = np.tril_indices(ld)
     assert np.max(np.abs(got[il] - ref[il])) <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(40, 300, 0.1), (700, 40000, 0.01), (30000, 70000, 0.0005)])
+def test_blocked_pattern_products(lib, shape):
+    """+/-1 matrices loaded for the PCG strategy use the pattern-only, shared-memory-staged products
+    (sb200_blocked.cu); they must agree with the value-carrying kernels / SciPy on A x and A' v, for one
+    and for several blocks of the dense vector (n > 16384, m > 13312)."""
+    import sypha_b200 as sb
+    m, n0, dens = shape
+    r = np.random.default_rng(m)
+    A0 = sp.random(m, n0, density=dens, format="csr", random_state=r, data_rvs=lambda k: np.ones(k))
+    A = sp.hstack([A0, -sp.identity(m)], format="csr")       # standard form [A0 | -I]
+    A.sort_indices()
+    n = n0 + m
+    env = sb.SyphaEnvironment(linearSolverStrategy="pcg")
+    node = sb.SyphaNodeSparse.from_csr(m, n, n0, A.indptr.astype(np.int32), A.indices.astype(np.int32),
+                                       A.data.astype(np.float64), np.ones(n), np.ones(m), env)
+    ws = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(ws)
+    try:
+        node.copyModelOnDevice(ws)
+        info = (C.c_longlong * 16)()
+        lib.sb200_model_info(ws.handle, info, 16)
+        assert info[12] == 1, "blocked pattern was not built for a +/-1 PCG model"
+        if n > 16384:
+            assert info[13] > 1
+        if m > 13312:
+            assert info[14] > 1
+        x, v = r.normal(size=n), r.normal(size=m)
+        X, Y = dev(x), torch.empty(m, dtype=torch.float64, device="cuda")
+        assert lib.sb200_ws_spmv(ws.handle, 0, ptr(X), ptr(Y)) == 0
+        ref = A @ x
+        assert np.allclose(Y.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+        V, Z = dev(v), torch.empty(n, dtype=torch.float64, device="cuda")
+        assert lib.sb200_ws_spmv(ws.handle, 1, ptr(V), ptr(Z)) == 0
+        ref = A.T @ v
+        assert np.allclose(Z.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+        # deterministic: bit-identical on repetition
+        Z2 = torch.empty(n, dtype=torch.float64, device="cuda")
+        lib.sb200_ws_spmv(ws.handle, 1, ptr(V), ptr(Z2))
+        assert torch.equal(Z, Z2)
+    finally:
+        sb.releaseIpmWorkspace(ws)
+
+
+def test_general_coefficients_keep_value_kernels(lib):
+    """a cut row with a coefficient 2 must not take the pattern-only path."""
+    import sypha_b200 as sb
+    m, n = 30, 200
+    r = np.random.default_rng(5)
+    A = sp.random(m, n, density=0.2, format="csr", random_state=r, data_rvs=lambda k: np.ones(k))
+    A = A.tolil()
+    A[3, 7] = 2.0
+    A = A.tocsr()
+    A.sort_indices()
+    env = sb.SyphaEnvironment(linearSolverStrategy="pcg")
+    node = sb.SyphaNodeSparse.from_csr(m, n, n, A.indptr.astype(np.int32), A.indices.astype(np.int32),
+                                       A.data.astype(np.float64), np.ones(n), np.ones(m), env)
+    ws = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(ws)
+    try:
+        node.copyModelOnDevice(ws)
+        info = (C.c_longlong * 16)()
+        lib.sb200_model_info(ws.handle, info, 16)
+        assert info[12] == 0
+        x = r.normal(size=n)
+        X, Y = dev(x), torch.empty(m, dtype=torch.float64, device="cuda")
+        assert lib.sb200_ws_spmv(ws.handle, 0, ptr(X), ptr(Y)) == 0
+        assert np.allclose(Y.cpu().numpy(), A @ x, rtol=1e-12)
+    finally:
+        sb.releaseIpmWorkspace(ws)

@@ -42,6 +42,9 @@ WORKLOADS = {
 }
 N_INSTANCES = 5
 MAX_ITER = 100
+# FP64 tensor-pipe (DMMA) peak measured on this pool with scripts/dfma (33.2 TFLOP/s; nominal 40):
+# MEASURED_PEAKS.json carries no FP64 entry
+FP64_DMMA_TFLOPS = 33.2
 
 
 def read_peaks():
@@ -86,6 +89,57 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def read_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch group from the committed ncu --set full captures."""
+    p = REPO / "profiles" / "traffic.json"
+    if p.exists():
+        return {k: v for k, v in json.load(open(p)).items() if not k.startswith("_")}
+    return {}
+
+
+def pcg_block(lib, sb, local_rank, peak):
+    """Secondary measurement: one CG iteration of the matrix-free normal-equations solve on the
+    50k x 1M synthetic instance (BASELINE.json configs[3]) - CUDA events, model resident."""
+    import ctypes as C
+    from sypha_b200.instances import gen_scp
+    m, n0, dens, desc = WORKLOADS["synth50k"]
+    mdl = gen_scp(m, n0, dens, 1)
+    env = sb.SyphaEnvironment(cudaDeviceId=local_rank, linearSolverStrategy="pcg")
+    node = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+    ws = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(ws, device=local_rank)
+    try:
+        t0 = time.perf_counter()
+        node.copyModelOnDevice(ws)
+        load_s = time.perf_counter() - t0
+        info = (C.c_longlong * 20)()
+        lib.sb200_model_info(ws.handle, info, 20)
+        out = {"workload": desc, "m": mdl.m, "n": mdl.n, "nnz": int(mdl.nnz), "load_model_s": load_s,
+               "representation": ("pattern-only 2-byte entries in 16-byte chunks, vector blocks staged in shared memory"
+                                  if info[12] else "value-carrying CSR/CSC")}
+        ms = C.c_double()
+        for pid, nm in ((6, "cg_iteration"), (7, "At_p"), (8, "A_q")):
+            if lib.sb200_time_phase(ws.handle, pid, 20, C.byref(ms)) == 0:
+                out[nm + "_us"] = 1e3 * ms.value
+        if "cg_iteration_us" in out:
+            nseg_r, nseg_c = info[13] * mdl.m, info[14] * mdl.n
+            # bytes our representation moves per CG iteration: entry chunks + segment bounds of both copies,
+            # the per-block partial sums of A q (written + read), q written + read, d, and 10 m-vector passes
+            ours = (16 * (info[15] + info[16]) + 4 * (nseg_r + nseg_c) + 16 * nseg_r + 8 * 3 * mdl.n + 8 * 10 * mdl.m
+                    if info[12] else 2 * 12 * int(mdl.nnz) + 8 * (3 * mdl.n + 10 * mdl.m))
+            survey = 2 * 12 * int(mdl.nnz) + 8 * (3 * mdl.n + 10 * mdl.m)      # SURVEY.md 8(d): 12 B per stored entry
+            t = out["cg_iteration_us"] * 1e-6
+            out["roofline"] = {"bound": "hbm", "kernel": "one CG iteration (A'p, A q, 2 fused vector kernels)",
+                               "algorithmic_bytes": ours, "achieved": ours / t / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": ours / t / 1e9 / peak,
+                               "csr12_equivalent_bytes": survey, "csr12_equivalent_gbs": survey / t / 1e9,
+                               "traffic": read_traffic().get("cg_iteration")}
+            out["cg_iterations_per_sec"] = 1.0 / t
+        return out
+    finally:
+        sb.releaseIpmWorkspace(ws)
+
+
 def algorithmic_bytes(info, phase):
     """Algorithmic bytes (or flops) of one launch group, DESIGN.md 'Kernels'."""
     m, n, nnz, mpad, n_pairs, n_terms, general = (info["m"], info["n"], info["nnz"], info["mpad"],
@@ -121,6 +175,9 @@ def run_ours(args, rank, world, local_rank):
     lib = L.load()
     m, n0, dens, desc = WORKLOADS[args.workload]
     strategy = args.strategy
+    global N_INSTANCES
+    if args.workload == "synth50k":
+        N_INSTANCES = 1           # 1.3 GB of structure per instance: larger than L2 on its own
     models = [gen_scp(m, n0, dens, 1000 * rank + i + 1) for i in range(N_INSTANCES)]
 
     env = sb.SyphaEnvironment(cudaDeviceId=local_rank, linearSolverStrategy=strategy,
@@ -159,10 +216,14 @@ def run_ours(args, rank, world, local_rank):
     results = [step(i) for i in range(args.steps)]
     barrier()
     elapsed = time.perf_counter() - t0
+    wall = elapsed
     iters = sum(r.iterations for r in results)
     launches = sum(r.kernelsLaunched for r in results)
+    # timed on the device: CUDA events on the workspace stream around every LP (start point, initial
+    # residuals, loop); LPs run back to back, so the sum is this rank's device time for the K steps
     dev_ms = sum(r.msStart + r.msSetup + r.msLoop for r in results)
     loop_ms = sum(r.msLoop for r in results)
+    elapsed = dev_ms / 1e3
 
     # ---- e2e: host buffers in, host results out, every step ---------------------------------
     e2e_ws = sb.IpmWorkspace()
@@ -202,9 +263,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- max over ranks / sums ----------------------------------------------------------------
     if dist:
-        t = torch.tensor([elapsed, e2e_elapsed], device="cuda", dtype=torch.float64)
+        t = torch.tensor([elapsed, e2e_elapsed, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed, e2e_elapsed = float(t[0]), float(t[1])
+        elapsed, e2e_elapsed, wall = float(t[0]), float(t[1]), float(t[2])
         c = torch.tensor([iters, launches, e2e_iters], device="cuda", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         iters, launches, e2e_iters = int(c[0]), int(c[1]), int(c[2])
@@ -234,9 +295,19 @@ def run_ours(args, rank, world, local_rank):
                     "frac": ph["frac_hbm"], "traffic": None, "peak_source": peak_src,
                     "ms_per_launch_group": ph["ms"], "algorithmic_bytes": ph["algorithmic_bytes"]}
             if dom in ("potrf",):
+                # the factorisation runs on the FP64 tensor pipe (DMMA): m^3/3 flops per launch
                 flops = info["m"] ** 3 / 3.0
-                roof["flops"] = flops
-                roof["tflops"] = flops / ph["ms"] / 1e9
+                tf = flops / ph["ms"] / 1e9
+                roof.update({"bound": "tensor", "achieved": tf, "peak": FP64_DMMA_TFLOPS, "unit": "TFLOP/s",
+                             "frac": tf / FP64_DMMA_TFLOPS, "flops": flops,
+                             "peak_source": "FP64 DMMA rate measured on this pool with scripts/dfma (MEASURED_PEAKS.json "
+                                            "has no FP64 entry; nominal 40 TFLOP/s)",
+                             "hbm_gbs": ph["gbs"], "hbm_frac": ph["frac_hbm"],
+                             "note": "latency-bound at m = 1000: 16 dependent 64-column steps (pivot chain + one "
+                                     "hand-off each); see profiles/ for the per-step timeline"})
+            tr = read_traffic().get(dom)
+            if tr is not None:
+                roof["traffic"] = tr
         out = {
             "metric": "ipm_iterations_per_sec", "value": iters / elapsed, "unit": "iter/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
@@ -248,6 +319,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"{N_INSTANCES} rotating instances, working set > 126 MB L2 (no flush needed)",
                        "poll_every": args.poll_every, "graph": not args.no_graph},
             "time_to_lp_opt_ms": 1e3 * elapsed / args.steps,
+            "timing": "CUDA events on the workspace stream around every LP, summed over the K steps, max over ranks",
+            "wall_ms_per_step": 1e3 * wall / args.steps,
             "iterations_per_lp": iters / (args.steps * world),
             "device_ms_per_lp": dev_ms / args.steps, "loop_ms_per_lp": loop_ms / args.steps,
             "e2e": ({"value": e2e_iters / e2e_elapsed, "unit": "iter/s", "h2d_bytes_per_step": h2d,
@@ -258,6 +331,11 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof,
             "phases": phases,
         }
+        if world == 1 and not args.no_pcg_block and args.workload != "synth50k":
+            try:
+                out["pcg_50kx1M"] = pcg_block(lib, sb, local_rank, peak)
+            except Exception as e:           # never lose the headline line to the secondary measurement
+                out["pcg_50kx1M"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(models[0], budget_s=args.cpu_budget)
     for ws in wss + [e2e_ws]:
@@ -336,6 +414,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
+    ap.add_argument("--no-pcg-block", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--cg-max-iter", type=int, default=50000)
     ap.add_argument("--cg-tol", type=float, default=1e-8)

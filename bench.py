@@ -140,11 +140,102 @@ def pcg_block(lib, sb, local_rank, peak):
         sb.releaseIpmWorkspace(ws)
 
 
+def run_bnb(args, rank, world, local_rank):
+    """B&B nodes/s (BASELINE.json configs[4]): scpnre-shaped synthetic instance, batched node LPs on every
+    GPU, ranks work on disjoint parts of the frontier, NCCL carries only the incumbent."""
+    import torch
+    import sypha_b200 as sb
+    from sypha_b200 import bnb, bnb_exchange
+    from sypha_b200.instances import gen_scp
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    m, n0, dens = 500, 5000, 0.10
+    mdl = gen_scp(m, n0, dens, 77)                 # same instance on every rank
+    exch_bytes = [0]
+
+    def exchange(obj, x):
+        if dist is None:
+            return obj, x
+        xt = None if x is None else torch.from_numpy(np.asarray(x, dtype=np.float64))
+        best, bx, owner = bnb_exchange.exchange_incumbent(obj, xt, n0)
+        exch_bytes[0] += 16 + 8 * n0
+        return best, (None if bx is None else bx.cpu().numpy())
+
+    drv = bnb.BatchedBnb(mdl, slots=args.slots, device=local_rank, exchange=exchange)
+    # every rank expands the same first levels (deterministic), then keeps its round-robin share
+    while len(drv.frontier) < world * args.slots and drv.frontier:
+        drv.round()
+    warm_nodes = drv.stats.processed
+    mine = bnb_exchange.partition_round_robin(list(drv.frontier), rank, world)
+    drv.frontier.clear()
+    drv.frontier.extend(mine)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    before = drv.stats.processed
+    dev_before = drv.stats.lp_device_ms
+    it_before = drv.stats.lp_iterations
+    kl_before = drv.stats.kernels_launched
+    t0 = time.perf_counter()
+    drv.run(max_nodes=10 ** 9, rounds=args.steps)          # a step = one round (window of K node LPs)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    sampler.stop_evt.set()
+    sampler.join(timeout=2)
+    nodes = drv.stats.processed - before
+    iters = drv.stats.lp_iterations - it_before
+    dev_ms = drv.stats.lp_device_ms - dev_before
+    launches = drv.stats.kernels_launched - kl_before
+    if dist:
+        elapsed, (nodes, iters, dev_ms, launches) = bnb_exchange.reduce_counters(elapsed, [nodes, iters, dev_ms, launches])
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "bnb_nodes_per_sec", "value": nodes / elapsed, "unit": "nodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm_nodes, "ms_per_step": 1e3 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "branch-and-bound on an scpnre-shaped synthetic SCP 500x5000, 10% density "
+                                   "(configs[4]); a step = one round of K batched node LPs per GPU",
+                       "slots_per_gpu": args.slots, "node_lp": "Mehrotra IPM to mu <= 1e-4, max_iter 100",
+                       "frontier": "FIFO, most-fractional branching, round-robin split across ranks",
+                       "collective": "all_reduce(MIN) of the incumbent objective + broadcast of the incumbent vector per round"},
+            "timing": "wall clock between device synchronisations around the K rounds, max over ranks "
+                      "(host node construction, upload, LP solves, heuristics, incumbent exchange)",
+            "nodes": int(nodes), "lp_iterations": int(iters), "lp_device_ms_per_node": dev_ms / max(nodes, 1),
+            "incumbent": drv.stats.incumbent, "root_bound": drv.stats.root_bound,
+            "incumbent_exchange_bytes_per_round": (16 + 8 * n0) if dist else 0,
+            "e2e": {"value": nodes / elapsed, "unit": "nodes/s",
+                    "h2d_bytes_per_step": int(args.slots * (mdl.offs.nbytes + mdl.inds.nbytes + mdl.vals.nbytes + mdl.c.nbytes + mdl.b.nbytes)),
+                    "d2h_bytes_per_step": int(args.slots * 8 * (2 * mdl.n + mdl.m)),
+                    "note": "every node model is built on the host and uploaded inside the timed region: value IS end to end"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+    drv.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
 def algorithmic_bytes(info, phase):
     """Algorithmic bytes (or flops) of one launch group, DESIGN.md 'Kernels'."""
     m, n, nnz, mpad, n_pairs, n_terms, general = (info["m"], info["n"], info["nnz"], info["mpad"],
                                                   info["n_pairs"], info["n_terms"], info["general"])
     if phase == "assemble":      # term stream + entry pointers + M written once
+        if info.get("pat_chunks"):                       # compact form: 16-byte chunks of 2-byte column ids
+            return info["pat_chunks"] * 16 + n_pairs * 4 + n_pairs * 8
         return n_terms * (12 if general else 4) + n_pairs * 4 + n_pairs * 8
     if phase == "potrf":         # M read once + L written once (lower triangles)
         return 2 * 8 * m * (m + 1) // 2
@@ -273,10 +364,10 @@ def run_ours(args, rank, world, local_rank):
     out = None
     if rank == 0:
         # ---- per-phase device timing (CUDA events on the workspace stream) and the roofline ---
-        info_arr = (C.c_longlong * 12)()
-        lib.sb200_model_info(wss[0].handle, info_arr, 12)
+        info_arr = (C.c_longlong * 20)()
+        lib.sb200_model_info(wss[0].handle, info_arr, 20)
         info = dict(m=info_arr[0], n=info_arr[1], nnz=info_arr[3], mpad=info_arr[4], strategy=info_arr[5],
-                    n_pairs=info_arr[6], n_terms=info_arr[7], general=info_arr[8])
+                    n_pairs=info_arr[6], n_terms=info_arr[7], general=info_arr[8], pat_chunks=info_arr[17])
         peak, peak_src = read_peaks()
         phases = {}
         names = {0: "assemble", 1: "potrf", 2: "potrs", 3: "spmv_csr", 4: "spmv_csc_recover", 5: "vector"}
@@ -407,7 +498,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="scpnrh", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="scpnrh", choices=sorted(WORKLOADS) + ["bnb"])
+    ap.add_argument("--slots", type=int, default=16, help="bnb: concurrent node LPs per GPU")
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--poll-every", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
@@ -432,7 +524,10 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
-        out = run_ours(args, rank, world, local_rank)
+        if args.workload == "bnb":
+            out = run_bnb(args, rank, world, local_rank)
+        else:
+            out = run_ours(args, rank, world, local_rank)
     sys.stdout.flush()
     if out is not None:
         os.write(real_stdout, (json.dumps(out) + "\n").encode())

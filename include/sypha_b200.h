@@ -139,6 +139,16 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz,
 
 /* ---- solve ---------------------------------------------------------------------------------- */
 int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result);
+/* Turn the resident BASE model into the model of one B&B node (base + appended branch rows,
+ * build_branch_model, src/sypha_solver_bnb.cpp:418-490) ON THE DEVICE: no host CSR copy, no re-upload, no
+ * new symbolic structure (replaces the per-node build + SyphaNodeSparse::copyModelOnDevice of
+ * src/sypha_solver_bnb_driver.cpp:807-826).  delta == NULL or n_extra_rows == 0 restores the base model.
+ * The workspace must have been created with sb200_caps covering the deepest node (m, n, nnz + 2 per row);
+ * direct (sparse-assembly + Cholesky) strategy only, otherwise SB200_ERR_UNSUPPORTED.  The next
+ * sb200_solve / x_host, y_host, s_host have the node's dimensions (m + k, n + k). */
+int sb200_set_node_delta(sb200_ws *ws, const sb200_node_delta *delta);
+/* k independent LPs, one workspace (own stream) each, solved concurrently.  deltas == NULL: the
+ * workspaces' resident models as they are; otherwise deltas[i] is applied to wss[i] first. */
 int sb200_solve_batch(sb200_ws **ws, int k, const sb200_node_delta *deltas,
                       const sb200_params *params, sb200_result *results);
 

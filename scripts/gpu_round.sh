@@ -1,10 +1,14 @@
 #!/usr/bin/env bash
-# bench line + ncu launch list + ncu --set full on the three dominant direct-path kernels
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pcg-block --no-e2e --no-phases"
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err
-$CMD > gpurun_out/plain_c.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_c.csv $CMD > gpurun_out/ncu_c1.log 2>&1
-$CMD > gpurun_out/plain_c2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "regex:k_potrf_df|k_trsv_df|k_assemble_normal" -s 30 -c 6 -o gpurun_out/prof_direct $CMD > gpurun_out/ncu_c2.log 2>&1
-cat gpurun_out/bench_f.json; tail -3 gpurun_out/ncu_c1.log gpurun_out/ncu_c2.log
+{
+  echo "== pytest bnb"; timeout 900 python -m pytest tests/test_gpu_bnb.py -x -q 2>&1 | tail -12
+  for s in 1 4 8 16 32; do echo "== bnb slots $s"; timeout 600 python bench.py --workload bnb --steps 12 --slots $s 2>> gpurun_out/bench_bnb.err; done
+} > gpurun_out/round12.log 2>&1
+python - <<'PY'
+import json
+for l in open('gpurun_out/round12.log'):
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','nodes','lp_iterations','lp_device_ms_per_node','incumbent','root_bound')}, d['config']['slots_per_gpu'])
+    else: print(l.rstrip())
+PY
+tail -5 gpurun_out/bench_bnb.err

@@ -60,6 +60,7 @@ SYMBOLS = {
     "sb200_default_params": (None, [C.POINTER(sb200_params)]),
     "sb200_load_model": (_i, [_vp, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "sb200_solve": (_i, [_vp, C.POINTER(sb200_params), C.POINTER(sb200_result)]),
+    "sb200_set_node_delta": (_i, [_vp, C.POINTER(sb200_node_delta)]),
     "sb200_solve_batch": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_node_delta), C.POINTER(sb200_params),
                                C.POINTER(sb200_result)]),
     "sb200_get_trace": (_i, [_vp, _vp, _i]),

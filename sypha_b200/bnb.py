@@ -1,0 +1,236 @@
+"""Batched branch-and-bound node loop on top of the LP hot path.
+
+The reference's driver (/root/reference/src/sypha_solver_bnb_driver.cpp:698-1046) pops ONE node at a time
+from a FIFO frontier, rebuilds its model on the host (``build_branch_model``,
+/root/reference/src/sypha_solver_bnb.cpp:418-490), re-uploads it and solves its LP.  Its search logic is
+out of scope here; what this module restructures is the node BODY: a window of K open nodes is popped
+per round and their LP relaxations are solved concurrently on one GPU (one persistent workspace and
+stream per slot, ``sb200_solve_batch``), and with several ranks every rank works on its own part of the
+frontier and only the incumbent travels (``bnb_exchange``).  The combinatorial parts kept on the host
+are deliberately the plain versions of the reference's: breadth-first order, most-fractional branching
+(sypha_solver_heuristics.cpp ``MostFractional``), nearest-integer rounding with greedy repair for
+incumbents, pruning by the parent / node dual bound with integer costs.
+"""
+from __future__ import annotations
+
+import collections
+import dataclasses
+import math
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .instances import ScpModel
+from .solver import (CODE_SUCCESSFUL, IpmWorkspace, SolverExecutionConfig, SolverGapStagnationConfig,
+                     SyphaEnvironment, SyphaNodeSparse, initializeIpmWorkspace, releaseIpmWorkspace, solve_batch,
+                     solve_batch_nodes, workspace_for_nodes)
+
+TERM_CONVERGED, TERM_MAX_ITER, TERM_GAP_STALLED, TERM_NUMERICAL = 0, 1, 2, 3
+
+
+def build_branch_model(base: ScpModel, decisions: Sequence[Tuple[int, int]]) -> ScpModel:
+    """Node model = base + one row per branching decision (bnb.cpp:453-468): row = (fix == 0 ? -1 : +1) at
+    ``var`` and -1 at a fresh slack column, rhs = fix, slack cost 0."""
+    k = len(decisions)
+    if k == 0:
+        return base
+    nnz = base.nnz
+    offs = np.concatenate([base.offs.astype(np.int64), base.offs[-1] + 2 * np.arange(1, k + 1, dtype=np.int64)])
+    inds = np.empty(nnz + 2 * k, dtype=np.int32)
+    vals = np.empty(nnz + 2 * k, dtype=np.float64)
+    inds[:nnz], vals[:nnz] = base.inds, base.vals
+    var = np.fromiter((d[0] for d in decisions), dtype=np.int32, count=k)
+    fix = np.fromiter((d[1] for d in decisions), dtype=np.float64, count=k)
+    inds[nnz::2], vals[nnz::2] = var, np.where(fix == 0.0, -1.0, 1.0)
+    inds[nnz + 1::2], vals[nnz + 1::2] = base.n + np.arange(k, dtype=np.int32), -1.0
+    return ScpModel(base.m + k, base.n + k, base.n_orig, offs.astype(np.int32), inds, vals,
+                    np.concatenate([base.c, np.zeros(k)]), np.concatenate([base.b, fix]), base.name + f"+{k}br")
+
+
+class CoverHeuristic:
+    """Nearest-integer rounding of the LP point, greedy repair of uncovered rows by cost per newly covered
+    row (gains kept up to date incrementally: O(nnz) per call), then removal of redundant columns (most
+    expensive first).  Host-side NumPy on the CSR / CSC lists of A0."""
+
+    def __init__(self, base: ScpModel):
+        import scipy.sparse as sp
+        m, n0 = base.m, base.n_orig
+        A = sp.csr_matrix((base.vals, base.inds, base.offs), shape=(m, base.n))[:, :n0]
+        self.A = sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=(m, n0))
+        At = self.A.T.tocsr()
+        self.col_ptr, self.col_rows = At.indptr, At.indices
+        self.row_ptr, self.row_cols = self.A.indptr, self.A.indices
+        self.c = base.c[:n0]
+        self.m, self.n0 = m, n0
+
+    def _rows(self, j):
+        return self.col_rows[self.col_ptr[j]:self.col_ptr[j + 1]]
+
+    def __call__(self, x_lp: np.ndarray, fixed_zero=()) -> Tuple[float, Optional[np.ndarray]]:
+        x = (x_lp[:self.n0] >= 0.5).astype(np.float64)
+        banned = np.zeros(self.n0, dtype=bool)
+        if len(fixed_zero):
+            banned[list(fixed_zero)] = True
+            x[banned] = 0.0
+        cover = self.A @ x
+        unc = cover < 0.5
+        if unc.any():
+            gain = self.A.T @ unc.astype(np.float64)           # rows each column would newly cover
+            usable = ~banned & (x == 0.0)
+            while unc.any():
+                score = np.where(usable & (gain > 0.5), self.c / np.maximum(gain, 0.5), np.inf)
+                j = int(np.argmin(score))
+                if not np.isfinite(score[j]):
+                    return math.inf, None                      # infeasible under the fixings
+                x[j] = 1.0
+                usable[j] = False
+                rows = self._rows(j)
+                cover[rows] += 1.0
+                new = rows[unc[rows]]
+                unc[new] = False
+                if len(new):                                   # those rows no longer count for anybody's gain
+                    touched = np.concatenate([self.row_cols[self.row_ptr[i]:self.row_ptr[i + 1]] for i in new])
+                    gain -= np.bincount(touched, minlength=self.n0)
+        chosen = np.nonzero(x)[0]
+        for j in chosen[np.argsort(-self.c[chosen], kind="stable")]:   # drop redundant columns, dearest first
+            rows = self._rows(j)
+            if np.all(cover[rows] >= 1.5):
+                x[j] = 0.0
+                cover[rows] -= 1.0
+        return float(self.c @ x), x
+
+
+@dataclasses.dataclass
+class BnbNode:
+    decisions: Tuple[Tuple[int, int], ...]
+    parent_bound: float
+
+
+@dataclasses.dataclass
+class BnbStats:
+    processed: int = 0
+    lp_iterations: int = 0
+    pruned_by_bound: int = 0
+    infeasible: int = 0
+    integral: int = 0
+    rounds: int = 0
+    incumbent: float = math.inf
+    lp_device_ms: float = 0.0
+    kernels_launched: int = 0
+    wall_s: float = 0.0
+    open_nodes: int = 0
+    root_bound: float = -math.inf
+
+
+class BatchedBnb:
+    """K LP slots on one GPU.  ``run(max_nodes)`` processes the frontier in windows of K nodes."""
+
+    def __init__(self, base: ScpModel, slots: int = 8, device: int = 0, max_iter: int = 100,
+                 exchange=None, integer_costs: bool = True, device_nodes: bool = True, max_depth: int = 64):
+        self.base = base
+        self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
+        self.max_depth = max_depth
+        self.env = SyphaEnvironment(cudaDeviceId=device)
+        # The reference runs node LPs with a gap-stagnation early exit (bnb_driver.cpp:835-837) and prunes with
+        # whatever dual objective the LP stopped at - not a bound before convergence (53.08 vs the
+        # LP optimum 48.12 on scpnrh1).  Here node LPs run to mu <= mu_tol and only converged LPs bound.
+        self.cfg = SolverExecutionConfig(maxIterations=max_iter, gapStagnation=SolverGapStagnationConfig(False, 0, 0.0))
+        self.slots = slots
+        self.ws: List[IpmWorkspace] = []
+        self.base_node = SyphaNodeSparse.from_csr(base.m, base.n, base.n_orig, base.offs, base.inds, base.vals,
+                                                  base.c, base.b, self.env)
+        for _ in range(slots):
+            if device_nodes:
+                self.ws.append(workspace_for_nodes(self.base_node, max_depth, device))   # base model resident
+            else:
+                w = IpmWorkspace()
+                initializeIpmWorkspace(w, device=device)
+                self.ws.append(w)
+        self.heur = CoverHeuristic(base)
+        self.frontier: collections.deque = collections.deque([BnbNode((), -math.inf)])
+        self.incumbent = math.inf
+        self.incumbent_x: Optional[np.ndarray] = None
+        self.integer_costs = integer_costs
+        self.exchange = exchange            # callable(obj, x) -> (obj, x) across ranks, or None
+        self.stats = BnbStats()
+
+    def close(self):
+        for w in self.ws:
+            releaseIpmWorkspace(w)
+        self.ws = []
+
+    # a node whose bound cannot beat the incumbent is dropped (integer costs: bound rounds up)
+    def _prunable(self, bound: float) -> bool:
+        if not math.isfinite(self.incumbent):
+            return False
+        # the LP objective at mu <= 1e-4 is good to ~1e-5 relative: keep a 1e-4 safety margin
+        bound = bound - 1e-4 * max(1.0, abs(bound))
+        b = math.ceil(bound) if self.integer_costs else bound
+        return b >= self.incumbent - (1e-9 if self.integer_costs else 1e-6 * max(1.0, abs(self.incumbent)))
+
+    def _offer(self, obj: float, x: Optional[np.ndarray]):
+        if x is not None and obj < self.incumbent:
+            self.incumbent, self.incumbent_x = obj, x
+
+    def round(self) -> int:
+        """Pop up to K nodes, solve their LPs as one batch, branch.  Returns the number processed."""
+        batch: List[BnbNode] = []
+        while self.frontier and len(batch) < self.slots:
+            nd = self.frontier.popleft()                       # FIFO, bnb.cpp:42-43
+            if self._prunable(nd.parent_bound):                # bnb_driver.cpp:797
+                self.stats.pruned_by_bound += 1
+                continue
+            batch.append(nd)
+        if batch:
+            if self.device_nodes and all(len(nd.decisions) <= self.max_depth for nd in batch):
+                results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self.ws)
+            else:
+                nodes = []
+                for nd in batch:
+                    mdl = build_branch_model(self.base, nd.decisions)
+                    nodes.append(SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals,
+                                                          mdl.c, mdl.b, self.env))
+                results = solve_batch(nodes, self.cfg, self.ws[:len(nodes)])
+                self.device_nodes = False      # the slots no longer hold the base model
+            for nd, res in zip(batch, results):
+                self.stats.processed += 1
+                self.stats.lp_iterations += res.iterations
+                self.stats.lp_device_ms += res.msStart + res.msSetup + res.msLoop
+                self.stats.kernels_launched += int(res.kernelsLaunched)
+                ok = res.status == CODE_SUCCESSFUL and res.terminationReason == TERM_CONVERGED
+                if not ok or not np.isfinite(res.dualObj):
+                    self.stats.infeasible += 1                 # failed non-root node is skipped (bnb_driver.cpp:844-859)
+                    continue
+                bound = max(nd.parent_bound, min(res.dualObj, res.primalObj))
+                if not nd.decisions:
+                    self.stats.root_bound = bound
+                x = res.primalSolution[:self.base.n_orig]
+                zero_fixed = [v for v, f in nd.decisions if f == 0]
+                self._offer(*self.heur(x, zero_fixed))
+                if self._prunable(bound):
+                    self.stats.pruned_by_bound += 1
+                    continue
+                frac = np.abs(x - np.round(x))
+                j = int(np.argmax(frac))
+                if frac[j] < 1e-6:                             # integral LP point
+                    self.stats.integral += 1
+                    self._offer(float(self.base.c[:self.base.n_orig] @ np.round(x)), np.round(x))
+                    continue
+                self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
+                self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+        if self.exchange is not None:                          # every rank calls it once per round
+            self.incumbent, self.incumbent_x = self.exchange(self.incumbent, self.incumbent_x)
+        self.stats.rounds += 1
+        return len(batch)
+
+    def run(self, max_nodes: int, rounds: Optional[int] = None) -> BnbStats:
+        t0 = time.perf_counter()
+        r = 0
+        while (rounds is None and self.frontier and self.stats.processed < max_nodes) or (rounds is not None and r < rounds):
+            self.round()
+            r += 1
+        self.stats.wall_s += time.perf_counter() - t0
+        self.stats.incumbent = self.incumbent
+        self.stats.open_nodes = len(self.frontier)
+        return self.stats

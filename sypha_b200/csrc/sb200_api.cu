@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -61,6 +62,21 @@ struct sb200_ws
     Scalars *sc_host = nullptr;   // pinned
     DevParams hparams{};
 
+    // B&B node = base model + node_k appended branch rows (build_branch_model, bnb.cpp:453-468), folded on
+    // the device: CSR rows appended in place, CSC rebuilt from a kept copy of the base CSC, the symbolic
+    // structure of M reused for the base rows and the extra rows of M written by their own kernel
+    int base_m = 0, base_n = 0;
+    long long base_nnz = 0;
+    int node_k = 0;
+    int *base_colptr = nullptr, *base_rows = nullptr;
+    double *base_cvals = nullptr;
+    bool base_csc_valid = false;
+    int *d_var = nullptr;
+    double *d_coef = nullptr;
+    unsigned char *h_delta = nullptr;      // pinned staging: var | coef | rhs
+    int delta_cap = 0;
+    std::map<int, std::pair<cudaGraphExec_t, long long>> node_graphs;   // iteration graph per depth
+
     // graph of one IPM iteration (direct strategies)
     cudaGraphExec_t iter_graph = nullptr;
     long long iter_graph_kernels = 0;
@@ -94,6 +110,9 @@ int fail(sb200_ws *ws, int code, const char *msg)
 
 void drop_graphs(sb200_ws *ws)
 {
+    for (auto &kv : ws->node_graphs)
+        if (kv.second.first && kv.second.first != ws->iter_graph) cudaGraphExecDestroy(kv.second.first);
+    ws->node_graphs.clear();
     if (ws->iter_graph) cudaGraphExecDestroy(ws->iter_graph);
     if (ws->cg_graph) cudaGraphExecDestroy(ws->cg_graph);
     ws->iter_graph = nullptr;
@@ -130,7 +149,7 @@ int ensure_capacity(sb200_ws *ws, int m, int n, long long nnz)
         if ((rc = grow(ws, &ws->c, (size_t)nc))) return rc;
         if ((rc = grow(ws, &ws->b, (size_t)mc))) return rc;
         // slab: 10 n-vectors, 9 m-vectors (padded), partials, trace
-        const size_t nv = (size_t)round_up(nc, 32), mv = (size_t)mp;
+        const size_t nv = (size_t)round_up(nc + 1, 32), mv = (size_t)mp;     // +1: d[n] = 0 pad slot of the compact assembly
         const size_t doubles = 11 * nv + 10 * mv + 4 * (size_t)SB200_MAX_PARTIAL_BLOCKS +
                                (size_t)SB200_TRACE_ROWS * SB200_TRACE_COLS;
         if (ws->slab) cudaFree(ws->slab);
@@ -145,7 +164,7 @@ int ensure_capacity(sb200_ws *ws, int m, int n, long long nnz)
 
 void carve(sb200_ws *ws)
 {
-    const size_t nv = (size_t)round_up(ws->n_cap, 32), mv = (size_t)round_up(ws->m_cap, SB200_TILE);
+    const size_t nv = (size_t)round_up(ws->n_cap + 1, 32), mv = (size_t)round_up(ws->m_cap, SB200_TILE);
     double *p = ws->slab;
     auto take = [&](size_t k) { double *r = p; p += k; return r; };
     IpmVecs &V = ws->V;
@@ -184,6 +203,88 @@ __global__ void k_densify(int m, const int *__restrict__ offs, const int *__rest
             atomicAdd(&A[(size_t)row * lda + inds[k]], vals[k]);   // duplicates sum, like CSR semantics
 }
 
+// ---- B&B node deltas -------------------------------------------------------------------------------
+__global__ void k_node_csr_append(int m0, long long nnz0, int n0, int k, const int *__restrict__ var,
+                                  const double *__restrict__ coef, int *__restrict__ offs, int *__restrict__ inds,
+                                  double *__restrict__ vals)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= k) return;
+    const long long p = nnz0 + 2ll * r;
+    inds[p] = var[r];
+    vals[p] = coef[r];
+    inds[p + 1] = n0 + r;
+    vals[p + 1] = -1.0;
+    offs[m0 + 1 + r] = (int)(p + 2);
+}
+// node CSC from the base CSC: column j keeps its base entries (shifted by the branch entries of earlier
+// columns) and gains (m0 + r, coef_r) for every branch row on j, appended in row order; the k new slack
+// columns follow with one entry (m0 + r, -1) each
+__global__ void k_node_csc(int n0, int m0, int k, const int *__restrict__ bptr, const int *__restrict__ brows,
+                           const double *__restrict__ bvals, const int *__restrict__ var,
+                           const double *__restrict__ coef, int *__restrict__ colptr, int *__restrict__ rows,
+                           double *__restrict__ vals)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j <= n0 + k; j += gridDim.x * wpb)
+    {
+        if (j >= n0)
+        {   // new slack columns and the end pointer
+            const int r = j - n0;
+            const int start = bptr[n0] + k + r;
+            if (lane == 0)
+            {
+                colptr[j] = start;
+                if (r < k)
+                {
+                    rows[start] = m0 + r;
+                    vals[start] = -1.0;
+                }
+            }
+            continue;
+        }
+        int shift = 0;
+        for (int r = 0; r < k; ++r)
+            shift += (var[r] < j) ? 1 : 0;
+        const int a = bptr[j], e = bptr[j + 1];
+        if (lane == 0) colptr[j] = a + shift;
+        for (int t = a + lane; t < e; t += 32)
+        {
+            rows[t + shift] = brows[t];
+            vals[t + shift] = bvals[t];
+        }
+        if (lane == 0)
+        {
+            int o = e + shift;
+            for (int r = 0; r < k; ++r)
+                if (var[r] == j)
+                {
+                    rows[o] = m0 + r;
+                    vals[o] = coef[r];
+                    ++o;
+                }
+        }
+    }
+}
+// rows m0 .. m0+k-1 of M = A D A' for the node (written whole every iteration: the factorisation is in place)
+__global__ void k_assemble_extra_rows(int m0, int n0, int k, int ld, const int *__restrict__ var,
+                                      const double *__restrict__ coef, const int *__restrict__ bptr,
+                                      const int *__restrict__ brows, const double *__restrict__ bvals,
+                                      const double *__restrict__ d, double *__restrict__ M)
+{
+    const int r = blockIdx.x, row = m0 + r, j = var[r];
+    const double cf = coef[r], dj = d[j];
+    double *Mr = M + (size_t)row * ld;
+    for (int c = threadIdx.x; c < row; c += blockDim.x)
+        Mr[c] = 0.0;
+    __syncthreads();
+    for (int t = bptr[j] + threadIdx.x; t < bptr[j + 1]; t += blockDim.x)
+        Mr[brows[t]] = cf * bvals[t] * dj;
+    for (int q = threadIdx.x; q < r; q += blockDim.x)
+        if (var[q] == j) Mr[m0 + q] = cf * coef[q] * dj;
+    if (threadIdx.x == 0) Mr[row] = cf * cf * dj + d[n0 + r];
+}
+
 // ---- normal-equations operator ---------------------------------------------------------------
 void enqueue_factor(sb200_ws *ws, const double *d)
 {
@@ -194,7 +295,16 @@ void enqueue_factor(sb200_ws *ws, const double *d)
         launch_pad_identity(ws->m, ws->M, ws->mpad, st);
     }
     else
+    {
         launch_assemble_normal(ws->pat, d, ws->M, ws->mpad, st);
+        if (ws->node_k)
+        {
+            k_assemble_extra_rows<<<ws->node_k, 256, 0, st>>>(ws->base_m, ws->base_n, ws->node_k, ws->mpad, ws->d_var,
+                                                             ws->d_coef, ws->base_colptr, ws->base_rows,
+                                                             ws->base_cvals, d, ws->M);
+            ++g_launch_count;
+        }
+    }
     launch_potrf(ws->chol, ws->m, ws->M, ws->mpad, &ws->sc->chol_info, st);
 }
 
@@ -292,6 +402,96 @@ int run_iteration_pcg(sb200_ws *ws)
     if ((rc = enqueue_or_run_solve(ws, V.d, 0.0, 1))) return rc;
     launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
     launch_update(V, ws->dparams, st);
+    return SB200_OK;
+}
+
+// node = base + delta; no allocation, no device-wide synchronisation once the one-time buffers exist
+int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
+{
+    if (!ws->loaded) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: no model loaded");
+    const int k = delta ? delta->n_extra_rows : 0;
+    if (k < 0) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: negative row count");
+    if (k == 0 && ws->node_k == 0) return SB200_OK;
+    if (ws->strategy != SB200_STRATEGY_CHOLESKY)
+        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_set_node_delta: only the sparse-assembly + Cholesky strategy folds node rows");
+    if (k && (!delta->var || !delta->coef || !delta->rhs))
+        return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: null delta arrays");
+    const int m0 = ws->base_m, n0 = ws->base_n;
+    const long long nnz0 = ws->base_nnz;
+    if (m0 + k > ws->m_cap || n0 + k > ws->n_cap || nnz0 + 2ll * k > ws->nnz_cap ||
+        (long long)round_up(m0 + k, SB200_TILE) * round_up(m0 + k, SB200_TILE) > ws->M_cap ||
+        round_up(m0 + k, SB200_TILE) / 64 > ws->chol.t_cap)
+        return fail(ws, SB200_ERR_UNSUPPORTED,
+                    "sb200_set_node_delta: workspace capacity too small (create it with sb200_caps covering the deepest node)");
+    WS_TRY(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    if (!ws->base_csc_valid)
+    {   // one-time copy of the base CSC (the working CSC is rebuilt from it for every node)
+        if (ws->node_k != 0) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: base CSC lost");
+        int rc;
+        if ((rc = grow(ws, &ws->base_colptr, (size_t)n0 + 1))) return rc;
+        if ((rc = grow(ws, &ws->base_rows, (size_t)nnz0))) return rc;
+        if ((rc = grow(ws, &ws->base_cvals, (size_t)nnz0))) return rc;
+        WS_TRY(cudaMemcpyAsync(ws->base_colptr, ws->csc_colptr, sizeof(int) * ((size_t)n0 + 1), cudaMemcpyDeviceToDevice, st));
+        WS_TRY(cudaMemcpyAsync(ws->base_rows, ws->csc_rows, sizeof(int) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
+        WS_TRY(cudaMemcpyAsync(ws->base_cvals, ws->csc_vals, sizeof(double) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
+        ws->base_csc_valid = true;
+    }
+    if (k > ws->delta_cap)
+    {
+        const int cap = std::max(64, k);
+        int rc;
+        if ((rc = grow(ws, &ws->d_var, (size_t)cap))) return rc;
+        if ((rc = grow(ws, &ws->d_coef, (size_t)cap))) return rc;
+        if (ws->h_delta) cudaFreeHost(ws->h_delta);
+        ws->h_delta = nullptr;
+        WS_TRY(cudaMallocHost(&ws->h_delta, (size_t)cap * 20));
+        ws->delta_cap = cap;
+    }
+    // keep the iteration graph of the depth we leave, pick up the one of the depth we enter
+    if (ws->iter_graph) ws->node_graphs[ws->node_k] = std::make_pair(ws->iter_graph, ws->iter_graph_kernels);
+    ws->iter_graph = nullptr;
+    auto g = ws->node_graphs.find(k);
+    if (g != ws->node_graphs.end())
+    {
+        ws->iter_graph = g->second.first;
+        ws->iter_graph_kernels = g->second.second;
+    }
+    if (k)
+    {
+        // the previous solve's staging copies have completed (every solve ends with a stream sync)
+        int *hv = reinterpret_cast<int *>(ws->h_delta);
+        double *hc = reinterpret_cast<double *>(ws->h_delta + 4 * (size_t)ws->delta_cap);
+        double *hr = hc + ws->delta_cap;
+        for (int r = 0; r < k; ++r)
+        {
+            if (delta->var[r] < 0 || delta->var[r] >= n0)
+                return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: branch variable out of range");
+            hv[r] = delta->var[r];
+            hc[r] = delta->coef[r];
+            hr[r] = delta->rhs[r];
+        }
+        WS_TRY(cudaMemcpyAsync(ws->d_var, hv, sizeof(int) * k, cudaMemcpyHostToDevice, st));
+        WS_TRY(cudaMemcpyAsync(ws->d_coef, hc, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+        WS_TRY(cudaMemcpyAsync(ws->b + m0, hr, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+        WS_TRY(cudaMemsetAsync(ws->c + n0, 0, sizeof(double) * k, st));
+        k_node_csr_append<<<(k + 63) / 64, 64, 0, st>>>(m0, nnz0, n0, k, ws->d_var, ws->d_coef, ws->csr_offs,
+                                                       ws->csr_inds, ws->csr_vals);
+        ++g_launch_count;
+    }
+    k_node_csc<<<grid_for((long long)(n0 + k + 1) * 32, 256, 148 * 8), 256, 0, st>>>(
+        n0, m0, k, ws->base_colptr, ws->base_rows, ws->base_cvals, ws->d_var, ws->d_coef, ws->csc_colptr, ws->csc_rows,
+        ws->csc_vals);
+    ++g_launch_count;
+    ws->m = m0 + k;
+    ws->n = n0 + k;
+    ws->nnz = nnz0 + 2ll * k;
+    ws->mpad = round_up(ws->m, SB200_TILE);
+    ws->node_k = k;
+    launch_pad_identity(ws->m, ws->M, ws->mpad, st);
+    int rc = chol_work_ensure(ws->err, ws->chol, ws->mpad);
+    if (rc) return rc;
+    carve(ws);
     return SB200_OK;
 }
 
@@ -567,7 +767,9 @@ int sb200_ws_destroy(sb200_ws *ws)
     free_blocked(&ws->blk_cols);
     chol_work_free(ws->chol);
     void *ptrs[] = {ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
-                    ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams};
+                    ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams, ws->base_colptr, ws->base_rows,
+                    ws->base_cvals, ws->d_var, ws->d_coef};
+    if (ws->h_delta) cudaFreeHost(ws->h_delta);
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ws->sc_host) cudaFreeHost(ws->sc_host);
@@ -597,6 +799,9 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
     int rc = ensure_capacity(ws, m, n, nnz);
     if (rc) return rc;
     ws->m = m; ws->n = n; ws->n_orig = n_orig; ws->nnz = nnz;
+    ws->base_m = m; ws->base_n = n; ws->base_nnz = nnz;
+    ws->node_k = 0;
+    ws->base_csc_valid = false;
     ws->mpad = round_up(m, SB200_TILE);
     const cudaMemcpyKind kind = ptrs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     WS_TRY(cudaMemcpyAsync(ws->csr_offs, csr_offs, sizeof(int) * ((size_t)m + 1), kind, st));
@@ -616,7 +821,9 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
     free_normal_pattern(&ws->pat);
     if (strat == SB200_STRATEGY_CHOLESKY)
     {
-        rc = build_normal_pattern(ws->err, m, n, nnz, ws->csc_colptr, ws->csc_rows, ws->csc_vals, &ws->pat, st);
+        // pad id of the compact term lists = n_cap: never a real column, d[n_cap] = 0 (also for B&B nodes
+        // whose extra slack columns take the ids n .. n_cap-1)
+        rc = build_normal_pattern(ws->err, m, n, nnz, ws->csc_colptr, ws->csc_rows, ws->csc_vals, &ws->pat, st, ws->n_cap);
         if (rc == SB200_ERR_UNSUPPORTED && strategy_hint == SB200_STRATEGY_AUTO)
             strat = SB200_STRATEGY_PCG;
         else if (rc)
@@ -669,7 +876,8 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
     }
     if (strat != SB200_STRATEGY_PCG)
     {
-        const long long need = (long long)ws->mpad * ws->mpad;
+        const int mpad_cap = round_up(ws->m_cap, SB200_TILE);      // deepest B&B node the workspace was sized for
+        const long long need = (long long)mpad_cap * mpad_cap;
         if (need > ws->M_cap)
         {
             if (ws->M) cudaFree(ws->M);
@@ -679,15 +887,21 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
         }
         WS_TRY(cudaMemsetAsync(ws->M, 0, sizeof(double) * (size_t)need, st));
         launch_pad_identity(m, ws->M, ws->mpad, st);
-        rc = chol_work_ensure(ws->err, ws->chol, ws->mpad);
+        rc = chol_work_ensure(ws->err, ws->chol, ws->mpad, mpad_cap);
         if (rc) return rc;
     }
     carve(ws);
     WS_TRY(cudaMemsetAsync(ws->slab, 0, ws->slab_bytes, st));
-    launch_fill(ws->ones_n, 1.0, round_up(ws->n_cap, 32), st);
+    launch_fill(ws->ones_n, 1.0, ws->n_cap, st);   // entry n_cap stays 0: pad slot of the compact assembly
     WS_TRY(cudaStreamSynchronize(st));
     ws->loaded = true;
     return SB200_OK;
+}
+
+int sb200_set_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
+{
+    if (!ws) return SB200_ERR_INVALID;
+    return apply_node_delta(ws, delta);
 }
 
 int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result)
@@ -710,13 +924,11 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     // LPs of a batch are independent: every workspace runs on its own stream and the
     // host interleaves enqueue/poll so their kernels overlap on the device.
     if (!wss || k <= 0 || !params || !results) return SB200_ERR_INVALID;
-    if (deltas)
-        for (int i = 0; i < k; ++i)
-            if (deltas[i].n_extra_rows != 0)
-                return fail(wss[i], SB200_ERR_UNSUPPORTED,
-                            "sb200_solve_batch: node deltas must be folded into the model by the caller");
     std::vector<int> live(k, 0);
     int rc, remaining = 0;
+    if (deltas)
+        for (int i = 0; i < k; ++i)
+            if ((rc = apply_node_delta(wss[i], &deltas[i]))) return rc;
     for (int i = 0; i < k; ++i)
     {
         if ((rc = solve_begin(wss[i], params, &results[i]))) return rc;
@@ -767,7 +979,7 @@ int sb200_model_info(sb200_ws *ws, long long *info, int n_info)
                               ws->pat.n_terms, ws->pat.term_w ? 1 : 0, ws->csc_lanes,
                               ws->iter_graph_kernels, ws->chol.max_coop_grid, ws->blk_rows.ptr ? 1 : 0,
                               ws->blk_rows.nblk, ws->blk_cols.nblk, (long long)ws->blk_rows.n_chunks,
-                              (long long)ws->blk_cols.n_chunks};
+                              (long long)ws->blk_cols.n_chunks, (long long)ws->pat.n_chunks};
     const int k = (int)(sizeof vals / sizeof vals[0]);
     for (int i = 0; i < n_info && i < k; ++i) info[i] = vals[i];
     return k;
@@ -973,7 +1185,10 @@ int sb200_assemble_normal(sb200_ws *ws, const double *d_d, double *d_m, int ld)
         launch_syrk_dmma(ws->m, ws->n, ws->denseA, ws->kpad, d_d, d_m, ld, ws->stream);
     }
     else if (ws->pat.pair_ptr)
-        launch_assemble_normal(ws->pat, d_d, d_m, ld, ws->stream);
+    {   // the compact term lists index one slot past the end (d[n] = 0): go through a workspace copy
+        WS_TRY(cudaMemcpyAsync(ws->cg_q, d_d, sizeof(double) * ws->n, cudaMemcpyDeviceToDevice, ws->stream));
+        launch_assemble_normal(ws->pat, ws->cg_q, d_m, ld, ws->stream);
+    }
     else
         return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_assemble_normal: model was loaded for the PCG strategy");
     return l0_done(ws->stream, true);

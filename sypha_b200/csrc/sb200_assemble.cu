@@ -173,8 +173,35 @@ __global__ void k_gather_terms(long long T, const unsigned int *__restrict__ per
     }
 }
 
+// ---- compact form of the unit-product case: 2-byte column ids in whole 16-byte chunks -----------------
+__global__ void k_pair_chunk_counts(long long n_pairs, const unsigned int *__restrict__ pair_ptr,
+                                    unsigned int *__restrict__ cnt)
+{
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p <= n_pairs;
+         p += (long long)gridDim.x * blockDim.x)
+        cnt[p] = p < n_pairs ? (pair_ptr[p + 1] - pair_ptr[p] + 7u) >> 3 : 0u;
+}
+__global__ void k_pack_terms16(long long n_pairs, const unsigned int *__restrict__ pair_ptr,
+                               const unsigned int *__restrict__ term_col, const unsigned int *__restrict__ chunk_ptr,
+                               unsigned short *__restrict__ term16, unsigned short pad)
+{
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_pairs;
+         p += (long long)gridDim.x * blockDim.x)
+    {
+        const unsigned a = pair_ptr[p], e = pair_ptr[p + 1];
+        size_t o = (size_t)chunk_ptr[p] << 3;
+        const size_t end = (size_t)chunk_ptr[p + 1] << 3;
+        for (unsigned t = a; t < e; ++t)
+            term16[o++] = (unsigned short)term_col[t];
+        while (o < end)
+            term16[o++] = pad;                  // d[n] = 0 by construction of the workspace
+    }
+}
+
 void free_normal_pattern(NormalPattern *p)
 {
+    if (p->chunk_ptr) cudaFree(p->chunk_ptr);
+    if (p->term16) cudaFree(p->term16);
     if (p->pair_ptr) cudaFree(p->pair_ptr);
     if (p->term_col) cudaFree(p->term_col);
     if (p->term_w) cudaFree(p->term_w);
@@ -183,9 +210,10 @@ void free_normal_pattern(NormalPattern *p)
 
 int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
                          const int *csc_rows, const double *csc_vals, NormalPattern *out,
-                         cudaStream_t st)
+                         cudaStream_t st, int pad_id)
 {
     (void)nnz;
+    if (pad_id < n) pad_id = n;
     free_normal_pattern(out);
     if (m > 65535)
     {
@@ -269,6 +297,25 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
         out->term_w = nullptr;
     }
     g_launch_count += 3;
+    if (!general && pad_id < 65535 && T > 0)
+    {   // repack: 2-byte column ids, every entry's list padded to whole 16-byte chunks with the id n
+        unsigned *ccnt = pair_cnt;      // reuse
+        SB200_CUDA_TRY(err, cudaMalloc(&out->chunk_ptr, 4 * (size_t)(n_pairs + 1)));
+        k_pair_chunk_counts<<<grid_for(n_pairs + 1, 256, 148 * 16), 256, 0, st>>>(n_pairs, out->pair_ptr, ccnt);
+        size_t sb = tmp_bytes;
+        SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, sb, ccnt, out->chunk_ptr, n_pairs + 1, st));
+        unsigned total = 0;
+        SB200_CUDA_TRY(err, cudaMemcpyAsync(&total, out->chunk_ptr + n_pairs, 4, cudaMemcpyDeviceToHost, st));
+        SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+        SB200_CUDA_TRY(err, cudaMalloc(&out->term16, 16 * ((size_t)total + 1)));
+        k_pack_terms16<<<grid_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(n_pairs, out->pair_ptr, out->term_col,
+                                                                        out->chunk_ptr, out->term16, (unsigned short)pad_id);
+        SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+        out->n_chunks = total;
+        cudaFree(out->term_col);
+        out->term_col = nullptr;
+        g_launch_count += 2;
+    }
     cudaFree(keys); cudaFree(keys_out); cudaFree(payload); cudaFree(pair_cnt); cudaFree(toff); cudaFree(tmp);
     if (colj) cudaFree(colj);
     if (w) cudaFree(w);
@@ -305,9 +352,51 @@ k_assemble_normal(long long n_pairs, const unsigned int *__restrict__ pair_ptr,
     }
 }
 
+// compact unit-product form: one thread per entry, its column ids arrive as aligned 16-byte chunks
+// (three requested together: one memory latency per entry instead of one per term); d is gathered
+// through the read-only path (88 KB at n = 11000: L1-resident); pad ids read d[n] = 0
+__device__ __forceinline__ double chunk_gather8(uint4 v, const double *__restrict__ d)
+{
+    return ((__ldg(d + (v.x & 0xffffu)) + __ldg(d + (v.x >> 16))) + (__ldg(d + (v.y & 0xffffu)) + __ldg(d + (v.y >> 16)))) +
+           ((__ldg(d + (v.z & 0xffffu)) + __ldg(d + (v.z >> 16))) + (__ldg(d + (v.w & 0xffffu)) + __ldg(d + (v.w >> 16))));
+}
+__global__ void __launch_bounds__(256)
+k_assemble_normal16(long long n_pairs, const unsigned int *__restrict__ chunk_ptr, const uint4 *__restrict__ term8,
+                    const double *__restrict__ d, double *__restrict__ M, int ld)
+{
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_pairs;
+         p += (long long)gridDim.x * blockDim.x)
+    {
+        const unsigned int a = chunk_ptr[p], e = chunk_ptr[p + 1];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (unsigned int c = a; c < e; c += 3)
+        {
+            const uint4 v0 = __ldg(term8 + c);
+            uint4 v1 = make_uint4(0u, 0u, 0u, 0u), v2 = v1;
+            const bool h1 = c + 1 < e, h2 = c + 2 < e;
+            if (h1) v1 = __ldg(term8 + c + 1);
+            if (h2) v2 = __ldg(term8 + c + 2);
+            s0 += chunk_gather8(v0, d);
+            if (h1) s1 += chunk_gather8(v1, d);
+            if (h2) s2 += chunk_gather8(v2, d);
+        }
+        long long i = (long long)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        const long long k = p - i * (i + 1) / 2;
+        M[i * ld + k] = (s0 + s1) + s2;
+    }
+}
+
 void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld, cudaStream_t st)
 {
     const int grid = grid_for(P.n_pairs, 256, 148 * 64);
+    if (P.term16)
+    {
+        k_assemble_normal16<<<grid, 256, 0, st>>>(P.n_pairs, P.chunk_ptr, reinterpret_cast<const uint4 *>(P.term16), d, M, ld);
+        ++g_launch_count;
+        return;
+    }
     if (P.term_w)
         k_assemble_normal<true><<<grid, 256, 0, st>>>(P.n_pairs, P.pair_ptr, P.term_col, P.term_w, d, M, ld);
     else

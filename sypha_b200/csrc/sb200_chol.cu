@@ -977,6 +977,14 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
 // ---------------------------------------------------------------------------------------------
 static int build_task_list(ErrorSink &err, CholWork &W, int T)
 {
+    auto hit = W.task_cache.find(T);
+    if (hit != W.task_cache.end())
+    {
+        W.tasks = hit->second.first;
+        W.ntasks = hit->second.second;
+        W.tasks_T = T;
+        return SB200_OK;
+    }
     std::vector<int2> tasks;
     for (int j = 0; j < T; ++j)
     {
@@ -986,21 +994,23 @@ static int build_task_list(ErrorSink &err, CholWork &W, int T)
         for (int i = j + 2; i < T; ++i)
             tasks.push_back(make_int2(i | (TASK_TILE << 16), j));
     }
-    if (W.tasks) cudaFree(W.tasks);
     W.tasks = nullptr;
     SB200_CUDA_TRY(err, cudaMalloc(&W.tasks, sizeof(int2) * tasks.size()));
     SB200_CUDA_TRY(err, cudaMemcpy(W.tasks, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice));
     W.ntasks = (int)tasks.size();
     W.tasks_T = T;
+    W.task_cache[T] = std::make_pair(W.tasks, W.ntasks);
     return SB200_OK;
 }
 
-int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad)
+int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve)
 {
-    const int T = n_pad / TB;
+    int T = n_pad / TB;
+    const int T_now = T, t_reserve = n_pad_reserve / TB;
     if (T > 0xffff) { err.msg = "chol_work_ensure: matrix too large"; return SB200_ERR_UNSUPPORTED; }
     if (T > W.t_cap)
     {
+        if (t_reserve > T) T = t_reserve;      // flags / inverse stores sized for the largest model expected
         chol_work_free(W);
         const int T2 = (T + 1) / 2;
         const size_t nflags = (size_t)T * T + T + 3 * (size_t)T2 + 32;
@@ -1026,16 +1036,19 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad)
         const char *mode = getenv("SB200_POTRF");
         W.panel_mode = (mode && std::string(mode) == "panel") ? 1 : 0;
     }
-    if (T != W.tasks_T) return build_task_list(err, W, T);
+    if (T_now != W.tasks_T) return build_task_list(err, W, T_now);
     return SB200_OK;
 }
 void chol_work_free(CholWork &W)
 {
+    for (auto &kv : W.task_cache)
+        if (kv.second.first) cudaFree(kv.second.first);
+    W.task_cache.clear();
+    W.tasks = nullptr;
     if (W.linv) cudaFree(W.linv);
     if (W.linv128) cudaFree(W.linv128);
     if (W.ctl) cudaFree(W.ctl);
     if (W.tagged) cudaFree(W.tagged);
-    if (W.tasks) cudaFree(W.tasks);
     W = CholWork{};
 }
 

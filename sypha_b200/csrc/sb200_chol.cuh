@@ -2,6 +2,9 @@
 #pragma once
 #include "sb200_common.cuh"
 
+#include <map>
+#include <utility>
+
 namespace sb200 {
 
 struct CholWork
@@ -12,13 +15,14 @@ struct CholWork
     int *ctl = nullptr;         // epochs, task counters, error flag, then the publish flags
     int2 *tasks = nullptr;      // task list of the data-flow factorisation for tasks_T tiles
     int ntasks = 0, tasks_T = 0;
+    std::map<int, std::pair<int2 *, int>> task_cache;   // task lists by tile count (B&B nodes change m)
     int t_cap = 0;
     int sms = 148, potrf_occ = 1;
     int panel_mode = 0;         // SB200_POTRF=panel: the two-launches-per-panel factorisation (A/B)
     int max_coop_grid = 148;
 };
 
-int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad);
+int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve = 0);
 void chol_work_free(CholWork &W);
 void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t st);
 void launch_potrs(CholWork &W, int n, const double *l, int ld, double *b, cudaStream_t st);

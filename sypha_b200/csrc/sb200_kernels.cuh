@@ -113,10 +113,15 @@ struct NormalPattern
     unsigned int *pair_ptr = nullptr;   // [n_pairs+1]
     unsigned int *term_col = nullptr;   // [n_terms] column j of each term
     double *term_w = nullptr;           // [n_terms] a_ij*a_kj, or nullptr when all products are +1
+    // compact form (all products +1, n < 65535): 2-byte column ids in whole 16-byte chunks per entry,
+    // padded with the id n (the workspace keeps d[n] = 0); term_col is dropped once this exists
+    unsigned int *chunk_ptr = nullptr;  // [n_pairs+1], in chunks
+    unsigned short *term16 = nullptr;   // [8 * n_chunks]
+    unsigned int n_chunks = 0;
 };
 int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
                          const int *csc_rows, const double *csc_vals, NormalPattern *out,
-                         cudaStream_t st);
+                         cudaStream_t st, int pad_id = -1);
 void free_normal_pattern(NormalPattern *p);
 void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld,
                             cudaStream_t st);

@@ -281,3 +281,51 @@ def solve_batch(nodes, config: SolverExecutionConfig, workspaces):
         _fill_result(node, workspaces[i], res[i], r, *bufs[i])
         out.append(r)
     return out
+
+
+def workspace_for_nodes(base: SyphaNodeSparse, max_depth: int, device: int = 0) -> IpmWorkspace:
+    """A workspace sized like the B&B driver sizes its IpmWorkspace (src/sypha_solver_bnb_driver.cpp:618-627,
+    KKT-shaped arguments) for nodes up to ``max_depth`` appended rows, with the BASE model resident."""
+    n_max, m_max, nnz_max = base.ncols + max_depth, base.nrows + max_depth, base.nnz + 2 * max_depth
+    ws = IpmWorkspace()
+    initializeIpmWorkspace(ws, maxKktNrows=2 * n_max + m_max, maxKktNnz=2 * nnz_max + 3 * n_max, maxNcols=n_max,
+                           device=device)
+    base.copyModelOnDevice(ws, "cholesky")
+    return ws
+
+
+def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecutionConfig, workspaces):
+    """B&B node body, batched and device-resident: workspace i holds the base model; node i = base + one row
+    per (var, fix) decision (bnb.cpp:453-468) is formed on the device (``sb200_node_delta``) and the LPs are
+    solved concurrently.  Returns one SolverExecutionResult per node (solutions have the node's dimensions)."""
+    lib = L.load()
+    k = len(decisions_list)
+    p = _params_from(base, config)
+    handles = (C.c_void_p * k)(*[ws.handle for ws in workspaces[:k]])
+    deltas = (L.sb200_node_delta * k)()
+    res = (L.sb200_result * k)()
+    keep, bufs = [], []
+    for i, dec in enumerate(decisions_list):
+        d = len(dec)
+        var = np.fromiter((v for v, _ in dec), dtype=np.int32, count=d)
+        fix = np.fromiter((f for _, f in dec), dtype=np.float64, count=d)
+        coef = np.where(fix == 0.0, -1.0, 1.0)
+        keep.append((var, coef, fix))
+        deltas[i].n_extra_rows = d
+        deltas[i].var = var.ctypes.data_as(C.POINTER(C.c_int))
+        deltas[i].coef = coef.ctypes.data_as(C.POINTER(C.c_double))
+        deltas[i].rhs = fix.ctypes.data_as(C.POINTER(C.c_double))
+        x, y, s = np.empty(base.ncols + d), np.empty(base.nrows + d), np.empty(base.ncols + d)
+        res[i].x_host, res[i].y_host, res[i].s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data
+        bufs.append((x, y, s))
+    rc = lib.sb200_solve_batch(handles, k, deltas, C.byref(p), res)
+    if rc != L.SB200_OK:
+        msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in workspaces[:k])
+        raise Sb200Error(f"sb200_solve_batch failed (code {rc}): {msgs}")
+    out = []
+    for i in range(k):
+        r = SolverExecutionResult()
+        shadow = SyphaNodeSparse(base.env)
+        _fill_result(shadow, workspaces[i], res[i], r, *bufs[i])
+        out.append(r)
+    return out

@@ -97,7 +97,7 @@ def read_traffic():
     return {}
 
 
-def pcg_block(lib, sb, local_rank, peak):
+def pcg_block(lib, sb, local_rank, peak, full_solve=True):
     """Secondary measurement: one CG iteration of the matrix-free normal-equations solve on the
     50k x 1M synthetic instance (BASELINE.json configs[3]) - CUDA events, model resident."""
     import ctypes as C
@@ -135,6 +135,22 @@ def pcg_block(lib, sb, local_rank, peak):
                                "csr12_equivalent_bytes": survey, "csr12_equivalent_gbs": survey / t / 1e9,
                                "traffic": read_traffic().get("cg_iteration")}
             out["cg_iterations_per_sec"] = 1.0 / t
+        if full_solve:
+            # time-to-LP-optimum of configs[3]: one whole solve (the reference cannot run this size: its
+            # start point needs 840 GB of host memory and its ratio test bails at n > 262144 - SURVEY F6, F7)
+            env2 = sb.SyphaEnvironment(cudaDeviceId=local_rank, linearSolverStrategy="pcg", krylovMaxCgIter=200000,
+                                       krylovCgTolInitial=1e-8, krylovCgTolFinal=1e-8, krylovCgTolDecayRate=1.0)
+            node.env = env2
+            res = sb.SolverExecutionResult()
+            t0 = time.perf_counter()
+            st = sb.solver_sparse_mehrotra_run(node, sb.SolverExecutionConfig(maxIterations=MAX_ITER), res, ws)
+            out["lp_solve"] = {"status": int(st), "reason": int(res.terminationReason), "iterations": int(res.iterations),
+                               "primal": res.primalObj, "dual": res.dualObj, "mu": res.mu,
+                               "cg_iterations": int(res.cgIterations), "cg_tol": 1e-8,
+                               "time_to_lp_opt_s": (res.msStart + res.msSetup + res.msLoop) / 1e3,
+                               "wall_s": time.perf_counter() - t0, "ipm_iterations_per_sec":
+                               res.iterations / max((res.msStart + res.msSetup + res.msLoop) / 1e3, 1e-9),
+                               "kernels_launched": int(res.kernelsLaunched)}
         return out
     finally:
         sb.releaseIpmWorkspace(ws)
@@ -216,9 +232,10 @@ def run_bnb(args, rank, world, local_rank):
             "incumbent": drv.stats.incumbent, "root_bound": drv.stats.root_bound,
             "incumbent_exchange_bytes_per_round": (16 + 8 * n0) if dist else 0,
             "e2e": {"value": nodes / elapsed, "unit": "nodes/s",
-                    "h2d_bytes_per_step": int(args.slots * (mdl.offs.nbytes + mdl.inds.nbytes + mdl.vals.nbytes + mdl.c.nbytes + mdl.b.nbytes)),
+                    "h2d_bytes_per_step": int(20 * drv.stats.delta_rows / max(args.steps, 1)),
                     "d2h_bytes_per_step": int(args.slots * 8 * (2 * mdl.n + mdl.m)),
-                    "note": "every node model is built on the host and uploaded inside the timed region: value IS end to end"},
+                    "note": "the base model is resident; every round sends the K decision lists (20 B per branch row) "
+                            "and reads x, y, s of every node back inside the timed region: value IS end to end"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
@@ -424,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_pcg_block and args.workload != "synth50k":
             try:
-                out["pcg_50kx1M"] = pcg_block(lib, sb, local_rank, peak)
+                out["pcg_50kx1M"] = pcg_block(lib, sb, local_rank, peak, full_solve=not args.no_pcg_solve)
             except Exception as e:           # never lose the headline line to the secondary measurement
                 out["pcg_50kx1M"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
@@ -507,6 +524,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
     ap.add_argument("--no-pcg-block", action="store_true")
+    ap.add_argument("--no-pcg-solve", action="store_true", help="skip the whole 50k x 1M LP solve (about 15 s)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--cg-max-iter", type=int, default=50000)
     ap.add_argument("--cg-tol", type=float, default=1e-8)

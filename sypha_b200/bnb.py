@@ -118,6 +118,7 @@ class BnbStats:
     incumbent: float = math.inf
     lp_device_ms: float = 0.0
     kernels_launched: int = 0
+    delta_rows: int = 0
     wall_s: float = 0.0
     open_nodes: int = 0
     root_bound: float = -math.inf
@@ -185,6 +186,7 @@ class BatchedBnb:
         if batch:
             if self.device_nodes and all(len(nd.decisions) <= self.max_depth for nd in batch):
                 results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self.ws)
+                self.stats.delta_rows += sum(len(nd.decisions) for nd in batch)
             else:
                 nodes = []
                 for nd in batch:

@@ -65,6 +65,30 @@ class ClockSampler(threading.Thread):
         self.sm, self.maxsm, self.reasons = [], [], set()
 
     def run(self):
+        """NVML in-process (no nvidia-smi process per sample: spawning it every 200 ms takes driver locks and
+        slowed the host-side-heavy e2e steps several-fold); nvidia-smi only if NVML cannot be imported."""
+        if os.environ.get("SB200_NO_SAMPLER"):
+            return
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.maxsm.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            while not self.stop_evt.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                self.stop_evt.wait(0.25)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -80,7 +104,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self.stop_evt.wait(0.2)
+            self.stop_evt.wait(1.0)
 
     def summary(self):
         if not self.sm:
@@ -355,13 +379,18 @@ def run_ours(args, rank, world, local_rank):
         return res
 
     e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
-    if e2e_steps:
-        e2e_step(0)
+    for i in range(3 if e2e_steps else 0):        # warm-up: the pools and the driver's allocation paths
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    e2e_res = [e2e_step(i) for i in range(e2e_steps)]
+    e2e_res, e2e_each = [], []
+    for i in range(e2e_steps):
+        t1 = time.perf_counter()
+        e2e_res.append(e2e_step(i))
+        e2e_each.append(round(1e3 * (time.perf_counter() - t1), 2))
     barrier()
     e2e_elapsed = time.perf_counter() - t0
+    print(f"[bench] e2e step times (ms): {e2e_each}", file=sys.stderr)
     e2e_iters = sum(r.iterations for r in e2e_res)
     mdl0 = models[0]
     h2d = int(mdl0.offs.nbytes + mdl0.inds.nbytes + mdl0.vals.nbytes + mdl0.c.nbytes + mdl0.b.nbytes)

@@ -1,14 +1,13 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
 {
-  echo "== pytest bnb"; timeout 900 python -m pytest tests/test_gpu_bnb.py -x -q 2>&1 | tail -12
-  for s in 1 4 8 16 32; do echo "== bnb slots $s"; timeout 600 python bench.py --workload bnb --steps 12 --slots $s 2>> gpurun_out/bench_bnb.err; done
-} > gpurun_out/round12.log 2>&1
+  echo "== pytest gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+  echo "== bench"; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-pcg-block 2> gpurun_out/bench_h.err | tee gpurun_out/bench_h.json
+} > gpurun_out/round13.log 2>&1
 python - <<'PY'
 import json
-for l in open('gpurun_out/round12.log'):
+for l in open('gpurun_out/round13.log'):
     if l.startswith('{'):
-        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','nodes','lp_iterations','lp_device_ms_per_node','incumbent','root_bound')}, d['config']['slots_per_gpu'])
+        d=json.loads(l); print(d['value'], d['e2e'], {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()})
     else: print(l.rstrip())
 PY
-tail -5 gpurun_out/bench_bnb.err

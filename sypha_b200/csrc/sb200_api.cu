@@ -741,6 +741,17 @@ int sb200_ws_create(int device, const sb200_caps *caps, sb200_ws **out)
     auto bail = [&](int rc) { sb200_ws_destroy(ws); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(SB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SB200_ERR_CUDA);
+    {   // set-up temporaries and symbolic structures come from the stream-ordered pool; keep what it has
+        // freed cached, so that re-loading a model (every e2e step, every base-model change of the B&B
+        // driver) does not go back to the driver for memory
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool)
+        {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     for (auto &e : ws->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return bail(SB200_ERR_CUDA);
     if (cudaMalloc(&ws->sc, sizeof(Scalars)) != cudaSuccess) return bail(SB200_ERR_NOMEM);
@@ -818,7 +829,7 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
     int strat = strategy_hint;
     if (strat == SB200_STRATEGY_AUTO)
         strat = (m <= 16384) ? SB200_STRATEGY_CHOLESKY : SB200_STRATEGY_PCG;
-    free_normal_pattern(&ws->pat);
+    free_normal_pattern(&ws->pat, st);
     if (strat == SB200_STRATEGY_CHOLESKY)
     {
         // pad id of the compact term lists = n_cap: never a real column, d[n_cap] = 0 (also for B&B nodes
@@ -837,13 +848,13 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
             if (t_syrk < t_sparse && (double)ws->mpad * round_up(n, 32) * 8.0 < 40e9)
             {
                 strat = SB200_STRATEGY_SYRK;
-                free_normal_pattern(&ws->pat);
+                free_normal_pattern(&ws->pat, st);
             }
         }
     }
     ws->strategy = strat;
-    free_blocked(&ws->blk_rows);
-    free_blocked(&ws->blk_cols);
+    free_blocked(&ws->blk_rows, st);
+    free_blocked(&ws->blk_cols, st);
     if (strat == SB200_STRATEGY_PCG)
     {   // +/-1 matrix => pattern-only, shared-memory-staged products (sb200_blocked.cu)
         const char *off = getenv("SB200_BLOCKED");

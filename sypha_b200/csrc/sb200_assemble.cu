@@ -70,11 +70,11 @@ int build_csc(ErrorSink &err, int m, int n, long long nnz, const int *csr_offs, 
     int *keys_out = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0, scan_bytes = 0;
-    SB200_CUDA_TRY(err, cudaMalloc(&rowid, sizeof(int) * (size_t)nnz));
-    SB200_CUDA_TRY(err, cudaMalloc(&pos, sizeof(int) * (size_t)nnz));
-    SB200_CUDA_TRY(err, cudaMalloc(&perm, sizeof(int) * (size_t)nnz));
-    SB200_CUDA_TRY(err, cudaMalloc(&keys_out, sizeof(int) * (size_t)nnz));
-    SB200_CUDA_TRY(err, cudaMalloc(&cnt, sizeof(int) * (size_t)(n + 1)));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&rowid, sizeof(int) * (size_t)nnz, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&pos, sizeof(int) * (size_t)nnz, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&perm, sizeof(int) * (size_t)nnz, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&keys_out, sizeof(int) * (size_t)nnz, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&cnt, sizeof(int) * (size_t)(n + 1), st));
     SB200_CUDA_TRY(err, cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n + 1), st));
     k_expand_rows<<<grid_for((long long)m * 32, 256, 148 * 16), 256, 0, st>>>(m, csr_offs, rowid, pos);
     k_count_cols<<<grid_for(nnz, 256, 148 * 16), 256, 0, st>>>(nnz, csr_inds, cnt);
@@ -83,7 +83,7 @@ int build_csc(ErrorSink &err, int m, int n, long long nnz, const int *csr_offs, 
                                                         nnz, 0, nb, st));
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, csc_colptr, n + 1, st));
     if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
-    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&tmp, tmp_bytes, st));
     size_t tb = tmp_bytes;
     SB200_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(tmp, tb, csr_inds, keys_out, pos, perm, nnz, 0, nb, st));
     tb = tmp_bytes;
@@ -91,7 +91,7 @@ int build_csc(ErrorSink &err, int m, int n, long long nnz, const int *csr_offs, 
     k_gather_csc<<<grid_for(nnz, 256, 148 * 16), 256, 0, st>>>(nnz, perm, rowid, csr_vals, csc_rows, csc_vals);
     g_launch_count += 3;
     SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
-    cudaFree(rowid); cudaFree(pos); cudaFree(perm); cudaFree(keys_out); cudaFree(cnt); cudaFree(tmp);
+    cudaFreeAsync(rowid, st); cudaFreeAsync(pos, st); cudaFreeAsync(perm, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(cnt, st); cudaFreeAsync(tmp, st);
     return SB200_OK;
 }
 
@@ -198,13 +198,13 @@ __global__ void k_pack_terms16(long long n_pairs, const unsigned int *__restrict
     }
 }
 
-void free_normal_pattern(NormalPattern *p)
+void free_normal_pattern(NormalPattern *p, cudaStream_t st)
 {
-    if (p->chunk_ptr) cudaFree(p->chunk_ptr);
-    if (p->term16) cudaFree(p->term16);
-    if (p->pair_ptr) cudaFree(p->pair_ptr);
-    if (p->term_col) cudaFree(p->term_col);
-    if (p->term_w) cudaFree(p->term_w);
+    if (p->chunk_ptr) cudaFreeAsync(p->chunk_ptr, st);
+    if (p->term16) cudaFreeAsync(p->term16, st);
+    if (p->pair_ptr) cudaFreeAsync(p->pair_ptr, st);
+    if (p->term_col) cudaFreeAsync(p->term_col, st);
+    if (p->term_w) cudaFreeAsync(p->term_w, st);
     *p = NormalPattern{};
 }
 
@@ -214,7 +214,7 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
 {
     (void)nnz;
     if (pad_id < n) pad_id = n;
-    free_normal_pattern(out);
+    free_normal_pattern(out, st);
     if (m > 65535)
     {
         err.msg = "build_normal_pattern: m > 65535 (packed pair index would overflow 32 bits)";
@@ -225,24 +225,24 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
     int *general_d = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    SB200_CUDA_TRY(err, cudaMalloc(&cnt, sizeof(unsigned long long) * (size_t)(n + 1)));
-    SB200_CUDA_TRY(err, cudaMalloc(&toff, sizeof(unsigned long long) * (size_t)(n + 1)));
-    SB200_CUDA_TRY(err, cudaMalloc(&general_d, sizeof(int)));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&cnt, sizeof(unsigned long long) * (size_t)(n + 1), st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&toff, sizeof(unsigned long long) * (size_t)(n + 1), st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&general_d, sizeof(int), st));
     SB200_CUDA_TRY(err, cudaMemsetAsync(general_d, 0, sizeof(int), st));
     k_col_term_counts<<<grid_for(n + 1, 256, 148 * 16), 256, 0, st>>>(n, csc_colptr, csc_vals, cnt, general_d);
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, toff, n + 1, st));
-    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&tmp, tmp_bytes, st));
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, toff, n + 1, st));
     unsigned long long T = 0;
     int general = 0;
     SB200_CUDA_TRY(err, cudaMemcpyAsync(&T, toff + n, sizeof T, cudaMemcpyDeviceToHost, st));
     SB200_CUDA_TRY(err, cudaMemcpyAsync(&general, general_d, sizeof general, cudaMemcpyDeviceToHost, st));
     SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
-    cudaFree(tmp); tmp = nullptr;
-    cudaFree(cnt); cudaFree(general_d);
+    cudaFreeAsync(tmp, st); tmp = nullptr;
+    cudaFreeAsync(cnt, st); cudaFreeAsync(general_d, st);
     if (T >= 0xFFFFFFF0ull)
     {
-        cudaFree(toff);
+        cudaFreeAsync(toff, st);
         err.msg = "build_normal_pattern: more than 2^32 product terms; use the PCG strategy";
         return SB200_ERR_UNSUPPORTED;
     }
@@ -251,17 +251,17 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
     unsigned int *colj = nullptr, *pair_cnt = nullptr;
     double *w = nullptr;
     const size_t Ts = (size_t)(T > 0 ? T : 1);
-    SB200_CUDA_TRY(err, cudaMalloc(&keys, 4 * Ts));
-    SB200_CUDA_TRY(err, cudaMalloc(&keys_out, 4 * Ts));
-    SB200_CUDA_TRY(err, cudaMalloc(&payload, 4 * Ts));
-    SB200_CUDA_TRY(err, cudaMalloc(&payload_out, 4 * Ts));
-    SB200_CUDA_TRY(err, cudaMalloc(&pair_cnt, 4 * (size_t)(n_pairs + 1)));
-    SB200_CUDA_TRY(err, cudaMalloc(&out->pair_ptr, 4 * (size_t)(n_pairs + 1)));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&keys, 4 * Ts, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&keys_out, 4 * Ts, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&payload, 4 * Ts, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&payload_out, 4 * Ts, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&pair_cnt, 4 * (size_t)(n_pairs + 1), st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&out->pair_ptr, 4 * (size_t)(n_pairs + 1), st));
     SB200_CUDA_TRY(err, cudaMemsetAsync(pair_cnt, 0, 4 * (size_t)(n_pairs + 1), st));
     if (general)
     {
-        SB200_CUDA_TRY(err, cudaMalloc(&colj, 4 * Ts));
-        SB200_CUDA_TRY(err, cudaMalloc(&w, 8 * Ts));
+        SB200_CUDA_TRY(err, cudaMallocAsync(&colj, 4 * Ts, st));
+        SB200_CUDA_TRY(err, cudaMallocAsync(&w, 8 * Ts, st));
         k_emit_terms<true><<<grid_for((long long)n * 32, 256, 148 * 16), 256, 0, st>>>(
             n, csc_colptr, csc_rows, csc_vals, toff, keys, payload, colj, w, pair_cnt);
     }
@@ -275,7 +275,7 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, pair_cnt, out->pair_ptr,
                                                       n_pairs + 1, st));
     tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
-    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&tmp, tmp_bytes, st));
     size_t tb = tmp_bytes;
     SB200_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_out, payload, payload_out,
                                                         (long long)T, 0, nb, st));
@@ -283,12 +283,12 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tb, pair_cnt, out->pair_ptr, n_pairs + 1, st));
     if (general)
     {
-        SB200_CUDA_TRY(err, cudaMalloc(&out->term_col, 4 * Ts));
-        SB200_CUDA_TRY(err, cudaMalloc(&out->term_w, 8 * Ts));
+        SB200_CUDA_TRY(err, cudaMallocAsync(&out->term_col, 4 * Ts, st));
+        SB200_CUDA_TRY(err, cudaMallocAsync(&out->term_w, 8 * Ts, st));
         k_gather_terms<<<grid_for((long long)T, 256, 148 * 16), 256, 0, st>>>((long long)T, payload_out, colj, w,
                                                                             out->term_col, out->term_w);
         SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
-        cudaFree(payload_out);
+        cudaFreeAsync(payload_out, st);
     }
     else
     {
@@ -300,25 +300,25 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
     if (!general && pad_id < 65535 && T > 0)
     {   // repack: 2-byte column ids, every entry's list padded to whole 16-byte chunks with the id n
         unsigned *ccnt = pair_cnt;      // reuse
-        SB200_CUDA_TRY(err, cudaMalloc(&out->chunk_ptr, 4 * (size_t)(n_pairs + 1)));
+        SB200_CUDA_TRY(err, cudaMallocAsync(&out->chunk_ptr, 4 * (size_t)(n_pairs + 1), st));
         k_pair_chunk_counts<<<grid_for(n_pairs + 1, 256, 148 * 16), 256, 0, st>>>(n_pairs, out->pair_ptr, ccnt);
         size_t sb = tmp_bytes;
         SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, sb, ccnt, out->chunk_ptr, n_pairs + 1, st));
         unsigned total = 0;
         SB200_CUDA_TRY(err, cudaMemcpyAsync(&total, out->chunk_ptr + n_pairs, 4, cudaMemcpyDeviceToHost, st));
         SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
-        SB200_CUDA_TRY(err, cudaMalloc(&out->term16, 16 * ((size_t)total + 1)));
+        SB200_CUDA_TRY(err, cudaMallocAsync(&out->term16, 16 * ((size_t)total + 1), st));
         k_pack_terms16<<<grid_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(n_pairs, out->pair_ptr, out->term_col,
                                                                         out->chunk_ptr, out->term16, (unsigned short)pad_id);
         SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
         out->n_chunks = total;
-        cudaFree(out->term_col);
+        cudaFreeAsync(out->term_col, st);
         out->term_col = nullptr;
         g_launch_count += 2;
     }
-    cudaFree(keys); cudaFree(keys_out); cudaFree(payload); cudaFree(pair_cnt); cudaFree(toff); cudaFree(tmp);
-    if (colj) cudaFree(colj);
-    if (w) cudaFree(w);
+    cudaFreeAsync(keys, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(payload, st); cudaFreeAsync(pair_cnt, st); cudaFreeAsync(toff, st); cudaFreeAsync(tmp, st);
+    if (colj) cudaFreeAsync(colj, st);
+    if (w) cudaFreeAsync(w, st);
     out->m = m;
     out->n_pairs = n_pairs;
     out->n_terms = (long long)T;

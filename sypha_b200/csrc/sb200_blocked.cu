@@ -76,11 +76,11 @@ __global__ void k_blk_pad(int majors, int nblk, int nb, const unsigned *__restri
             ent[pos] = (unsigned short)nb;
 }
 
-void free_blocked(BlockedPattern *p)
+void free_blocked(BlockedPattern *p, cudaStream_t st)
 {
-    if (p->ptr) cudaFree(p->ptr);
-    if (p->ent) cudaFree(p->ent);
-    if (p->partial) cudaFree(p->partial);
+    if (p->ptr) cudaFreeAsync(p->ptr, st);
+    if (p->ent) cudaFreeAsync(p->ent, st);
+    if (p->partial) cudaFreeAsync(p->partial, st);
     *p = BlockedPattern{};
 }
 
@@ -88,16 +88,16 @@ void free_blocked(BlockedPattern *p)
 int build_blocked(ErrorSink &err, int majors, int minors, long long nnz, const int *mptr, const int *midx,
                   const double *vals, int nb, bool with_partials, BlockedPattern *out, cudaStream_t st)
 {
-    free_blocked(out);
+    free_blocked(out, st);
     const int nblk = (minors + nb - 1) / nb;
     const size_t nseg = (size_t)nblk * majors;
     unsigned *cnt = nullptr, *cursor = nullptr;
     int *general = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    SB200_CUDA_TRY(err, cudaMalloc(&cnt, sizeof(unsigned) * (nseg + 1)));
-    SB200_CUDA_TRY(err, cudaMalloc(&cursor, sizeof(unsigned) * (nseg + 1)));
-    SB200_CUDA_TRY(err, cudaMalloc(&general, sizeof(int)));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&cnt, sizeof(unsigned) * (nseg + 1), st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&cursor, sizeof(unsigned) * (nseg + 1), st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&general, sizeof(int), st));
     SB200_CUDA_TRY(err, cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (nseg + 1), st));
     SB200_CUDA_TRY(err, cudaMemsetAsync(general, 0, sizeof(int), st));
     k_blk_count<<<grid_for(majors, 128, 148 * 32), 128, 0, st>>>(majors, mptr, midx, vals, nb, cnt, general);
@@ -106,26 +106,26 @@ int build_blocked(ErrorSink &err, int majors, int minors, long long nnz, const i
     SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
     if (h_general)
     {
-        cudaFree(cnt); cudaFree(cursor); cudaFree(general);
+        cudaFreeAsync(cnt, st); cudaFreeAsync(cursor, st); cudaFreeAsync(general, st);
         return SB200_ERR_UNSUPPORTED;
     }
-    SB200_CUDA_TRY(err, cudaMalloc(&out->ptr, sizeof(unsigned) * (nseg + 1)));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&out->ptr, sizeof(unsigned) * (nseg + 1), st));
     k_blk_to_chunks<<<grid_for((long long)nseg, 256, 148 * 16), 256, 0, st>>>(nseg, cnt);
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, out->ptr, nseg + 1, st));
-    SB200_CUDA_TRY(err, cudaMalloc(&tmp, tmp_bytes));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&tmp, tmp_bytes, st));
     SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, out->ptr, nseg + 1, st));
     unsigned total_chunks = 0;
     SB200_CUDA_TRY(err, cudaMemcpyAsync(&total_chunks, out->ptr + nseg, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
     out->n_chunks = total_chunks;
-    SB200_CUDA_TRY(err, cudaMalloc(&out->ent, sizeof(uint4) * ((size_t)total_chunks + 1)));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&out->ent, sizeof(uint4) * ((size_t)total_chunks + 1), st));
     k_blk_cursor<<<grid_for((long long)nseg, 256, 148 * 16), 256, 0, st>>>(nseg, out->ptr, cursor);
     k_blk_fill<<<grid_for(majors, 128, 148 * 32), 128, 0, st>>>(majors, mptr, midx, vals, nb, cursor, out->ent);
     k_blk_pad<<<grid_for((long long)nseg, 256, 148 * 16), 256, 0, st>>>(majors, nblk, nb, out->ptr, cursor, out->ent);
     g_launch_count += 5;
-    if (with_partials) SB200_CUDA_TRY(err, cudaMalloc(&out->partial, sizeof(double) * nseg));
+    if (with_partials) SB200_CUDA_TRY(err, cudaMallocAsync(&out->partial, sizeof(double) * nseg, st));
     SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
-    cudaFree(cnt); cudaFree(cursor); cudaFree(general); cudaFree(tmp);
+    cudaFreeAsync(cnt, st); cudaFreeAsync(cursor, st); cudaFreeAsync(general, st); cudaFreeAsync(tmp, st);
     out->majors = majors;
     out->minors = minors;
     out->nb = nb;

@@ -11,6 +11,7 @@ struct CholWork
 {
     double *linv = nullptr;     // [T][64][64] inverses of the 64x64 diagonal blocks of L
     double *linv128 = nullptr;  // [ceil(T/2)][128][128] inverses of the 128x128 diagonal blocks
+    double2 *d1tag = nullptr;   // [T][2560] tagged hand-off of a factored diagonal tile to the next chain task
     double2 *tagged = nullptr;  // [2][ceil(T/2)*128] {value, epoch tag}: forward / backward solve hand-off
     int *ctl = nullptr;         // epochs, task counters, error flag, then the publish flags
     int2 *tasks = nullptr;      // task list of the data-flow factorisation for tasks_T tiles

@@ -91,7 +91,7 @@ int pick_csc_lanes(long long nnz, int n);
 // ---- sb200_blocked.cu ------------------------------------------------------------------------
 int build_blocked(ErrorSink &err, int majors, int minors, long long nnz, const int *mptr, const int *midx,
                   const double *vals, int nb, bool with_partials, BlockedPattern *out, cudaStream_t st);
-void free_blocked(BlockedPattern *p);
+void free_blocked(BlockedPattern *p, cudaStream_t st = 0);
 int blocked_nb_for_rows(int n);
 int blocked_nb_for_cols(int m);
 void launch_blk_spmv_rows(const BlockedPattern &B, const double *x, const double *z, double *out, double alpha,
@@ -122,7 +122,7 @@ struct NormalPattern
 int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
                          const int *csc_rows, const double *csc_vals, NormalPattern *out,
                          cudaStream_t st, int pad_id = -1);
-void free_normal_pattern(NormalPattern *p);
+void free_normal_pattern(NormalPattern *p, cudaStream_t st = 0);
 void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld,
                             cudaStream_t st);
 void launch_syrk_dmma(int m, int k, const double *a, int lda, const double *d, double *c, int ld,

@@ -15,7 +15,11 @@
 
 namespace sb200 {
 
-static constexpr int LP = TB + 1;    // padded row stride of the tile in shared memory (doubles)
+#ifndef SB200_V_LP
+#define SB200_V_LP 68
+#endif
+static constexpr int LP = SB200_V_LP;    // padded row stride of the tile in shared memory (doubles): 65 favours
+                                         // one-thread-per-row access, 68 makes the DMMA fragment loads conflict-free
 
 // dynamic shared-memory layout (bytes) of the kernels that factor a diagonal tile
 static constexpr int SM_LS = 0;                                   // L tile (aliases the MMA staging buffers)
@@ -81,7 +85,8 @@ __device__ __forceinline__ double rsqrt_pivot(double x)
 #define SB200_V_RSQ 1
 #endif
 #ifndef SB200_V_TRAIL
-#define SB200_V_TRAIL 0      // 1 = three interleaved blocks per warp: measured SLOWER (354 -> 395 us at m = 1024)
+#define SB200_V_TRAIL 1      // three interleaved blocks per warp (straight-line form; the first form with per-slot
+                             // branches and pointer arrays measured slower: 354 -> 395 us at m = 1024)
 #endif
 #if SB200_V_RSQ
 #define SB200_RSQ(x) rsqrt_pivot(x)
@@ -126,7 +131,11 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid)
         const int c0 = 16 * kb;
         __syncthreads();
         TT(8 + 4 * kb);
+#ifndef SB200_SKIP_DIAG
         if (warp == 0)
+#else
+        if (false)
+#endif
         {
             const int r = lane & 15;
             const bool inv_lane = lane >= 16;          // lanes 16..31: column r of W = L_dd^-1
@@ -178,7 +187,11 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid)
         __syncthreads();
         TT(9 + 4 * kb);
         const int nrows = 48 - c0;
+#ifdef SB200_SKIP_ROWS
+        if (false)
+#else
         if (8 * warp < nrows)
+#endif
         {   // ---- rows below: X = A W' (W lower triangular: k <= n), one 8-row block per warp ----------
             const int R = c0 + 16 + 8 * warp;
             double af[4];
@@ -205,46 +218,56 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid)
         }
         __syncthreads();
         TT(10 + 4 * kb);
+#ifdef SB200_SKIP_TRAIL
+        if (false)
+#endif
 #if SB200_V_TRAIL
         {   // ---- trailing update on the tensor pipe: 8x8 blocks of the lower triangle; a warp owns up to
-            //      three blocks (q = warp, warp+8, warp+16) and interleaves their independent DMMA chains
+            //      three blocks (q = warp, warp+8, warp+16).  Straight-line code: all fragment loads first,
+            //      then the three independent DMMA chains interleaved; a slot without a block works on
+            //      block (0,0) and simply does not store.
             const int r0 = c0 + 16, nb = nrows >> 3, nblk = nb * (nb + 1) / 2;
-            double af[3][4], bf[3][4], u[3][2];
-            double *Cp[3];
-            bool act[3];
-#pragma unroll
-            for (int v = 0; v < 3; ++v)
+            if (nblk > 0)
             {
-                const int q = warp + 8 * v;
-                act[v] = q < nblk;
-                int bi = 0;
-                while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
-                const int bj = q - bi * (bi + 1) / 2;
-                Cp[v] = &Ls[r0 + 8 * bi + g][r0 + 8 * bj + 2 * tg];
-                if (act[v])
+                int ro[3], co[3];
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                {
+                    const int q = warp + 8 * v;
+                    int bi = 0;
+                    bi += (q >= 1) + (q >= 3) + (q >= 6) + (q >= 10) + (q >= 15);
+                    const int bj = q - bi * (bi + 1) / 2;
+                    const bool act = q < nblk;
+                    ro[v] = act ? r0 + 8 * bi : r0;
+                    co[v] = act ? r0 + 8 * bj : r0;
+                }
+                double af[3][4], bf[3][4], u[3][2];
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
                 {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                     {
-                        af[v][kk] = -Ls[r0 + 8 * bi + g][c0 + 4 * kk + tg];
-                        bf[v][kk] = Ls[r0 + 8 * bj + g][c0 + 4 * kk + tg];
+                        af[v][kk] = -Ls[ro[v] + g][c0 + 4 * kk + tg];
+                        bf[v][kk] = Ls[co[v] + g][c0 + 4 * kk + tg];
                     }
-                    u[v][0] = Cp[v][0];
-                    u[v][1] = Cp[v][1];
+                    u[v][0] = Ls[ro[v] + g][co[v] + 2 * tg];
+                    u[v][1] = Ls[ro[v] + g][co[v] + 2 * tg + 1];
                 }
-            }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int v = 0; v < 3; ++v)
+                        dmma_8x8x4(u[v][0], u[v][1], af[v][kk], bf[v][kk]);
+                __syncwarp();
 #pragma unroll
                 for (int v = 0; v < 3; ++v)
-                    if (act[v]) dmma_8x8x4(u[v][0], u[v][1], af[v][kk], bf[v][kk]);
-#pragma unroll
-            for (int v = 0; v < 3; ++v)
-                if (act[v])
-                {
-                    Cp[v][0] = u[v][0];
-                    Cp[v][1] = u[v][1];
-                }
+                    if (warp + 8 * v < nblk)
+                    {
+                        Ls[ro[v] + g][co[v] + 2 * tg] = u[v][0];
+                        Ls[ro[v] + g][co[v] + 2 * tg + 1] = u[v][1];
+                    }
+            }
         }
     }
 #else

@@ -6,15 +6,9 @@
 //
 // Layout: row-major, lower triangle, leading dimension ld = m rounded up to 64, identity pad.
 //
-// Default factorisation: k_potrf_df, ONE data-flow launch (left-looking 64x64 tile tasks, see below).
-// The earlier right-looking panel version is kept behind SB200_POTRF=panel for A/B measurements
-// (right-looking, 64-wide panels, 2 launches per panel):
-//   k_trsm_panel : X = A_ik (L_kk^-1)' as a 64x64x64 FP64 tensor-core GEMM against the pre-inverted
-//                  diagonal block
-//   k_update     : A_ij -= L_ik L_jk'  on 64x64 tiles with FP64 tensor-core MMA
-//                  (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4); the CTA that owns the next diagonal
-//                  tile factors AND inverts it in shared memory before writing it back (look-ahead),
-//                  so no separate potrf launch sits on the critical path.
+// Factorisation: k_potrf_df, ONE data-flow launch (left-looking 64x64 tile tasks, see below).  The earlier
+// right-looking version (2 launches per 64-wide panel, 500 us at m = 1000) is in the history of this file;
+// DESIGN.md 3.2 has the measurements of every step from there to here.
 // Solves (k_trsv_df, one launch for forward + backward, data-flow): every 128-row block is a task
 //   which accumulates its right-hand side as the blocks it depends on are published through
 //   release/acquire flags, then multiplies by the pre-inverted 128x128 diagonal block.  Tasks are
@@ -33,152 +27,6 @@ __device__ __forceinline__ void report_fail(int *info, int fail, int base)
 {
     if (fail && threadIdx.x == 0)
         atomicCAS(info, 0, base + fail);
-}
-
-// write L (lower) back to the matrix and L^-1 to the inverse store
-__device__ __forceinline__ void store_factored_tile(const unsigned char *smem, double *__restrict__ Atile, int ld,
-                                                    double *__restrict__ linv_k, int tid)
-{
-    const double(*Ls)[LP] = reinterpret_cast<const double(*)[LP]>(smem + SM_LS);
-    const double(*Li)[LP] = reinterpret_cast<const double(*)[LP]>(smem + SM_LI);
-    for (int idx = tid; idx < TB * TB; idx += NT_TILE)
-    {
-        const int r = idx >> 6, c = idx & 63;
-        if (c <= r) Atile[(size_t)r * ld + c] = Ls[r][c];
-        linv_k[idx] = Li[r][c];
-    }
-}
-
-// first diagonal tile
-__global__ void __launch_bounds__(NT_TILE) k_potrf_first(double *__restrict__ A, int ld, double *__restrict__ linv,
-                                                         int *info)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LS);
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < TB * TB; idx += NT_TILE)
-    {
-        const int r = idx >> 6, c = idx & 63;
-        Ls[r][c] = A[(size_t)r * ld + c];
-    }
-    __syncthreads();
-    const int fail = potrf_inv_tile64(dyn_smem, tid);
-    store_factored_tile(dyn_smem, A, ld, linv, tid);
-    report_fail(info, fail, 0);
-}
-
-// X = A_ik L_kk^-T = A_ik (L_kk^-1)' for every tile row i > k: one CTA per 64x64 tile, DMMA GEMM
-__global__ void __launch_bounds__(128) k_trsm_panel(double *__restrict__ A, int ld, int k,
-                                                    const double *__restrict__ linv)
-{
-    __shared__ __align__(16) double smem[2 * TB * KP];
-    double(*As)[KP] = reinterpret_cast<double(*)[KP]>(smem);
-    double(*Bs)[KP] = reinterpret_cast<double(*)[KP]>(smem + TB * KP);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wm = w >> 1, wn = w & 1, g = lane >> 2, tg = lane & 3;
-    const size_t r0 = ((size_t)k + 1 + blockIdx.x) * TB, k0 = (size_t)k * TB;
-    const double *Lk = linv + (size_t)k * TB * TB;
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll
-    for (int kc = 0; kc < TB; kc += KC)
-    {
-        __syncthreads();
-        load_tile_64xKC(As, A + r0 * ld + k0 + kc, ld, tid, 128, nullptr);
-        load_tile_64xKC(Bs, Lk + kc, TB, tid, 128, nullptr);
-        __syncthreads();
-        warp_mma_32x32(As, Bs, wm, wn, lane, 1.0, acc);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<double2 *>(A + (r0 + wm * 32 + i * 8 + g) * ld + k0 + wn * 32 + j * 8 + tg * 2) =
-                make_double2(acc[i][j][0], acc[i][j][1]);
-}
-
-// trailing update with look-ahead factorisation (+ inverse) of the next diagonal tile
-__global__ void __launch_bounds__(NT_TILE) k_update(double *__restrict__ A, int ld, int k, int T,
-                                                    double *__restrict__ linv, int *info)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double(*As)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem);
-    double(*Bs)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem + TB * KP * 8);
-
-    // decode (ti, tj), tj <= ti, both relative to k+1
-    const int p = blockIdx.x;
-    int ri = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-    while ((ri + 1) * (ri + 2) / 2 <= p) ++ri;
-    while (ri * (ri + 1) / 2 > p) --ri;
-    const int rj = p - ri * (ri + 1) / 2;
-    const int ti = k + 1 + ri, tj = k + 1 + rj;
-    if (ti >= T) return;
-
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int row0 = (w >> 2) * 32, col0 = (w & 3) * 16;     // 8 warps: 2 x 4, warp tile 32 x 16
-    const int g = lane >> 2, tg = lane & 3;
-    const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB, k0 = (size_t)k * TB;
-
-    const bool mma_warp = w < 8;           // warp 8 only takes part in the tile factorisation
-    double acc[4][2][2];
-    if (mma_warp)
-    {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-            {
-                const double2 v = *reinterpret_cast<const double2 *>(
-                    A + (r0 + row0 + i * 8 + g) * ld + c0 + col0 + j * 8 + tg * 2);
-                acc[i][j][0] = v.x;
-                acc[i][j][1] = v.y;
-            }
-    }
-#pragma unroll
-    for (int kc = 0; kc < TB; kc += KC)
-    {
-        __syncthreads();
-        load_tile_64xKC(As, A + r0 * ld + k0 + kc, ld, tid, NT_TILE, nullptr);
-        load_tile_64xKC(Bs, A + c0 * ld + k0 + kc, ld, tid, NT_TILE, nullptr);
-        __syncthreads();
-        if (mma_warp) warp_mma<4, 2>(As, Bs, row0, col0, lane, -1.0, acc);
-    }
-
-    if (ri == 0 && rj == 0)
-    {   // next diagonal tile: factor + invert it before it goes back to memory
-        __syncthreads();
-        double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LS);
-        if (mma_warp)
-        {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                {
-                    const int r = row0 + i * 8 + g, c = col0 + j * 8 + tg * 2;
-                    Ls[r][c] = acc[i][j][0];
-                    Ls[r][c + 1] = acc[i][j][1];
-                }
-        }
-        __syncthreads();
-        const int fail = potrf_inv_tile64(dyn_smem, tid);
-        store_factored_tile(dyn_smem, A + r0 * ld + c0, ld, linv + (size_t)ti * TB * TB, tid);
-        report_fail(info, fail, (int)r0);
-        return;
-    }
-    if (mma_warp)
-    {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<double2 *>(A + (r0 + row0 + i * 8 + g) * ld + c0 + col0 + j * 8 + tg * 2) =
-                    make_double2(acc[i][j][0], acc[i][j][1]);
-    }
 }
 
 __global__ void k_pad_identity(int n, double *__restrict__ A, int ld)
@@ -365,6 +213,8 @@ struct PotrfDf
     int *pair_flag;      // [(T+1)/2]
     int *info;
     double2 *d1tag;      // [T][D1_PAIRS]: what the next chain task needs of a factored diagonal tile, tagged
+    double *gbuf;        // [T2(T2-1)/2][128][128]: G_ik = W_i L_ik, the blocks the solves stream (see k_trsv_df)
+    double *gbufT;       // the same blocks transposed (backward sweep)
 };
 // payload of a tagged D1: the six strictly-lower 16x16 blocks of L_jj, then its four 16x16 diagonal inverses
 static constexpr int D1_PAIRS = 6 * 256 + 4 * 256;
@@ -385,7 +235,7 @@ __device__ __forceinline__ void d1_slot(int p, bool &is_l, int &r, int &c)
         c = 16 * b + (e & 15);
     }
 }
-enum { TASK_TILE = 0, TASK_PAIR = 1, TASK_CHAIN = 2 };
+enum { TASK_TILE = 0, TASK_PAIR = 1, TASK_CHAIN = 2, TASK_G = 3 };
 
 __device__ __forceinline__ void ldcg_tile_chunk(double (*S)[KP], const double *g, size_t ld, int tid)
 {   // 64 x KC block, bypassing L1 (the tile was written by another SM during this launch)
@@ -456,6 +306,99 @@ __device__ void pair_inverse_128(unsigned char *smem, const double *__restrict__
             dmma_8x8x4(c0, c1, -S1[8 * warp + g][kk + tg], S0[kk + tg][8 * nb + g]);
         *reinterpret_cast<double2 *>(out + (size_t)(64 + 8 * warp + g) * 128 + 8 * nb + 2 * tg) = make_double2(c0, c1);
     }
+}
+
+// G = blockdiag(W_i) L for block row i and tile column tj (both 64x64 tiles of the 128-row block), WITHOUT
+// the 128x128 pair inverse: with W_i = [W0 0; -W1 L10 W0, W1],
+//     G0 = W0 L(2i, tj)                         needs D2(2i)            (long before the end)
+//     T  = L(2i+1, tj) - L10 G0                 needs tile (2i+1, 2i)   (published before chain(2i+1) factors)
+//     G1 = W1 T                                 needs D2(2i+1)          (one GEMM after the last inverse)
+// so the tail of the factorisation is not lengthened by the solves' operand.  Warp w owns rows 8w..8w+7.
+__device__ void g_rows(unsigned char *smem, const PotrfDf &P, const DfCtl &C, int epoch, int i, int tj, int tid)
+{
+    double(*S0)[XP] = reinterpret_cast<double(*)[XP]>(smem + SM_LS);
+    double(*S1)[XP] = reinterpret_cast<double(*)[XP]>(smem + SM_LI);
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const int T = P.T, ld = P.ld, t0 = 2 * i, t1 = 2 * i + 1;
+    double *out = P.gbuf + ((size_t)i * (i - 1) / 2 + (tj >> 1)) * 128 * 128 + 64 * (tj & 1);
+    // transposed copy for the backward sweep (its threads then read contiguous rows, like the forward sweep)
+    double *outT = P.gbufT + ((size_t)i * (i - 1) / 2 + (tj >> 1)) * 128 * 128 + (size_t)(64 * (tj & 1)) * 128;
+    auto put = [&](const double acc[8][2], int a) {
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+        {
+            *reinterpret_cast<double2 *>(out + (size_t)(64 * a + 8 * warp + g) * 128 + 8 * nb + 2 * tg) =
+                make_double2(acc[nb][0], acc[nb][1]);
+            outT[(size_t)(8 * nb + 2 * tg) * 128 + 64 * a + 8 * warp + g] = acc[nb][0];
+            outT[(size_t)(8 * nb + 2 * tg + 1) * 128 + 64 * a + 8 * warp + g] = acc[nb][1];
+        }
+    };
+    auto stage = [&](double (*S)[XP], const double *src, size_t lds) {
+        for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
+        {
+            const int r = idx >> 5, c2 = (idx & 31) * 2;
+            *reinterpret_cast<double2 *>(&S[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)r * lds + c2));
+        }
+    };
+    auto gemm = [&](double acc[8][2], double sign, int kend) {     // acc += sign * S0 S1 (k < kend)
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+            for (int kk = 0; kk < kend; kk += 4)
+                dmma_8x8x4(acc[nb][0], acc[nb][1], sign * S0[8 * warp + g][kk + tg], S1[kk + tg][8 * nb + g]);
+    };
+    double acc[8][2];
+    // ---- G0 = W0 L(2i, tj) ---------------------------------------------------------------------------
+    if (tid == 0)
+    {
+        spin_until(P.d2_flag + t0, epoch, C.err);
+        spin_until(P.tile_flag + t0 * T + tj, epoch, C.err);
+    }
+    __syncthreads();
+    stage(S0, P.linv + (size_t)t0 * TB * TB, TB);
+    stage(S1, P.A + (size_t)t0 * TB * ld + (size_t)tj * TB, ld);
+    __syncthreads();
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+        acc[nb][0] = acc[nb][1] = 0.0;
+    gemm(acc, 1.0, 8 * warp + 8);                      // W0 lower triangular
+    put(acc, 0);
+    if (t1 >= T) return;                                // odd tile count: the block has one tile row
+    __syncthreads();
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)                      // G0 becomes the right operand
+        *reinterpret_cast<double2 *>(&S1[8 * warp + g][8 * nb + 2 * tg]) = make_double2(acc[nb][0], acc[nb][1]);
+    // ---- T = L(2i+1, tj) - L10 G0 ------------------------------------------------------------------------
+    if (tid == 0)
+    {
+        spin_until(P.tile_flag + t1 * T + t0, epoch, C.err);
+        spin_until(P.tile_flag + t1 * T + tj, epoch, C.err);
+    }
+    __syncthreads();
+    stage(S0, P.A + (size_t)t1 * TB * ld + (size_t)t0 * TB, ld);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+    {
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(
+            P.A + ((size_t)t1 * TB + 8 * warp + g) * ld + (size_t)tj * TB + 8 * nb + 2 * tg));
+        acc[nb][0] = v.x;
+        acc[nb][1] = v.y;
+    }
+    __syncthreads();
+    gemm(acc, -1.0, TB);
+    __syncthreads();
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+        *reinterpret_cast<double2 *>(&S1[8 * warp + g][8 * nb + 2 * tg]) = make_double2(acc[nb][0], acc[nb][1]);
+    // ---- G1 = W1 T -------------------------------------------------------------------------------------
+    if (tid == 0) spin_until(P.d2_flag + t1, epoch, C.err);
+    __syncthreads();
+    stage(S0, P.linv + (size_t)t1 * TB * TB, TB);
+    __syncthreads();
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+        acc[nb][0] = acc[nb][1] = 0.0;
+    gemm(acc, 1.0, 8 * warp + 8);
+    put(acc, 1);
 }
 
 // acc (warp tile 32x16 of the 8-warp 2x4 grid) -= X(rows) X(cols)' with both operands in one
@@ -696,6 +639,14 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             continue;
         }
 
+        if (type == TASK_G)
+        {   // ---- two 64x64 tiles of G = blockdiag(W) L: block row ti, tile column tj (consumed by the
+            //      solves only: visible at kernel end, nothing inside this launch waits for them)
+            g_rows(dyn_smem, P, C, epoch, ti, tj, tid);
+            DFT(t, 3);
+            continue;
+        }
+
         if (type == TASK_TILE)
         {   // ---- regular off-diagonal tile (ti >= tj + 2): left-looking accumulation, then X = acc L_jj^-T
             const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
@@ -847,23 +798,18 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
     df_epilogue(C);
 }
 
-// pair inverses after the panel-launch factorisation (A/B path): one CTA per 128x128 diagonal block
-__global__ void __launch_bounds__(NT_TILE) k_pair_inverse(const double *__restrict__ A, int ld, int T,
-                                                          const double *__restrict__ linv,
-                                                          double *__restrict__ linv128)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const int b = blockIdx.x, j0 = 2 * b, j1 = j0 + 1;
-    pair_inverse_128(dyn_smem, j1 < T ? A + (size_t)j1 * TB * ld + (size_t)j0 * TB : nullptr, ld,
-                     linv + (size_t)j0 * TB * TB, linv + (size_t)(j1 < T ? j1 : j0) * TB * TB,
-                     linv128 + (size_t)b * 128 * 128, threadIdx.x);
-}
-
 // ---------------------------------------------------------------------------------------------
-// data-flow triangular solves: ONE launch for L y = b and L' x = y, 128-row blocks.
-// Tasks 0..T2-1 are the forward blocks (ascending), T2..2T2-1 the backward blocks (descending); a block
-// accumulates its right-hand side as the blocks it depends on arrive, then multiplies by the
-// pre-inverted 128x128 diagonal block held in shared memory.
+// data-flow triangular solves: ONE launch for both sweeps, 128-row blocks.
+//
+// With D = blockdiag(L_ii) (128x128 blocks), W = D^-1 and G = W L (unit block diagonal; formed tile by
+// tile inside k_potrf_df), M = L L' = D G G' D'.  So M x = b is
+//     forward   G y = W b        y_i = (W_i b_i) - sum_{k<i} G_ik y_k
+//     backward  G' z = y         z_i = y_i - sum_{k>i} G_ki' z_k
+//     scaling   x_i = W_i' z_i
+// and a hop of either sweep is ONE 128x128 block times the vector that just arrived, with the block
+// already sitting in registers - the two diagonal-inverse products are off the chain (before the
+// forward loop, after the backward hand-off).  Tasks 0..T2-1 are the forward blocks (ascending),
+// T2..2T2-1 the backward blocks (descending), claimed in dependency order.
 // Hand-off without flags or fences: every published value travels as one aligned 16-byte
 // {value, epoch tag} store; the consumer polls the pair itself (relaxed 128-bit loads) until the tag
 // is this launch's epoch, so a hop costs one store -> L2 -> load round trip.
@@ -874,11 +820,11 @@ static constexpr int TRSV_SMEM = 128 * WP * 8;
 
 struct TrsvDf
 {
-    const double *L;
+    const double *G, *GT;            // [T2(T2-1)/2][128][128], block (i,k) at i(i-1)/2 + k; GT = blocks transposed
     int ld, T2;
     const double *linv128;
     double *b;
-    double2 *fwd_val, *bwd_val;      // [T2*128] tagged y / x
+    double2 *fwd_val, *bwd_val;      // [T2*128] tagged y / z
 };
 
 __device__ __forceinline__ void trsv_load_w(double (*Ws)[WP], const double *__restrict__ Wg, int tid)
@@ -889,7 +835,7 @@ __device__ __forceinline__ void trsv_load_w(double (*Ws)[WP], const double *__re
         *reinterpret_cast<double2 *>(&Ws[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(Wg + (size_t)r * 128 + c2));
     }
 }
-// warp 0 polls the 128 tagged values of block k into dst (padded by one per 32), then the block syncs
+// warp 0 polls the 128 tagged values of a block into dst (padded by one per 32), then the block syncs
 __device__ __forceinline__ void trsv_fetch(double *dst, const double2 *src, double tag, int *err, int tid)
 {
     if (tid < 32)
@@ -926,6 +872,7 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ int s_task;
     __shared__ double ys[2][132];
+    __shared__ double yi[132];
     __shared__ double rs[128];
     double(*Ws)[WP] = reinterpret_cast<double(*)[WP]>(dyn_smem);
     const int tid = threadIdx.x, e = tid >> 2, q = tid & 3;
@@ -945,76 +892,83 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         double cur[32];
         if (fwd)
-        {   // ---- L y = b: thread (row e, q) owns columns q*32..q*32+31 of every block of its row ------
+        {   // ---- G y = W b: thread (row e, q) owns the column pairs 8j + 2q, 8j + 2q + 1 of its row -------
             const bool rv = ge < ld;
+            const double *Grow = P.G + ((size_t)i * (i - 1) / 2) * 128 * 128 + (size_t)e * 128 + 2 * q;
             auto load_cur = [&](int k) {
-                const double2 *src = reinterpret_cast<const double2 *>(P.L + (size_t)ge * ld + (size_t)k * 128 + q * 32);
+                const double *src = Grow + (size_t)k * 128 * 128;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                 {
-                    const double2 v = rv ? __ldcg(src + j) : make_double2(0.0, 0.0);
+                    const double2 v = rv ? __ldcg(reinterpret_cast<const double2 *>(src + 8 * j)) : make_double2(0.0, 0.0);
                     cur[2 * j] = v.x;
                     cur[2 * j + 1] = v.y;
                 }
             };
             if (i > 0) load_cur(0);
-            for (int k = 0; k < i; ++k)
-            {
-                const double *yk = ys[k & 1] + q * 33;
-                trsv_fetch(ys[k & 1], P.fwd_val + (size_t)k * 128, tag, C.err, tid);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                {
-                    a0 -= cur[j] * yk[j];
-                    a1 -= cur[j + 1] * yk[j + 1];
-                    a2 -= cur[j + 2] * yk[j + 2];
-                    a3 -= cur[j + 3] * yk[j + 3];
-                }
-                if (k + 1 < i) load_cur(k + 1);
-            }
-            DFT(4096 + t, 1);
-            double acc = (a0 + a1) + (a2 + a3);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (q == 0) rs[e] = (rv ? __ldcg(P.b + ge) : 0.0) + acc;
+            if (tid < 128) rs[tid] = (i * 128 + tid < ld) ? __ldcg(P.b + i * 128 + tid) : 0.0;
             __syncthreads();
-            a0 = a1 = a2 = a3 = 0.0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)          // columns interleaved over q: conflict-free with WP % 16 == 4
+            for (int j = 0; j < 32; j += 4)          // (W_i b_i): columns interleaved over q, conflict-free with WP % 16 == 4
             {
                 a0 += Ws[e][4 * j + q] * rs[4 * j + q];
                 a1 += Ws[e][4 * j + 4 + q] * rs[4 * j + 4 + q];
                 a2 += Ws[e][4 * j + 8 + q] * rs[4 * j + 8 + q];
                 a3 += Ws[e][4 * j + 12 + q] * rs[4 * j + 12 + q];
             }
+            for (int k = 0; k < i; ++k)
+            {
+                const double *yk = ys[k & 1];
+                trsv_fetch(ys[k & 1], P.fwd_val + (size_t)k * 128, tag, C.err, tid);
+#pragma unroll
+                for (int j = 0; j < 16; j += 2)
+                {   // column c = 8j + 2q (+1) lives at yk[c + (c >> 5)]
+                    const int c0 = 8 * j + 2 * q, c1 = 8 * (j + 1) + 2 * q;
+                    a0 -= cur[2 * j] * yk[c0 + (c0 >> 5)];
+                    a1 -= cur[2 * j + 1] * yk[c0 + 1 + (c0 >> 5)];
+                    a2 -= cur[2 * j + 2] * yk[c1 + (c1 >> 5)];
+                    a3 -= cur[2 * j + 3] * yk[c1 + 1 + (c1 >> 5)];
+                }
+                if (k + 1 < i) load_cur(k + 1);
+            }
+            DFT(4096 + t, 1);
             double yv = (a0 + a1) + (a2 + a3);
             yv += __shfl_xor_sync(0xffffffffu, yv, 1);
             yv += __shfl_xor_sync(0xffffffffu, yv, 2);
             if (q == 0) st_tagged(P.fwd_val + ge, yv, tag);
         }
         else
-        {   // ---- L' x = y: thread (column e, q) owns rows 4j+q of every block below ---------------------
+        {   // ---- G' z = y, then x = W' z: thread (column e, q) owns rows 4j + q of every block below -------
+            // row e of the transposed block (k, i) = column e of G_ki; the pair (8j + 2q, 8j + 2q + 1) are rows of
+            // block k: both beyond ld (odd tile count) only if the whole pair is (rows come in 64s)
             auto load_cur = [&](int k) {
+                const double *src = P.GT + ((size_t)k * (k - 1) / 2 + i) * 128 * 128 + (size_t)e * 128 + 2 * q;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < 16; ++j)
                 {
-                    const int gr = k * 128 + 4 * j + q;
-                    cur[j] = gr < ld ? __ldcg(P.L + (size_t)gr * ld + ge) : 0.0;
+                    const double2 v = (k * 128 + 8 * j + 2 * q < ld) ? __ldcg(reinterpret_cast<const double2 *>(src + 8 * j))
+                                                                  : make_double2(0.0, 0.0);
+                    cur[2 * j] = v.x;
+                    cur[2 * j + 1] = v.y;
                 }
             };
             if (i < T2 - 1) load_cur(T2 - 1);
+            // y_i (tagged forward result of the same rows) is final long before this block's turn: fetch it
+            // now, not on the chain
+            trsv_fetch(yi, P.fwd_val + (size_t)i * 128, tag, C.err, tid);
             for (int k = T2 - 1; k > i; --k)
             {
                 const double *xk = ys[k & 1];
                 trsv_fetch(ys[k & 1], P.bwd_val + (size_t)k * 128, tag, C.err, tid);
                 DFT(4096 + t, 4);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
+                for (int j = 0; j < 16; j += 2)
                 {
-                    a0 -= cur[j] * xk[4 * j + q + (j >> 3)];
-                    a1 -= cur[j + 1] * xk[4 * j + 4 + q + (j >> 3)];
-                    a2 -= cur[j + 2] * xk[4 * j + 8 + q + (j >> 3)];
-                    a3 -= cur[j + 3] * xk[4 * j + 12 + q + (j >> 3)];
+                    const int c0 = 8 * j + 2 * q, c1 = 8 * (j + 1) + 2 * q;
+                    a0 -= cur[2 * j] * xk[c0 + (c0 >> 5)];
+                    a1 -= cur[2 * j + 1] * xk[c0 + 1 + (c0 >> 5)];
+                    a2 -= cur[2 * j + 2] * xk[c1 + (c1 >> 5)];
+                    a3 -= cur[2 * j + 3] * xk[c1 + 1 + (c1 >> 5)];
                 }
                 if (k - 1 > i) load_cur(k - 1);
             }
@@ -1022,10 +976,13 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
             double acc = (a0 + a1) + (a2 + a3);
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            // y_i (tagged forward result of the same rows)
-            trsv_fetch(ys[i & 1], P.fwd_val + (size_t)i * 128, tag, C.err, tid);
             DFT(4096 + t, 5);
-            if (q == 0) rs[e] = ys[i & 1][e + (e >> 5)] + acc;
+            const double z = yi[e + (e >> 5)] + acc;
+            if (q == 0)
+            {
+                st_tagged(P.bwd_val + ge, z, tag);       // hand-off first: the scaling below is off the chain
+                rs[e] = z;
+            }
             __syncthreads();
             a0 = a1 = a2 = a3 = 0.0;
 #pragma unroll
@@ -1040,11 +997,7 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
             DFT(4096 + t, 6);
             xv += __shfl_xor_sync(0xffffffffu, xv, 1);
             xv += __shfl_xor_sync(0xffffffffu, xv, 2);
-            if (q == 0)
-            {
-                st_tagged(P.bwd_val + ge, xv, tag);
-                if (ge < ld) P.b[ge] = xv;
-            }
+            if (q == 0 && ge < ld) P.b[ge] = xv;
         }
         DFT(4096 + t, 3);
     }
@@ -1065,14 +1018,27 @@ static int build_task_list(ErrorSink &err, CholWork &W, int T)
         return SB200_OK;
     }
     std::vector<int2> tasks;
+    auto push_g = [&](int i) {           // G tiles of block row i: one task per tile column below the block
+        for (int tj = 0; tj < 2 * i; ++tj)
+            tasks.push_back(make_int2(i | (TASK_G << 16), tj));
+    };
+    int g_done = 0;                      // block rows whose G tasks are listed
     for (int j = 0; j < T; ++j)
     {
         tasks.push_back(make_int2(j | (TASK_CHAIN << 16), j));      // tile (j, j-1) + diagonal tile j
-        if (j & 1) tasks.push_back(make_int2(TASK_PAIR << 16, j >> 1));
-        else if (j == T - 1) tasks.push_back(make_int2(TASK_PAIR << 16, j >> 1));    // odd tile count
+        if ((j & 1) || j == T - 1)
+            tasks.push_back(make_int2(TASK_PAIR << 16, j >> 1));    // j even and last: odd tile count
         for (int i = j + 2; i < T; ++i)
             tasks.push_back(make_int2(i | (TASK_TILE << 16), j));
+        // block row i is complete after column 2i+1; list its G tasks two columns later: their inputs are
+        // final by then, so the CTAs that claim them do not sit on a slot spinning (matters when T is large)
+        // (when the task list is longer than the grid can hold at once, they go to the very end instead:
+        // interleaved they cost the m = 4096 factorisation 40 %, at the end they are a short tail)
+        while (T <= 20 && 2 * g_done + 3 <= j)
+            push_g(g_done++);
     }
+    while (2 * g_done < T)
+        push_g(g_done++);
     W.tasks = nullptr;
     SB200_CUDA_TRY(err, cudaMalloc(&W.tasks, sizeof(int2) * tasks.size()));
     SB200_CUDA_TRY(err, cudaMemcpy(W.tasks, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice));
@@ -1096,6 +1062,13 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve)
         SB200_CUDA_TRY(err, cudaMalloc(&W.linv, sizeof(double) * (size_t)T * TB * TB));
         SB200_CUDA_TRY(err, cudaMemset(W.linv, 0, sizeof(double) * (size_t)T * TB * TB));
         SB200_CUDA_TRY(err, cudaMalloc(&W.linv128, sizeof(double) * (size_t)T2 * 128 * 128));
+        {
+            const size_t nblk = (size_t)T2 * (T2 - 1) / 2;
+            SB200_CUDA_TRY(err, cudaMalloc(&W.gbuf, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
+            SB200_CUDA_TRY(err, cudaMemset(W.gbuf, 0, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
+            SB200_CUDA_TRY(err, cudaMalloc(&W.gbufT, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
+            SB200_CUDA_TRY(err, cudaMemset(W.gbufT, 0, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
+        }
         SB200_CUDA_TRY(err, cudaMalloc(&W.d1tag, sizeof(double2) * (size_t)T * D1_PAIRS));
         SB200_CUDA_TRY(err, cudaMemset(W.d1tag, 0, sizeof(double2) * (size_t)T * D1_PAIRS));
         SB200_CUDA_TRY(err, cudaMalloc(&W.tagged, sizeof(double2) * (size_t)T2 * 128 * 2));
@@ -1106,16 +1079,11 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve)
         int dev = 0;
         SB200_CUDA_TRY(err, cudaGetDevice(&dev));
         SB200_CUDA_TRY(err, cudaDeviceGetAttribute(&W.sms, cudaDevAttrMultiProcessorCount, dev));
-        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_potrf_first, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_potrf_df, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_pair_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         SB200_CUDA_TRY(err, cudaFuncSetAttribute(k_trsv_df, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
         int occ = 0;
         SB200_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_potrf_df, NT_TILE, SM_TOTAL));
         W.potrf_occ = occ < 1 ? 1 : occ;
-        const char *mode = getenv("SB200_POTRF");
-        W.panel_mode = (mode && std::string(mode) == "panel") ? 1 : 0;
     }
     if (T_now != W.tasks_T) return build_task_list(err, W, T_now);
     return SB200_OK;
@@ -1131,6 +1099,8 @@ void chol_work_free(CholWork &W)
     if (W.ctl) cudaFree(W.ctl);
     if (W.tagged) cudaFree(W.tagged);
     if (W.d1tag) cudaFree(W.d1tag);
+    if (W.gbuf) cudaFree(W.gbuf);
+    if (W.gbufT) cudaFree(W.gbufT);
     W = CholWork{};
 }
 
@@ -1140,24 +1110,9 @@ void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t
 {
     (void)n;
     const int T = ld / TB, T2 = (T + 1) / 2;
-    if (W.panel_mode)
-    {
-        k_potrf_first<<<1, NT_TILE, SM_TOTAL, st>>>(a, ld, W.linv, info);
-        ++g_launch_count;
-        for (int k = 0; k + 1 < T; ++k)
-        {
-            const int rem = T - 1 - k;
-            k_trsm_panel<<<rem, 128, 0, st>>>(a, ld, k, W.linv);
-            k_update<<<rem * (rem + 1) / 2, NT_TILE, SM_TOTAL, st>>>(a, ld, k, T, W.linv, info);
-            g_launch_count += 2;
-        }
-        k_pair_inverse<<<T2, NT_TILE, SM_TOTAL, st>>>(a, ld, T, W.linv, W.linv128);
-        ++g_launch_count;
-        return;
-    }
     int *ctl = W.ctl, *flags = W.ctl + 32;
     const size_t tc = (size_t)W.t_cap;
-    PotrfDf P{a, ld, T, W.linv, W.linv128, W.tasks, W.ntasks, flags, flags + tc * tc, flags + tc * tc + tc, info, W.d1tag};
+    PotrfDf P{a, ld, T, W.linv, W.linv128, W.tasks, W.ntasks, flags, flags + tc * tc, flags + tc * tc + tc, info, W.d1tag, W.gbuf, W.gbufT};
     DfCtl C{ctl + 0, reinterpret_cast<unsigned *>(ctl + 1), reinterpret_cast<unsigned *>(ctl + 2), ctl + 8};
     const int cap = W.sms * W.potrf_occ;
     const int grid = W.ntasks < cap ? W.ntasks : cap;
@@ -1172,7 +1127,8 @@ void launch_potrs(CholWork &W, int n, const double *l, int ld, double *b, cudaSt
     int *ctl = W.ctl, *flags = W.ctl + 32;
     const size_t tc = (size_t)W.t_cap, tc2 = (tc + 1) / 2;
     (void)flags;
-    TrsvDf P{l, ld, T2, W.linv128, b, W.tagged, W.tagged + tc2 * 128};
+    (void)l;     // the solves stream G = blockdiag(W) L, built by the factorisation
+    TrsvDf P{W.gbuf, W.gbufT, ld, T2, W.linv128, b, W.tagged, W.tagged + tc2 * 128};
     DfCtl C{ctl + 4, reinterpret_cast<unsigned *>(ctl + 5), reinterpret_cast<unsigned *>(ctl + 6), ctl + 8};
     const int grid = 2 * T2 < W.sms ? 2 * T2 : W.sms;
     k_trsv_df<<<grid, NT_TRSV, TRSV_SMEM, st>>>(P, C);

@@ -11,6 +11,8 @@ struct CholWork
 {
     double *linv = nullptr;     // [T][64][64] inverses of the 64x64 diagonal blocks of L
     double *linv128 = nullptr;  // [ceil(T/2)][128][128] inverses of the 128x128 diagonal blocks
+    double *gbufT = nullptr;    // the same blocks transposed (backward sweep)
+    double *gbuf = nullptr;     // [T2(T2-1)/2][128][128] G_ik = W_i L_ik: the blocks the solves stream
     double2 *d1tag = nullptr;   // [T][2560] tagged hand-off of a factored diagonal tile to the next chain task
     double2 *tagged = nullptr;  // [2][ceil(T/2)*128] {value, epoch tag}: forward / backward solve hand-off
     int *ctl = nullptr;         // epochs, task counters, error flag, then the publish flags
@@ -19,7 +21,6 @@ struct CholWork
     std::map<int, std::pair<int2 *, int>> task_cache;   // task lists by tile count (B&B nodes change m)
     int t_cap = 0;
     int sms = 148, potrf_occ = 1;
-    int panel_mode = 0;         // SB200_POTRF=panel: the two-launches-per-panel factorisation (A/B)
     int max_coop_grid = 148;
 };
 

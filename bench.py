@@ -417,7 +417,7 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = read_peaks()
         phases = {}
         names = {0: "assemble", 1: "potrf", 2: "potrs", 3: "spmv_csr", 4: "spmv_csc_recover", 5: "vector"}
-        per_iter = {"assemble": 1, "potrf": 1, "potrs": 2, "spmv_csr": 2, "spmv_csc_recover": 2, "vector": 3}
+        per_iter = {"assemble": 1, "potrf": 1, "potrs": 2, "spmv_csr": 2, "spmv_csc_recover": 2, "vector": 2}
         for pid, nm in ({} if args.no_phases else names).items():
             ms = C.c_double()
             if lib.sb200_time_phase(wss[0].handle, pid, 20, C.byref(ms)) == 0:

@@ -163,7 +163,7 @@ int sb200_model_info(sb200_ws *ws, long long *info, int n_info);
 void *sb200_stream(sb200_ws *ws);
 /* time one phase of the loop on the resident model with CUDA events on the workspace stream:
  * phase 0 = normal-matrix assembly, 1 = Cholesky factorisation, 2 = one solve (forward+backward),
- * 3 = CSR SpMV (rhs), 4 = CSC SpMV + recovery + ratio test, 5 = fused update kernel,
+ * 3 = CSR SpMV (rhs), 4 = CSC SpMV + recovery + ratio test, 5 = fused step-length / mu_aff / sigma / corrector kernel(s),
  * 6 = one whole CG iteration, 7 = its A'p product, 8 = its A q product (PCG strategy only).
  * Writes the mean milliseconds per launch group over `reps` runs (after one warm-up). */
 int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out);

@@ -376,8 +376,7 @@ void enqueue_iteration_direct(sb200_ws *ws)
     launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);                 // rhs = resB + A t
     launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, V.rhs, st);            // dy (affine)
     launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
-    launch_affine_mu(V, st);
-    launch_corrector(V, st);
+    launch_affine_corrector(V, st);
     launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);
     launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, V.rhs, st);            // dy (corrector)
     launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
@@ -396,8 +395,7 @@ int run_iteration_pcg(sb200_ws *ws)
     launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);
     if ((rc = enqueue_or_run_solve(ws, V.d, 0.0, 1))) return rc;
     launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
-    launch_affine_mu(V, st);
-    launch_corrector(V, st);
+    launch_affine_corrector(V, st);
     launch_spmv_csr(A, V.t, V.resB, V.rhs, 1.0, 1.0, st);
     if ((rc = enqueue_or_run_solve(ws, V.d, 0.0, 1))) return rc;
     launch_spmv_csc(At, CSC_RECOVER, V.dy, nullptr, nullptr, 0, 0, &V, st);
@@ -1045,7 +1043,7 @@ int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out)
         case 2: launch_potrs(ws->chol, ws->m, ws->M, ws->mpad, V.rhs, st); break;
         case 3: launch_spmv_csr(csr_of(ws), V.t, V.resB, V.rhs, 1.0, 1.0, st); break;
         case 4: launch_spmv_csc(csc_of(ws), CSC_RECOVER, V.y, nullptr, nullptr, 0, 0, &V, st); break;
-        case 5: launch_affine_mu(V, st); break;
+        case 5: launch_affine_corrector(V, st); break;
         case 6:
         case 7:
         case 8:

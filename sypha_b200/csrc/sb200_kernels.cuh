@@ -74,6 +74,7 @@ void launch_init_mu(const IpmVecs &V, const DevParams *P, cudaStream_t st);   //
 void launch_prologue(const IpmVecs &V, cudaStream_t st);
 void launch_affine_mu(const IpmVecs &V, cudaStream_t st);
 void launch_corrector(const IpmVecs &V, cudaStream_t st);
+void launch_affine_corrector(const IpmVecs &V, cudaStream_t st);     // both; one single-CTA kernel when n is small
 void launch_update(const IpmVecs &V, const DevParams *P, cudaStream_t st);    // P: device pointer
 void launch_start_shift1(const IpmVecs &V, cudaStream_t st);
 void launch_start_shift2(const IpmVecs &V, cudaStream_t st);

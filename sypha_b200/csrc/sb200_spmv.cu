@@ -27,13 +27,23 @@ k_spmv_csr(int m, const int *__restrict__ offs, const int *__restrict__ inds,
     for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < m; row += gridDim.x * wpb)
     {
         const int a = offs[row], e = offs[row + 1];
-        double acc = 0.0;
-        for (int k = a + lane; k < e; k += 32)
+        // four index/value pairs per lane in flight: at OR-Library sizes (1000 rows of 500 entries) the
+        // kernel is one warp per row on fewer warps than the GPU has schedulers, i.e. a chain of dependent
+        // L2 latencies (index -> gather); unrolling the chain is what shortens it
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        for (int k = a + lane; k < e; k += 128)
         {
-            const double v = vals[k];
-            const double xv = __ldg(x + inds[k]);
-            acc += (MODE == 1) ? v * v * xv : v * xv;
+            const int k1 = k + 32, k2 = k + 64, k3 = k + 96;
+            const bool h1 = k1 < e, h2 = k2 < e, h3 = k3 < e;
+            const int i0 = inds[k], i1 = h1 ? inds[k1] : 0, i2 = h2 ? inds[k2] : 0, i3 = h3 ? inds[k3] : 0;
+            const double v0 = vals[k], v1 = h1 ? vals[k1] : 0.0, v2 = h2 ? vals[k2] : 0.0, v3 = h3 ? vals[k3] : 0.0;
+            const double x0 = __ldg(x + i0), x1 = __ldg(x + i1), x2 = __ldg(x + i2), x3 = __ldg(x + i3);
+            acc0 += (MODE == 1) ? v0 * v0 * x0 : v0 * x0;
+            acc1 += (MODE == 1) ? v1 * v1 * x1 : v1 * x1;
+            acc2 += (MODE == 1) ? v2 * v2 * x2 : v2 * x2;
+            acc3 += (MODE == 1) ? v3 * v3 * x3 : v3 * x3;
         }
+        double acc = (acc0 + acc1) + (acc2 + acc3);
         acc = warp_sum(acc);
         if (lane == 0)
         {
@@ -65,6 +75,13 @@ void launch_jacobi_diag(const CsrView &A, const double *d, double *diag, cudaStr
 // CSC: G lanes per column (G = 1..32 chosen from the mean column length), segmented shuffle
 // reduction, epilogue by the group leader.
 // ---------------------------------------------------------------------------------------------
+// atomicMin with a relaxed pre-check: the value read can only be >= the current minimum, so skipping when
+// key >= read never loses a smaller key; the result stays the exact minimum
+__device__ __forceinline__ void ord_min(unsigned long long *addr, unsigned long long key)
+{
+    if (key < *reinterpret_cast<volatile unsigned long long *>(addr)) atomicMin(addr, key);
+}
+
 template <int G>
 __device__ __forceinline__ double group_sum(double v)
 {
@@ -92,9 +109,17 @@ k_spmv_csc(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
          col += gridDim.x * groups_per_block)
     {
         double acc = 0.0;
+        double e_rc = 0.0, e_x = 0.0, e_s = 1.0, e_rxs = 0.0;
         if (col < n)
         {
             const int a = colptr[col], e = colptr[col + 1];
+            if (MODE == CSC_RECOVER && gl == 0)
+            {   // epilogue operands requested together with the column, not after the reduction
+                e_rc = V.resC[col];
+                e_x = V.x[col];
+                e_s = V.s[col];
+                e_rxs = V.resXS[col];
+            }
             for (int k = a + gl; k < e; k += G)
                 acc += vals[k] * __ldg(v + rows[k]);
         }
@@ -105,9 +130,9 @@ k_spmv_csc(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
                 out[col] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[col];
             else if (MODE == CSC_RECOVER)
             {   // krylov.cu:74-82 + utils.cu:68-79
-                const double ds = V.resC[col] - acc;
-                const double xj = V.x[col], sj = V.s[col];
-                const double dx = (V.resXS[col] - xj * ds) / sj;
+                const double ds = e_rc - acc;
+                const double xj = e_x, sj = e_s;
+                const double dx = (e_rxs - xj * ds) / sj;
                 V.ds[col] = ds;
                 V.dx[col] = dx;
                 if (dx < 0.0) m0 = fmin(m0, -xj / dx);
@@ -133,16 +158,16 @@ k_spmv_csc(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
         m0 = block_min(m0, sh);
         m1 = block_min(m1, sh);
         if (threadIdx.x == 0)
-        {
+        {   // a CTA that cannot lower the minimum does not touch it (hundreds of CTAs, two addresses)
             if (MODE == CSC_RECOVER)
             {
-                atomicMin(&V.sc->amax_p, ord_encode(m0));
-                atomicMin(&V.sc->amax_d, ord_encode(m1));
+                ord_min(&V.sc->amax_p, ord_encode(m0));
+                ord_min(&V.sc->amax_d, ord_encode(m1));
             }
             else if (MODE == CSC_START_X)
-                atomicMin(&V.sc->min_x, ord_encode(m0));
+                ord_min(&V.sc->min_x, ord_encode(m0));
             else
-                atomicMin(&V.sc->min_s, ord_encode(m1));
+                ord_min(&V.sc->min_s, ord_encode(m1));
         }
     }
 }

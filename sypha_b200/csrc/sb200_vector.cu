@@ -226,6 +226,44 @@ void launch_affine_mu(const IpmVecs &V, cudaStream_t st)
     ++g_launch_count;
 }
 
+// Tiny LPs (scp4x: n = 1200): the step-length / mu_aff / sigma reduction and the corrector right-hand side
+// are ONE single-CTA kernel - no partials, no last-block ticket, one launch instead of two.  Not beyond a
+// few thousand columns: one SM pulls ~126 GB/s from L2, and at n = 11000 the single-CTA pair measured
+// 19.1 us against 6.4 + 4.3 us for the multi-CTA kernels.
+static constexpr int kSingleCtaMax = 4096;
+static constexpr int kSingleCtaThreads = 1024;
+__global__ void __launch_bounds__(kSingleCtaThreads) k_affine_corrector(IpmVecs V)
+{
+    __shared__ double sh[32];
+    __shared__ double s_sm;
+    Scalars *sc = V.sc;
+    if (sc->done) return;
+    const double ap = fmin(1.0, ord_decode(sc->amax_p));
+    const double ad = fmin(1.0, ord_decode(sc->amax_d));
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < V.n; j += blockDim.x)
+        acc += (V.x[j] + ap * V.dx[j]) * (V.s[j] + ad * V.ds[j]);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0)
+    {
+        const double mu_aff = acc / (double)V.n;
+        const double r = mu_aff / sc->mu;
+        sc->mu_aff = mu_aff;
+        sc->sigma = r * r * r;                        // gsl_pow_3, :622
+        sc->amax_p = sc->amax_d = SB200_ORD_DBL_MAX;  // re-arm the ratio test
+        s_sm = r * r * r * sc->mu;
+    }
+    __syncthreads();
+    const double sm = s_sm;
+    for (int j = threadIdx.x; j < V.n; j += blockDim.x)
+    {
+        const double corr = -V.dx[j] * V.ds[j] + sm;
+        const double rxs = V.resXS[j] + corr;
+        V.resXS[j] = rxs;
+        V.t[j] = (V.x[j] * V.resC[j] - rxs) / V.s[j];
+    }
+}
+
 // resXS += -dxa.*dsa + sigma*mu ; t = (x.*resC - resXS)/s      (sypha_solver.cpp:625-629)
 __global__ void k_corrector(IpmVecs V)
 {
@@ -244,6 +282,17 @@ void launch_corrector(const IpmVecs &V, cudaStream_t st)
 {
     k_corrector<<<grid_for(V.n, kBlock), kBlock, 0, st>>>(V);
     ++g_launch_count;
+}
+void launch_affine_corrector(const IpmVecs &V, cudaStream_t st)
+{
+    if (V.n <= kSingleCtaMax)
+    {
+        k_affine_corrector<<<1, kSingleCtaThreads, 0, st>>>(V);
+        ++g_launch_count;
+        return;
+    }
+    launch_affine_mu(V, st);
+    launch_corrector(V, st);
 }
 
 // step, residual scaling, mu / objectives / termination, and the next iteration's prologue
@@ -350,7 +399,11 @@ __global__ void k_update(IpmVecs V, const DevParams *__restrict__ Pp)
 }
 void launch_update(const IpmVecs &V, const DevParams *P, cudaStream_t st)
 {
-    k_update<<<grid_for(max(V.n, V.m), kBlock), kBlock, 0, st>>>(V, P);
+    const int lim = max(V.n, V.m);
+    if (lim <= kSingleCtaMax)       // one CTA: the "last block" is the only block
+        k_update<<<1, kSingleCtaThreads, 0, st>>>(V, P);
+    else
+        k_update<<<grid_for(lim, kBlock), kBlock, 0, st>>>(V, P);
     ++g_launch_count;
 }
 

@@ -37,6 +37,7 @@ WORKLOADS = {
     "scpnrh": (1000, 10000, 0.05, "scpnrh-shaped synthetic SCP LP relaxation 1000x10000, 5% density (configs[1])"),
     "scp4": (200, 1000, 0.02, "scp4x-shaped synthetic SCP LP relaxation 200x1000, 2% density (configs[0])"),
     "scpnrf": (500, 5000, 0.20, "scpnrf-shaped synthetic SCP LP relaxation 500x5000, 20% density (configs[2])"),
+    "scpclr13": (4095, 715, 0.125, "scpclr13-shaped synthetic SCP LP relaxation 4095x715, 12.5% density (configs[2])"),
     "synth5k": (5000, 100000, 0.001, "synthetic SCP 5000x100000, 0.1% density (configs[3] ladder rung)"),
     "synth50k": (50000, 1000000, 0.001, "synthetic SCP 50000x1000000, 0.1% density (configs[3])"),
 }
@@ -424,6 +425,11 @@ def run_ours(args, rank, world, local_rank):
                 by = algorithmic_bytes(info, nm)
                 phases[nm] = {"ms": ms.value, "algorithmic_bytes": by, "gbs": by / ms.value / 1e6,
                               "frac_hbm": by / ms.value / 1e6 / peak, "per_iteration": per_iter[nm]}
+                if nm == "potrf" or (nm == "assemble" and info["strategy"] == 2):
+                    # FP64 tensor-pipe kernels: m^3/3 (Cholesky), m^2 n (SYRK on the lower tiles)
+                    fl = info["m"] ** 3 / 3.0 if nm == "potrf" else float(info["m"]) ** 2 * info["n"]
+                    phases[nm].update({"flops": fl, "tflops": fl / ms.value / 1e9,
+                                       "frac_fp64_tensor": fl / ms.value / 1e9 / FP64_DMMA_TFLOPS})
         roof = None
         if phases:
             dom = max(phases, key=lambda k: phases[k]["ms"] * phases[k]["per_iteration"])

@@ -312,6 +312,7 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
                                                                         out->chunk_ptr, out->term16, (unsigned short)pad_id);
         SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
         out->n_chunks = total;
+        out->pad_id = pad_id;
         cudaFreeAsync(out->term_col, st);
         out->term_col = nullptr;
         g_launch_count += 2;
@@ -388,9 +389,102 @@ k_assemble_normal16(long long n_pairs, const unsigned int *__restrict__ chunk_pt
     }
 }
 
+// Same, with d staged in shared memory by persistent CTAs (one per SM).  ncu on the version above at scpnrh
+// size: lg_throttle 31 / long_scoreboard 20 stall cycles per issue - every 8-byte gather of d is its own L1
+// sector request (up to 32 per warp instruction), 14 M of them per launch.  From shared memory the same
+// gather is ~6 wavefronts per warp instruction; d (88 KB at n = 11000) is staged once per CTA.
+static constexpr int ASM_SMEM_THREADS = 1024;
+__device__ __forceinline__ double chunk_gather8_s(uint4 v, const double *ds)
+{
+    return ((ds[v.x & 0xffffu] + ds[v.x >> 16]) + (ds[v.y & 0xffffu] + ds[v.y >> 16])) +
+           ((ds[v.z & 0xffffu] + ds[v.z >> 16]) + (ds[v.w & 0xffffu] + ds[v.w >> 16]));
+}
+__global__ void __launch_bounds__(ASM_SMEM_THREADS, 1)
+k_assemble_normal16_smem(long long n_pairs, int m_rows, const unsigned int *__restrict__ chunk_ptr,
+                         const uint4 *__restrict__ term8, const double *__restrict__ d, int nd, double *__restrict__ M, int ld)
+{
+    extern __shared__ __align__(16) double ds[];
+    for (int i = threadIdx.x; i < nd; i += ASM_SMEM_THREADS)
+        ds[i] = d[i];
+    __syncthreads();
+    // ncu (source page) on the first form of this loop: 30 % of the stall samples sat on the first use of a
+    // chunk load and a warp ran 3.2 three-chunk trips per entry although the mean list is 3.1 chunks: the
+    // DIAGONAL entries carry a whole row (500 terms at scpnrh size) and one of them per row boundary kept
+    // its warp - and, at the end, the whole kernel - waiting.  So: off-diagonal entries one thread each with
+    // six chunk loads in flight and the next entry's bounds requested early; diagonal entries afterwards,
+    // one WARP each, lanes striding the chunks.
+    const long long stride = (long long)gridDim.x * ASM_SMEM_THREADS;
+    long long p = blockIdx.x * (long long)ASM_SMEM_THREADS + threadIdx.x;
+    unsigned int a = 0, e = 0;
+    if (p < n_pairs)
+    {
+        a = __ldg(chunk_ptr + p);
+        e = __ldg(chunk_ptr + p + 1);
+    }
+    while (p < n_pairs)
+    {
+        const long long pn = p + stride;
+        unsigned int na = 0, ne = 0;
+        if (pn < n_pairs)
+        {
+            na = __ldg(chunk_ptr + pn);
+            ne = __ldg(chunk_ptr + pn + 1);
+        }
+        long long i = (long long)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        const long long k = p - i * (i + 1) / 2;
+        if (k == i) e = a;                      // diagonal entry: left to the warp pass below
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (unsigned int c = a; c < e; c += 6)
+        {
+            uint4 v[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                v[q] = (c + q < e) ? __ldg(term8 + c + q) : make_uint4(0u, 0u, 0u, 0u);
+            s0 += chunk_gather8_s(v[0], ds);
+            if (c + 1 < e) s1 += chunk_gather8_s(v[1], ds);
+            if (c + 2 < e) s2 += chunk_gather8_s(v[2], ds);
+            if (c + 3 < e) s0 += chunk_gather8_s(v[3], ds);
+            if (c + 4 < e) s1 += chunk_gather8_s(v[4], ds);
+            if (c + 5 < e) s2 += chunk_gather8_s(v[5], ds);
+        }
+        if (k != i) M[i * ld + k] = (s0 + s1) + s2;
+        p = pn;
+        a = na;
+        e = ne;
+    }
+    // diagonal entries: M[r][r] = sum over the columns of row r, one warp per row
+    const int lane = threadIdx.x & 31, wpb = ASM_SMEM_THREADS >> 5;
+    for (long long r = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); r < m_rows; r += (long long)gridDim.x * wpb)
+    {
+        const long long pd = r * (r + 1) / 2 + r;
+        const unsigned int da = __ldg(chunk_ptr + pd), de = __ldg(chunk_ptr + pd + 1);
+        double sum = 0.0;
+        for (unsigned int c = da + lane; c < de; c += 32)
+            sum += chunk_gather8_s(__ldg(term8 + c), ds);
+        sum = warp_sum(sum);
+        if (lane == 0) M[r * ld + r] = sum;
+    }
+}
+
 void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld, cudaStream_t st)
 {
     const int grid = grid_for(P.n_pairs, 256, 148 * 64);
+    if (P.term16 && P.pad_id >= 0 && (size_t)(P.pad_id + 1) * 8 <= 200 * 1024 && P.n_pairs >= 148ll * ASM_SMEM_THREADS)
+    {
+        static bool attr_set = false;
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute(k_assemble_normal16_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        const int nd = P.pad_id + 1;
+        k_assemble_normal16_smem<<<148, ASM_SMEM_THREADS, sizeof(double) * (size_t)nd, st>>>(
+            P.n_pairs, P.m, P.chunk_ptr, reinterpret_cast<const uint4 *>(P.term16), d, nd, M, ld);
+        ++g_launch_count;
+        return;
+    }
     if (P.term16)
     {
         k_assemble_normal16<<<grid, 256, 0, st>>>(P.n_pairs, P.chunk_ptr, reinterpret_cast<const uint4 *>(P.term16), d, M, ld);

@@ -129,7 +129,7 @@ __device__ __forceinline__ unsigned long long df_now()
 #define SB200_V_LJ 0
 #endif
 #ifndef SB200_V_PUB
-#define SB200_V_PUB 0
+#define SB200_V_PUB 0      // 1: released after the diagonal update, 2: by warp 1 inside the tile factorisation (both measured equal to 0)
 #endif
 #ifndef SB200_V_ST
 #define SB200_V_ST 1
@@ -682,6 +682,7 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
         //      hand-off on the critical path per 64 columns is D1(j-1) -> here ------------------------
         const int j = tj, jm = tj - 1;
         const size_t c0 = (size_t)j * TB;
+        int *deferred = nullptr;
         double acc2[4][2][2];
         load_acc(acc2, c0, c0);
         if (j > 0)
@@ -710,7 +711,14 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             }
             __syncthreads();
             DFT(t, 1);
-#if SB200_V_PUB
+#if SB200_V_PUB == 2
+            trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
+            __syncthreads();                                    // Xs complete, X stored
+            DFT(t, 4);
+            warp_mma_xx(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), row0, col0, lane, acc2);
+            __syncthreads();
+            deferred = P.tile_flag + j * T + jm;                // released inside the factorisation (warp 1)
+#elif SB200_V_PUB
             trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
             __syncthreads();                                    // Xs complete
             DFT(t, 4);
@@ -741,7 +749,7 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
                     Ls[r][c + 1] = acc2[i][jj][1];
                 }
             __syncthreads();
-            const int fail = potrf_tile64_factor(dyn_smem, tid);
+            const int fail = potrf_tile64_factor(dyn_smem, tid, deferred, epoch);
             DFT(t, 6);
             if (j + 1 < T)
             {   // what chain(j+1) needs, as tagged pairs: it is polling for them already

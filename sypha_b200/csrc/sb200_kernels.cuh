@@ -119,6 +119,7 @@ struct NormalPattern
     unsigned int *chunk_ptr = nullptr;  // [n_pairs+1], in chunks
     unsigned short *term16 = nullptr;   // [8 * n_chunks]
     unsigned int n_chunks = 0;
+    int pad_id = -1;                    // the id the pad slots carry (d[pad_id] = 0)
 };
 int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
                          const int *csc_rows, const double *csc_vals, NormalPattern *out,

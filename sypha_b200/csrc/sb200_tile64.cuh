@@ -107,7 +107,15 @@ __device__ __forceinline__ double rsqrt_pivot(double x)
 //   2. the rows below become X = A W' on the tensor pipe (one 8-row block per warp) instead of a
 //      16-step substitution;
 //   3. the trailing lower triangle is updated with unrolled 8x8x16 DMMA blocks.
-__device__ int potrf_tile64_factor(unsigned char *smem, int tid)
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// `deferred_flag`: a publish the caller still owes (its data was stored and a block barrier has passed): a
+// thread of warp 1 releases it while warp 0 runs the first pivot chain, so the release fence (~1 us) is
+// hidden instead of delaying the caller's critical path.
+__device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_flag = nullptr, int deferred_value = 0)
 {
     TT(0);
     double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
@@ -131,6 +139,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid)
         const int c0 = 16 * kb;
         __syncthreads();
         TT(8 + 4 * kb);
+        if (kb == 0 && tid == 32 && deferred_flag) st_release_gpu(deferred_flag, deferred_value);
 #ifndef SB200_SKIP_DIAG
         if (warp == 0)
 #else

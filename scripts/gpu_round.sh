@@ -1,15 +1,13 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-{
-  echo "== timeline"; timeout 60 scripts/bin/df_timeline 1024 > gpurun_out/tl11.log; grep "^rep\|residual" gpurun_out/tl11.log; grep "^trsv" gpurun_out/tl11.log | cut -c1-40
-  echo "== timeline 4096"; timeout 60 scripts/bin/df_timeline 4096 | grep "^rep [23]\|residual"
-  echo "== pytest gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-  echo "== bench"; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-pcg-block 2> gpurun_out/bench_k.err | tee gpurun_out/bench_k.json
-} > gpurun_out/round16.log 2>&1
+rm -f gpurun_out/bench_ladder.jsonl
+timeout 600 python bench.py --workload synth5k --strategy cholesky --steps 3 --warmup 3 --no-pcg-block --no-cpu-baseline --no-phases --no-e2e 2>> gpurun_out/bench_ladder.err >> gpurun_out/bench_ladder.jsonl
+for tol in 1e-8 1e-6; do
+timeout 900 python bench.py --workload synth5k --strategy pcg --cg-tol $tol --steps 3 --warmup 3 --no-pcg-block --no-cpu-baseline --no-phases --no-e2e 2>> gpurun_out/bench_ladder.err >> gpurun_out/bench_ladder.jsonl
+done
 python - <<'PY'
 import json
-for l in open('gpurun_out/round16.log'):
-    if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['e2e']['value'], {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()})
-    else: print(l.rstrip())
+for l in open('gpurun_out/bench_ladder.jsonl'):
+    d=json.loads(l); print(d['config']['strategy'], round(d['value'],1), 'iter/s', round(d['time_to_lp_opt_ms'],1), 'ms/LP', round(d['iterations_per_lp'],2), 'it/LP', 'launches', d['gpu_launches'])
 PY
+timeout 300 python scripts/run_synth.py --max-iter 100 --cg-max-iter 200000 --cg-tol 1e-6 2>&1 | tail -2

@@ -1,13 +1,15 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
 {
-  echo "== pytest bnb"; timeout 900 python -m pytest tests/test_gpu_bnb.py -x -q 2>&1 | tail -4
-  for s in 8 16 32; do echo "== bnb slots $s"; timeout 600 python bench.py --workload bnb --steps 12 --slots $s 2>> gpurun_out/bench_bnb.err; done
-} > gpurun_out/round18.log 2>&1
+  echo "== timeline"; timeout 60 scripts/bin/df_timeline 1024 > gpurun_out/tl12.log; grep "^rep\|residual" gpurun_out/tl12.log; grep -A2 "^chain   [67] " gpurun_out/tl12.log
+  echo "== timeline 4096"; timeout 60 scripts/bin/df_timeline 4096 | grep "^rep [23]\|residual"
+  echo "== pytest gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+  echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pcg-block 2> gpurun_out/bench_m.err | tee gpurun_out/bench_m.json
+} > gpurun_out/round19.log 2>&1
 python - <<'PY'
 import json
-for l in open('gpurun_out/round18.log'):
+for l in open('gpurun_out/round19.log'):
     if l.startswith('{'):
-        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','nodes','lp_iterations','lp_device_ms_per_node','incumbent','root_bound')}, d['config']['slots_per_gpu'])
+        d=json.loads(l); print(d['value'], d['e2e']['value'], d['gpu_launches'], {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()})
     else: print(l.rstrip())
 PY

@@ -424,6 +424,53 @@ __device__ __forceinline__ void warp_mma_xx(const double (*Xs)[XP], int row0, in
     }
 }
 
+// Lower-triangle accumulator of a DIAGONAL tile: the 36 8x8 blocks (bi >= bj) of the 64x64 tile are dealt
+// to the 8 warps as 5 + 4 per pair of block rows (p, 7 - p) - warp 2p takes the first five of
+// [(p,0..p), (7-p,0..7-p)], warp 2p+1 the other four (its fifth slot repeats its last block and is never
+// stored).  5 DMMAs per k-step and warp instead of the 8 of the full 32x16 warp tile: the diagonal update
+// and the left-looking accumulation of the chain task are bound by the DMMA issue rate.
+struct TriMap
+{
+    int ro[5], co[5];      // first row / first column of slot s
+    int nslots;
+};
+__device__ __forceinline__ TriMap tri_map(int warp)
+{
+    TriMap m;
+    const int p = warp >> 1, h = warp & 1;
+    m.nslots = h ? 4 : 5;
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+    {
+        int q = h * 5 + s;                    // index in the pair's list of 9
+        if (q > 8) q = 8;
+        const int bi = q <= p ? p : 7 - p;
+        const int bj = q <= p ? q : q - (p + 1);
+        m.ro[s] = 8 * bi;
+        m.co[s] = 8 * bj;
+    }
+    return m;
+}
+template <int STRIDE>
+__device__ __forceinline__ void mma_tri(const double (*S)[STRIDE], int kdepth, const TriMap &m, int lane, double t2[5][2])
+{   // t2[s] -= S(rows of slot s) S(cols of slot s)'
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll 2
+    for (int kk = 0; kk < kdepth; kk += 4)
+    {
+        double a[5], b[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+        {
+            a[s] = -S[m.ro[s] + g][kk + tg];
+            b[s] = S[m.co[s] + g][kk + tg];
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+            dmma_8x8x4(t2[s][0], t2[s][1], a[s], b[s]);
+    }
+}
+
 // X = acc L_jj^-T for tile (ti, tj): block substitution with the 16x16 inverses of L_jj (each warp owns
 // 8 rows - no block barrier inside), result written to the matrix and left in Xs (stride XP).
 // Waits for D1(tj).  All threads must call; ends WITHOUT a barrier (publish() provides it).
@@ -683,8 +730,16 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
         const int j = tj, jm = tj - 1;
         const size_t c0 = (size_t)j * TB;
         int *deferred = nullptr;
-        double acc2[4][2][2];
-        load_acc(acc2, c0, c0);
+        const TriMap tm = tri_map(w);
+        double acc2[5][2];
+#pragma unroll
+        for (int sl = 0; sl < 5; ++sl)
+        {
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(
+                P.A + (c0 + tm.ro[sl] + g) * ld + c0 + tm.co[sl] + tg * 2));
+            acc2[sl][0] = v.x;
+            acc2[sl][1] = v.y;
+        }
         if (j > 0)
         {
             const size_t cm = (size_t)jm * TB;
@@ -706,7 +761,7 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
                     ldcg_tile_chunk(Bs, P.A + cm * ld + k0 + kc, ld, tid);
                     __syncthreads();
                     warp_mma<4, 2>(As, Bs, row0, col0, lane, -1.0, acc1);
-                    warp_mma<4, 2>(As, As, row0, col0, lane, -1.0, acc2);
+                    mma_tri<KP>(As, KC, tm, lane, acc2);
                 }
             }
             __syncthreads();
@@ -715,14 +770,14 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
             __syncthreads();                                    // Xs complete, X stored
             DFT(t, 4);
-            warp_mma_xx(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), row0, col0, lane, acc2);
+            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), TB, tm, lane, acc2);
             __syncthreads();
             deferred = P.tile_flag + j * T + jm;                // released inside the factorisation (warp 1)
 #elif SB200_V_PUB
             trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
             __syncthreads();                                    // Xs complete
             DFT(t, 4);
-            warp_mma_xx(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), row0, col0, lane, acc2);
+            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), TB, tm, lane, acc2);
             // tile (j, j-1) is published after the update and by a thread of warp 1: the release fence
             // then overlaps the pivot chain (warp 0) instead of delaying it; its consumers have a whole
             // tile factorisation of slack
@@ -731,7 +786,7 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
             publish(P.tile_flag + j * T + jm, epoch);           // barrier inside: Xs complete
             DFT(t, 4);
-            warp_mma_xx(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), row0, col0, lane, acc2);
+            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), TB, tm, lane, acc2);
             __syncthreads();
 #endif
             DFT(t, 5);
@@ -739,14 +794,14 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
         {   // ---- diagonal tile ----------------------------------------------------------------------
             double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LS);
             double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(dyn_smem + SM_LI);
+            // lower blocks only: what is left above the diagonal in Ls (the X tile of the previous step, or
+            // uninitialised shared memory for j = 0) is finite-or-not but never reaches a result
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
+            for (int sl = 0; sl < 5; ++sl)
+                if (sl < tm.nslots)
                 {
-                    const int r = row0 + i * 8 + g, c = col0 + jj * 8 + tg * 2;
-                    Ls[r][c] = acc2[i][jj][0];
-                    Ls[r][c + 1] = acc2[i][jj][1];
+                    Ls[tm.ro[sl] + g][tm.co[sl] + tg * 2] = acc2[sl][0];
+                    Ls[tm.ro[sl] + g][tm.co[sl] + tg * 2 + 1] = acc2[sl][1];
                 }
             __syncthreads();
             const int fail = potrf_tile64_factor(dyn_smem, tid, deferred, epoch);

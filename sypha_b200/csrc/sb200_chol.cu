@@ -719,7 +719,13 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             }
             __syncthreads();
             DFT(t, 1);
-            trsm_tile<false>(dyn_smem, P, C, epoch, ti, tj, acc);
+            // tile (j+2, j) feeds the chain task two columns on (its last accumulation step waits for it): it takes
+            // the tagged hand-off of the diagonal tile like the chain does; the tiles further down have slack and
+            // use the flag + plain loads (fewer pollers on the tagged payload)
+            if (ti == tj + 2)
+                trsm_tile<true>(dyn_smem, P, C, epoch, ti, tj, acc);
+            else
+                trsm_tile<false>(dyn_smem, P, C, epoch, ti, tj, acc);
             publish(P.tile_flag + ti * T + tj, epoch);
             DFT(t, 3);
             continue;
@@ -746,22 +752,30 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             double acc1[4][2][2];
             load_acc(acc1, c0, cm);
             for (int k = 0; k < jm; ++k)
-            {
-                if (tid == 0)
-                {
-                    spin_until(P.tile_flag + j * T + k, epoch, C.err);
-                    spin_until(P.tile_flag + jm * T + k, epoch, C.err);
-                }
+            {   // the diagonal tile needs only row j of column k; the sub-diagonal tile also row j-1, which for
+                // the last k is the tile the previous chain task has just published: it is waited for last, after
+                // the diagonal tile's share of this step is done
                 const size_t k0 = (size_t)k * TB;
+                if (tid == 0) spin_until(P.tile_flag + j * T + k, epoch, C.err);
 #pragma unroll
                 for (int kc = 0; kc < TB; kc += KC)
                 {
                     __syncthreads();
-                    ldcg_tile_chunk(As, P.A + c0 * ld + k0 + kc, ld, tid);
-                    ldcg_tile_chunk(Bs, P.A + cm * ld + k0 + kc, ld, tid);
+                    ldcg_tile_chunk(kc ? Bs : As, P.A + c0 * ld + k0 + kc, ld, tid);   // row j: both halves staged
+                }
+                __syncthreads();
+                mma_tri<KP>(As, KC, tm, lane, acc2);
+                mma_tri<KP>(Bs, KC, tm, lane, acc2);
+                if (tid == 0) spin_until(P.tile_flag + jm * T + k, epoch, C.err);
+                // acc1 -= L_jk L_(j-1)k' : the halves of L_jk are in As / Bs; stream L_(j-1)k through the scratch tile
+                double(*Cs)[KP] = reinterpret_cast<double(*)[KP]>(dyn_smem + SM_LI);
+#pragma unroll
+                for (int kc = 0; kc < TB; kc += KC)
+                {
                     __syncthreads();
-                    warp_mma<4, 2>(As, Bs, row0, col0, lane, -1.0, acc1);
-                    mma_tri<KP>(As, KC, tm, lane, acc2);
+                    ldcg_tile_chunk(Cs, P.A + cm * ld + k0 + kc, ld, tid);
+                    __syncthreads();
+                    warp_mma<4, 2>(kc ? Bs : As, Cs, row0, col0, lane, -1.0, acc1);
                 }
             }
             __syncthreads();

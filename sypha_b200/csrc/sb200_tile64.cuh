@@ -95,7 +95,8 @@ __device__ __forceinline__ double rsqrt_pivot(double x)
 #endif
 
 // Factor: returns 0 or the 1-based local index of the first non-positive pivot (same value in all
-// threads).  On exit Ls = L (upper zeroed) and the four 16x16 diagonal blocks of Li hold the inverses
+// threads).  On exit Ls = L (zero above the diagonal inside the 16x16 diagonal blocks, unspecified in the
+// strictly-upper 16x16 blocks) and the four 16x16 diagonal blocks of Li hold the inverses
 // of the diagonal blocks of L (the strictly-upper 16x16 blocks of Li are cleared).
 //
 // Per 16-column panel:
@@ -124,6 +125,10 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
     int *sflag = reinterpret_cast<int *>(smem + SM_FLAG);
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
     if (tid == 0) *sflag = 0;
+#ifdef SB200_SKIP_FACTOR
+    __syncthreads();
+    return 0;
+#endif
     // clear the strictly-upper 16x16 blocks of Li: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
     for (int idx = tid; idx < 6 * 256; idx += NT_TILE)
     {
@@ -220,11 +225,8 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
             Ls[R + g][c0 + 8 + 2 * tg] = x10;
             Ls[R + g][c0 + 8 + 2 * tg + 1] = x11;
         }
-        else if (kb < 3 && warp == 7)
-        {   // meanwhile: zero the part of the block row right of the diagonal block
-            for (int idx = lane; idx < 16 * (48 - c0); idx += 32)
-                Ls[c0 + idx / (48 - c0)][c0 + 16 + idx % (48 - c0)] = 0.0;
-        }
+        // (the part of Ls right of the diagonal blocks is never read: it used to be zeroed here by one warp with
+        //  a runtime division per element - 1.5 us per tile on the critical path, found by skipping phases)
         __syncthreads();
         TT(10 + 4 * kb);
 #ifdef SB200_SKIP_TRAIL

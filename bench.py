@@ -207,7 +207,12 @@ def run_bnb(args, rank, world, local_rank):
         exch_bytes[0] += 16 + 8 * n0
         return best, (None if bx is None else bx.cpu().numpy())
 
-    drv = bnb.BatchedBnb(mdl, slots=args.slots, device=local_rank, exchange=exchange)
+    def rebalance(nodes):
+        return bnb_exchange.rebalance_frontier(nodes, max_depth=64, min_imbalance=args.slots // 2)
+
+    drv = bnb.BatchedBnb(mdl, slots=args.slots, device=local_rank, exchange=exchange,
+                         device_heuristics=not args.host_heuristics,
+                         rebalance=rebalance if (dist is not None and not args.no_donation) else None, rebalance_every=4)
     # every rank expands the same first levels (deterministic), then keeps its round-robin share
     while len(drv.frontier) < world * args.slots and drv.frontier:
         drv.round()
@@ -248,19 +253,26 @@ def run_bnb(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "branch-and-bound on an scpnre-shaped synthetic SCP 500x5000, 10% density "
                                    "(configs[4]); a step = one round of K batched node LPs per GPU",
-                       "slots_per_gpu": args.slots, "node_lp": "Mehrotra IPM to mu <= 1e-4, max_iter 100",
+                       "slots_per_gpu": args.slots,
+                       "node_heuristics": "host NumPy" if args.host_heuristics else "device kernel (sb200_node_heuristics)", "node_lp": "Mehrotra IPM to mu <= 1e-4, max_iter 100",
                        "frontier": "FIFO, most-fractional branching, round-robin split across ranks",
-                       "collective": "all_reduce(MIN) of the incumbent objective + broadcast of the incumbent vector per round"},
+                       "collective": "all_reduce(MIN) of the incumbent objective + broadcast of the incumbent vector per round; "
+                                     "every 4 rounds an all_gather of the frontier sizes and, when they differ by more than "
+                                     "half a window, node donation (decision lists, 536 B per node)"},
             "timing": "wall clock between device synchronisations around the K rounds, max over ranks "
                       "(host node construction, upload, LP solves, heuristics, incumbent exchange)",
             "nodes": int(nodes), "lp_iterations": int(iters), "lp_device_ms_per_node": dev_ms / max(nodes, 1),
             "incumbent": drv.stats.incumbent, "root_bound": drv.stats.root_bound,
             "incumbent_exchange_bytes_per_round": (16 + 8 * n0) if dist else 0,
+            "node_donation": {"every_rounds": 4, "sent_by_rank0": drv.stats.nodes_sent, "received_by_rank0": drv.stats.nodes_received}
+            if drv.rebalance is not None else None,
             "e2e": {"value": nodes / elapsed, "unit": "nodes/s",
                     "h2d_bytes_per_step": int(20 * drv.stats.delta_rows / max(args.steps, 1)),
-                    "d2h_bytes_per_step": int(args.slots * 8 * (2 * mdl.n + mdl.m)),
+                    "d2h_bytes_per_step": int(args.slots * (8 * (2 * mdl.n + mdl.m) if args.host_heuristics else 40 + 96)),
                     "note": "the base model is resident; every round sends the K decision lists (20 B per branch row) "
-                            "and reads x, y, s of every node back inside the timed region: value IS end to end"},
+                            "and reads back, per node, the LP result scalars and the 40-byte branching / incumbent "
+                            "record of sb200_node_heuristics (x, y, s of every node with --host-heuristics) inside "
+                            "the timed region: value IS end to end"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
@@ -552,6 +564,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="scpnrh", choices=sorted(WORKLOADS) + ["bnb"])
     ap.add_argument("--slots", type=int, default=16, help="bnb: concurrent node LPs per GPU")
+    ap.add_argument("--host-heuristics", action="store_true",
+                    help="bnb: branching rule and rounding/repair heuristic on the host (NumPy) instead of the device kernel")
+    ap.add_argument("--no-donation", action="store_true", help="bnb, N > 1: keep the initial round-robin split (no node donation)")
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--poll-every", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")

@@ -14,6 +14,10 @@
  *                                + host KKT assembly src/sypha_solver.cpp:96-207 (disappears)
  *   sb200_solve_batch .......... the B&B node body                    src/sypha_solver_bnb_driver.cpp:789-859
  *                                + build_branch_model                 src/sypha_solver_bnb.cpp:418-490
+ *   sb200_node_heuristics ...... MostFractionalSelector, NearestIntegerFixingHeuristic and the cover repair
+ *                                of DualGuidedCoverRepairHeuristic (plain versions), run per node by
+ *                                src/sypha_solver_bnb_driver.cpp:861-1005 on a host copy of the LP point
+ *                                src/sypha_solver_heuristics.cpp:10-30,53-110,112-292
  *   sb200_k_* .................. the L0 free functions (device pointers + stream):
  *     sb200_k_elem_min_mult .... elem_min_mult_dev                    src/sypha_solver_utils.h:7
  *     sb200_k_corrector_rhs .... corrector_rhs_dev                    src/sypha_solver_utils.h:12
@@ -152,12 +156,34 @@ int sb200_set_node_delta(sb200_ws *ws, const sb200_node_delta *delta);
 int sb200_solve_batch(sb200_ws **ws, int k, const sb200_node_delta *deltas,
                       const sb200_params *params, sb200_result *results);
 
+/* The combinatorial step that follows a node's LP in the B&B loop, on the device (one single-CTA kernel per
+ * node on the node's stream, reading the LP point where the solve left it): most-fractional branching variable
+ * (src/sypha_solver_heuristics.cpp:10-30), nearest-integer rounding with greedy cover repair and removal of
+ * redundant columns for an incumbent (:53-110, :112-292, plain versions; columns the node's decisions fix to 0
+ * are never chosen), and c.rint(x) for an integral LP point.  Only the first n_orig columns and the base rows
+ * take part. */
+typedef struct sb200_heur_result {
+    int feasible;               /* 0: no cover exists under the node's zero-fixings */
+    int n_chosen;               /* columns in the cover */
+    int branch_var;             /* most fractional original column, first index on ties (-1: none) */
+    int repair_steps;           /* greedy picks that were needed */
+    double cover_obj;           /* cost of the cover (DBL_MAX when infeasible) */
+    double branch_frac;         /* |x - rint(x)| at branch_var */
+    double rounded_obj;         /* c . rint(x) over the original columns */
+} sb200_heur_result;
+/* runs the kernel for each of the k workspaces (their last solve must have finished) concurrently, then waits */
+int sb200_node_heuristics(sb200_ws **ws, int k, sb200_heur_result *out);
+/* the cover of the last sb200_node_heuristics on this workspace: n_orig bytes of 0/1 */
+int sb200_get_cover(sb200_ws *ws, unsigned char *x_host);
+
 /* per-iteration trace of the last solve: rows of SB200_TRACE_COLS doubles
  * (mu_in, mu, mu_aff, sigma, alpha_p, alpha_d, primal, dual); returns rows written */
 #define SB200_TRACE_COLS 8
 int sb200_get_trace(sb200_ws *ws, double *out, int max_rows);
 /* device addresses of the resident iterates (length n, m, n) */
 int sb200_get_device_iterates(sb200_ws *ws, void **x, void **y, void **s);
+/* host copies of the resident iterates (any pointer may be NULL) */
+int sb200_get_iterates(sb200_ws *ws, double *x_host, double *y_host, double *s_host);
 /* introspection used by bench.py for the roofline arithmetic */
 int sb200_model_info(sb200_ws *ws, long long *info, int n_info);
 void *sb200_stream(sb200_ws *ws);

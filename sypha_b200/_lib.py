@@ -49,6 +49,11 @@ class sb200_node_delta(C.Structure):
                 ("rhs", C.POINTER(C.c_double))]
 
 
+class sb200_heur_result(C.Structure):
+    _fields_ = [("feasible", C.c_int), ("n_chosen", C.c_int), ("branch_var", C.c_int), ("repair_steps", C.c_int),
+                ("cover_obj", C.c_double), ("branch_frac", C.c_double), ("rounded_obj", C.c_double)]
+
+
 # every symbol include/sypha_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 SYMBOLS = {
@@ -63,8 +68,11 @@ SYMBOLS = {
     "sb200_set_node_delta": (_i, [_vp, C.POINTER(sb200_node_delta)]),
     "sb200_solve_batch": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_node_delta), C.POINTER(sb200_params),
                                C.POINTER(sb200_result)]),
+    "sb200_node_heuristics": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_heur_result)]),
+    "sb200_get_cover": (_i, [_vp, _vp]),
     "sb200_get_trace": (_i, [_vp, _vp, _i]),
     "sb200_get_device_iterates": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sb200_get_iterates": (_i, [_vp, _vp, _vp, _vp]),
     "sb200_model_info": (_i, [_vp, C.POINTER(_ll), _i]),
     "sb200_stream": (_vp, [_vp]),
     "sb200_time_phase": (_i, [_vp, _i, _i, C.POINTER(_d)]),

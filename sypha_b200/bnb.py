@@ -23,8 +23,8 @@ import numpy as np
 
 from .instances import ScpModel
 from .solver import (CODE_SUCCESSFUL, IpmWorkspace, SolverExecutionConfig, SolverGapStagnationConfig,
-                     SyphaEnvironment, SyphaNodeSparse, initializeIpmWorkspace, releaseIpmWorkspace, solve_batch,
-                     solve_batch_nodes, workspace_for_nodes)
+                     SyphaEnvironment, SyphaNodeSparse, get_cover, get_primal, initializeIpmWorkspace, node_heuristics,
+                     releaseIpmWorkspace, solve_batch, solve_batch_nodes, workspace_for_nodes)
 
 TERM_CONVERGED, TERM_MAX_ITER, TERM_GAP_STALLED, TERM_NUMERICAL = 0, 1, 2, 3
 
@@ -51,7 +51,9 @@ def build_branch_model(base: ScpModel, decisions: Sequence[Tuple[int, int]]) -> 
 class CoverHeuristic:
     """Nearest-integer rounding of the LP point, greedy repair of uncovered rows by cost per newly covered
     row (gains kept up to date incrementally: O(nnz) per call), then removal of redundant columns (most
-    expensive first).  Host-side NumPy on the CSR / CSC lists of A0."""
+    expensive first).  Host-side NumPy on the CSR / CSC lists of A0.  The product path runs the same rules on
+    the device (``sb200_node_heuristics``, csrc/sb200_heur.cu); this class is what the tests check that kernel
+    against, and what ``device_heuristics=False`` (the reference's host-side arrangement) uses."""
 
     def __init__(self, base: ScpModel):
         import scipy.sparse as sp
@@ -122,6 +124,8 @@ class BnbStats:
     wall_s: float = 0.0
     open_nodes: int = 0
     root_bound: float = -math.inf
+    nodes_sent: int = 0
+    nodes_received: int = 0
 
 
 class BatchedBnb:
@@ -129,10 +133,13 @@ class BatchedBnb:
 
     def __init__(self, base: ScpModel, slots: int = 8, device: int = 0, max_iter: int = 100,
                  exchange=None, integer_costs: bool = True, device_nodes: bool = True, max_depth: int = 64,
-                 heuristic_threads: int = 0):
+                 heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
+        # branching variable + rounding/repair incumbent per node on the device, behind the node's LP on its own
+        # stream (sb200_node_heuristics); False: the host-side NumPy versions on a host copy of x
+        self.device_heuristics = device_heuristics and device_nodes
         self.env = SyphaEnvironment(cudaDeviceId=device)
         # The reference runs node LPs with a gap-stagnation early exit (bnb_driver.cpp:835-837) and prunes with
         # whatever dual objective the LP stopped at - not a bound before convergence (53.08 vs the
@@ -155,6 +162,11 @@ class BatchedBnb:
         self.incumbent_x: Optional[np.ndarray] = None
         self.integer_costs = integer_costs
         self.exchange = exchange            # callable(obj, x) -> (obj, x) across ranks, or None
+        # node donation between ranks (bnb_exchange.rebalance_frontier): callable(list of (decisions, bound)) ->
+        # (list, open nodes over all ranks, sent, received); every rank calls it in the same rounds
+        self.rebalance = rebalance
+        self.rebalance_every = max(1, rebalance_every)
+        self.global_open: Optional[int] = None
         self.stats = BnbStats()
         # optional: incumbent heuristics of round r on host threads WHILE the GPU solves round r+1 (the ctypes
         # call releases the GIL); results are folded in at a fixed point (after that solve), so the search stays
@@ -200,7 +212,10 @@ class BatchedBnb:
             batch.append(nd)
         if batch:
             if self.device_nodes and all(len(nd.decisions) <= self.max_depth for nd in batch):
-                results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self.ws)
+                on_dev = self.device_heuristics
+                results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self.ws,
+                                            fetch_solutions=not on_dev)
+                heur = node_heuristics(self.ws[:len(batch)]) if on_dev else None
                 self.stats.delta_rows += sum(len(nd.decisions) for nd in batch)
             else:
                 nodes = []
@@ -209,9 +224,10 @@ class BatchedBnb:
                     nodes.append(SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals,
                                                           mdl.c, mdl.b, self.env))
                 results = solve_batch(nodes, self.cfg, self.ws[:len(nodes)])
-                self.device_nodes = False      # the slots no longer hold the base model
+                heur = None
+                self.device_nodes = self.device_heuristics = False      # the slots no longer hold the base model
             self._fold_pending()               # heuristics of the previous round (ran beside this solve)
-            for nd, res in zip(batch, results):
+            for slot, (nd, res) in enumerate(zip(batch, results)):
                 self.stats.processed += 1
                 self.stats.lp_iterations += res.iterations
                 self.stats.lp_device_ms += res.msStart + res.msSetup + res.msLoop
@@ -223,10 +239,25 @@ class BatchedBnb:
                 bound = max(nd.parent_bound, min(res.dualObj, res.primalObj))
                 if not nd.decisions:
                     self.stats.root_bound = bound
-                x = res.primalSolution[:self.base.n_orig]
                 if self._prunable(bound):
                     self.stats.pruned_by_bound += 1
                     continue
+                if heur is not None:                           # same rules, computed on the device
+                    h = heur[slot]
+                    self.stats.kernels_launched += 1
+                    if h.feasible and h.coverObj < self.incumbent:
+                        self._offer(h.coverObj, get_cover(self.ws[slot], self.base.n_orig))
+                    if h.branchVar < 0 or h.branchFrac < 1e-6:     # integral LP point
+                        self.stats.integral += 1
+                        if h.roundedObj < self.incumbent:
+                            self._offer(h.roundedObj, np.round(get_primal(self.ws[slot], self.base.n + len(nd.decisions))
+                                                               [:self.base.n_orig]))
+                        continue
+                    j = h.branchVar
+                    self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
+                    self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+                    continue
+                x = res.primalSolution[:self.base.n_orig]
                 zero_fixed = [v for v, f in nd.decisions if f == 0]
                 if self._pool is not None:
                     self._pending.append(self._pool.submit(self.heur, x.copy(), zero_fixed))
@@ -244,13 +275,27 @@ class BatchedBnb:
             self._fold_pending()
         if self.exchange is not None:                          # every rank calls it once per round
             self.incumbent, self.incumbent_x = self.exchange(self.incumbent, self.incumbent_x)
+        if self.rebalance is not None and self.stats.rounds % self.rebalance_every == 0:
+            nodes, self.global_open, sent, recv = self.rebalance([(nd.decisions, nd.parent_bound) for nd in self.frontier])
+            if sent or recv:
+                self.frontier = collections.deque(BnbNode(d, b) for d, b in nodes)
+            self.stats.nodes_sent += sent
+            self.stats.nodes_received += recv
         self.stats.rounds += 1
         return len(batch)
 
     def run(self, max_nodes: int, rounds: Optional[int] = None) -> BnbStats:
         t0 = time.perf_counter()
         r = 0
-        while (rounds is None and self.frontier and self.stats.processed < max_nodes) or (rounds is not None and r < rounds):
+        # with several ranks the stop test must be the same on every rank (the collectives of a round are
+        # matched): open nodes over ALL ranks, as of the last rebalance
+        def more():
+            if rounds is not None:
+                return r < rounds
+            if self.rebalance is not None and self.rebalance_every == 1 and self.global_open is not None:
+                return self.global_open > 0
+            return bool(self.frontier) and self.stats.processed < max_nodes
+        while more():
             self.round()
             r += 1
             if not self.frontier and self._pending:            # last word of the heuristics before stopping

@@ -63,3 +63,86 @@ def reduce_counters(elapsed_s: float, counts: Sequence[float], group=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
     return float(t.item()), [float(v) for v in c.tolist()]
+
+
+def plan_transfers(sizes: Sequence[int]):
+    """Deterministic balancing plan from the frontier sizes of all ranks: returns (targets, moves) with
+    ``moves`` a list of (src, dst, count).  Targets differ by at most one node; ranks are matched in rank
+    order, so every rank derives the same plan from the same ``all_gather``."""
+    world = len(sizes)
+    total = int(sum(sizes))
+    targets = [total // world + (1 if r < total % world else 0) for r in range(world)]
+    surplus = [[r, int(sizes[r]) - targets[r]] for r in range(world) if sizes[r] > targets[r]]
+    deficit = [[r, targets[r] - int(sizes[r])] for r in range(world) if sizes[r] < targets[r]]
+    moves = []
+    i = j = 0
+    while i < len(surplus) and j < len(deficit):
+        k = min(surplus[i][1], deficit[j][1])
+        moves.append((surplus[i][0], deficit[j][0], k))
+        surplus[i][1] -= k
+        deficit[j][1] -= k
+        if surplus[i][1] == 0:
+            i += 1
+        if deficit[j][1] == 0:
+            j += 1
+    return targets, moves
+
+
+def rebalance_frontier(nodes: list, max_depth: int, min_imbalance: int = 1, group=None):
+    """Node donation between ranks (frontier sizes gathered, nodes moved from the long
+    frontiers to the short ones).  A node is just its decision list and its parent bound
+    (/root/reference/src/sypha_solver_heuristics.h:9-30), so it travels as ``max_depth + 2`` 8-byte words:
+    [n_decisions, bits of the bound, var * 2 + fix ...].
+
+    ``nodes``: this rank's open nodes as (decisions, bound) pairs in processing order; donated nodes are
+    taken from the END (processed last) and appended at the end of the receiver's list.  Nodes deeper than
+    ``max_depth`` stay where they are.  All ranks must call this in the same round.  Returns
+    (new_nodes, global_open_count, n_sent, n_received)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = _dev(group)
+    mine = torch.tensor([len(nodes)], dtype=torch.int64, device=dev)
+    sizes_t = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes_t, mine, group=group)
+    sizes = [int(t.item()) for t in sizes_t]
+    total = sum(sizes)
+    if world == 1 or max(sizes) - min(sizes) <= min_imbalance:
+        return nodes, total, 0, 0
+    _, moves = plan_transfers(sizes)
+    cap = max(sum(k for s, _, k in moves if s == r) for r in range(world))     # rows every rank contributes
+    width = max_depth + 3
+    out = torch.zeros((cap, width), dtype=torch.int64)
+    out[:, 0] = -1                                                              # destination; -1 = empty row
+    keep = list(nodes)
+    sent = 0
+    for src, dst, k in moves:
+        if src != rank:
+            continue
+        for _ in range(k):
+            # last donatable node (depth <= max_depth)
+            idx = next((i for i in range(len(keep) - 1, -1, -1) if len(keep[i][0]) <= max_depth), None)
+            if idx is None:
+                break
+            dec, bound = keep.pop(idx)
+            row = out[sent]
+            row[0] = dst
+            row[1] = len(dec)
+            row[2] = torch.tensor([bound], dtype=torch.float64).view(torch.int64)[0]
+            if dec:
+                row[3:3 + len(dec)] = torch.tensor([2 * int(v) + int(f) for v, f in dec], dtype=torch.int64)
+            sent += 1
+    out = out.to(dev)
+    gathered = [torch.zeros_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out, group=group)
+    received = 0
+    for r in range(world):
+        if r == rank:
+            continue
+        rows = gathered[r].cpu()
+        for row in rows[rows[:, 0] == rank]:
+            d = int(row[1])
+            bound = float(row[2:3].view(torch.float64)[0])
+            dec = tuple((int(w) // 2, int(w) % 2) for w in row[3:3 + d].tolist())
+            keep.append((dec, bound))
+            received += 1
+    return keep, total, sent, received

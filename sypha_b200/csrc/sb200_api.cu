@@ -12,6 +12,7 @@
 #include "sb200_kernels.cuh"
 #include "sb200_chol.cuh"
 #include "sb200_pcg.cuh"
+#include "sb200_heur.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -76,6 +77,11 @@ struct sb200_ws
     unsigned char *h_delta = nullptr;      // pinned staging: var | coef | rhs
     int delta_cap = 0;
     std::map<int, std::pair<cudaGraphExec_t, long long>> node_graphs;   // iteration graph per depth
+    // per-node branching / incumbent kernel (sb200_heur.cu)
+    int *heur_list = nullptr, *heur_sorted = nullptr;
+    unsigned char *heur_cover = nullptr;
+    sb200_heur_result *heur_out = nullptr, *heur_out_host = nullptr;   // device, pinned
+    int heur_cap = 0;
 
     // graph of one IPM iteration (direct strategies)
     cudaGraphExec_t iter_graph = nullptr;
@@ -777,8 +783,9 @@ int sb200_ws_destroy(sb200_ws *ws)
     chol_work_free(ws->chol);
     void *ptrs[] = {ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
                     ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams, ws->base_colptr, ws->base_rows,
-                    ws->base_cvals, ws->d_var, ws->d_coef};
+                    ws->base_cvals, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out};
     if (ws->h_delta) cudaFreeHost(ws->h_delta);
+    if (ws->heur_out_host) cudaFreeHost(ws->heur_out_host);
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ws->sc_host) cudaFreeHost(ws->sc_host);
@@ -964,6 +971,59 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     return SB200_OK;
 }
 
+int sb200_node_heuristics(sb200_ws **wss, int k, sb200_heur_result *out)
+{
+    if (!wss || k <= 0 || !out) return SB200_ERR_INVALID;
+    for (int i = 0; i < k; ++i)
+    {
+        sb200_ws *ws = wss[i];
+        if (!ws || !ws->loaded) return SB200_ERR_INVALID;
+        if (ws->active) return fail(ws, SB200_ERR_INVALID, "sb200_node_heuristics: a solve is still in flight");
+        if (!ws->csr_offs || !ws->csc_colptr || ws->n_orig <= 0)
+            return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_node_heuristics: the model keeps no CSR/CSC lists");
+        WS_TRY(cudaSetDevice(ws->device));
+        const int n0 = ws->n_orig;
+        if (n0 > ws->heur_cap)
+        {
+            int rc;
+            if ((rc = grow(ws, &ws->heur_list, (size_t)n0))) return rc;
+            if ((rc = grow(ws, &ws->heur_sorted, (size_t)n0))) return rc;
+            if ((rc = grow(ws, &ws->heur_cover, (size_t)n0))) return rc;
+            if (!ws->heur_out)
+            {
+                if ((rc = grow(ws, &ws->heur_out, 1))) return rc;
+                WS_TRY(cudaMallocHost(&ws->heur_out_host, sizeof(sb200_heur_result)));
+            }
+            ws->heur_cap = n0;
+        }
+        HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
+                   ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out};
+        const int rc = launch_node_heuristics(a, ws->stream);
+        if (rc == SB200_ERR_UNSUPPORTED)
+            return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
+        if (rc) return fail(ws, rc, "sb200_node_heuristics: launch configuration failed");
+        WS_TRY(cudaGetLastError());
+        WS_TRY(cudaMemcpyAsync(ws->heur_out_host, ws->heur_out, sizeof(sb200_heur_result), cudaMemcpyDeviceToHost,
+                               ws->stream));
+    }
+    for (int i = 0; i < k; ++i)
+    {
+        sb200_ws *ws = wss[i];
+        WS_TRY(cudaStreamSynchronize(ws->stream));
+        out[i] = *ws->heur_out_host;
+    }
+    return SB200_OK;
+}
+
+int sb200_get_cover(sb200_ws *ws, unsigned char *x_host)
+{
+    if (!ws || !ws->loaded || !x_host || !ws->heur_cover) return SB200_ERR_INVALID;
+    WS_TRY(cudaSetDevice(ws->device));
+    WS_TRY(cudaMemcpyAsync(x_host, ws->heur_cover, (size_t)ws->n_orig, cudaMemcpyDeviceToHost, ws->stream));
+    WS_TRY(cudaStreamSynchronize(ws->stream));
+    return SB200_OK;
+}
+
 int sb200_get_trace(sb200_ws *ws, double *out, int max_rows)
 {
     if (!ws || !out) return 0;
@@ -978,6 +1038,17 @@ int sb200_get_device_iterates(sb200_ws *ws, void **x, void **y, void **s)
     if (x) *x = ws->V.x;
     if (y) *y = ws->V.y;
     if (s) *s = ws->V.s;
+    return SB200_OK;
+}
+
+int sb200_get_iterates(sb200_ws *ws, double *x_host, double *y_host, double *s_host)
+{
+    if (!ws || !ws->loaded) return SB200_ERR_INVALID;
+    WS_TRY(cudaSetDevice(ws->device));
+    if (x_host) WS_TRY(cudaMemcpyAsync(x_host, ws->V.x, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, ws->stream));
+    if (y_host) WS_TRY(cudaMemcpyAsync(y_host, ws->V.y, sizeof(double) * ws->m, cudaMemcpyDeviceToHost, ws->stream));
+    if (s_host) WS_TRY(cudaMemcpyAsync(s_host, ws->V.s, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, ws->stream));
+    WS_TRY(cudaStreamSynchronize(ws->stream));
     return SB200_OK;
 }
 

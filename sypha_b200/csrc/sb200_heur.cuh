@@ -1,0 +1,25 @@
+// sb200_heur.cuh - launcher of the per-node branching / incumbent kernel (sb200_heur.cu).
+#pragma once
+#include "sb200_common.cuh"
+
+namespace sb200 {
+
+struct HeurArgs
+{
+    int m0, n0;                       // base rows, original (non-slack) columns
+    const int *row_ptr, *row_cols;    // CSR of the node model (rows >= m0 and columns >= n0 are skipped)
+    const int *col_ptr, *col_rows;    // CSC of the node model
+    const double *c;
+    const double *x_lp;               // the LP point, where the solver left it
+    int k;                            // the node's decisions (coef < 0: variable fixed to 0)
+    const int *var;
+    const double *coef;
+    int *list, *sorted;               // scratch, n0 ints each
+    unsigned char *cover_x;           // out: the cover, n0 bytes
+    sb200_heur_result *out;           // out (device)
+};
+
+size_t heur_smem_bytes(int m0, int n0);
+int launch_node_heuristics(const HeurArgs &a, cudaStream_t st);
+
+} // namespace sb200

@@ -113,6 +113,263 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifndef SB200_V_LOOKAHEAD
+#define SB200_V_LOOKAHEAD 1  // the pivot-chain warp also applies a finished 16-column panel to the NEXT 16x16 diagonal
+                             // block (all its next chain needs); the other seven warps apply it to the rest of the
+                             // tile one step later, beside that chain
+#endif
+
+__device__ __forceinline__ void named_bar_sync(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// The 16x16 diagonal block at c0 of Ls factored by ONE warp (see potrf_tile64_factor below): lanes 0..15 hold
+// the rows, lanes 16..31 the columns of the identity (-> W = L_dd^-1 in Li).  Returns the 1-based tile-local
+// index of the first non-positive pivot, or 0.
+__device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)[LP], double *Tb, int c0, int lane)
+{
+    const int r = lane & 15;
+    const bool inv_lane = lane >= 16;
+    double(*Cb)[17] = reinterpret_cast<double(*)[17]>(Tb);
+    double a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        a[j] = inv_lane ? (j == r ? 1.0 : 0.0) : Ls[c0 + r][c0 + j];
+    double dg = a[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j)
+        dg = (r == j) ? a[j] : dg;
+    int bad = 0;
+    double d = __shfl_sync(0xffffffffu, dg, 0);
+    double inv = SB200_RSQ(d);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+    {
+        if (!(d > 0.0) && bad == 0) bad = c0 + c + 1;
+        const double l = (!inv_lane && r == c) ? d * inv : a[c] * inv;
+        a[c] = l;
+        dg -= l * l;
+        if (!inv_lane) Cb[c][r] = l;
+        if (c < 15)
+        {
+            d = __shfl_sync(0xffffffffu, dg, c + 1);
+            inv = SB200_RSQ(d);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c2 = c + 1; c2 < 16; ++c2)
+            a[c2] -= l * Cb[c][c2];
+    }
+    if (!inv_lane)
+    {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            Ls[c0 + r][c0 + j] = (j <= r) ? a[j] : 0.0;
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            Li[c0 + j][c0 + r] = a[j];
+    }
+    return bad;
+}
+
+#if SB200_V_LOOKAHEAD
+// Look-ahead form of the tile factorisation.  With 16x16 blocks A[i][j] (i >= j) of the tile and panel k =
+// block column k, the dependent chain is
+//     P(k): chol(A[k][k]) -> N(k): L[k+1][k] = A[k+1][k] W_k', A[k+1][k+1] -= L[k+1][k] L[k+1][k]' -> P(k+1)
+// and everything else panel k has to do - R(k): L[i][k] = A[i][k] W_k' for i >= k+2, T(k): A[i][j] -= L[i][k]
+// L[j][k]' for i >= j >= k+1 except (k+1, k+1) - is only needed by N(k+1).  Warp 0 runs P and N back to back;
+// warps 1..7 run R(k-1) and T(k-1) during P(k) (step k), so a panel costs one pivot chain plus two 16x16x16
+// products instead of a chain, a rows-below phase and a trailing phase separated by block barriers.  Every
+// element still receives its panel updates in panel order with the same DMMA sequences as the phased form.
+//   barriers per step: named 1 (warps 1..7, between R and T), named 2 (warps 1..7 arrive after T, warp 0 waits
+//   before N), block barrier at the end of the step (W_k, L[k+1][k] visible to warps 1..7).
+__device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_flag = nullptr, int deferred_value = 0)
+{
+    TT(0);
+    double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
+    double(*Li)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LI);
+    double *Tb = reinterpret_cast<double *>(smem + SM_T);
+    int *sflag = reinterpret_cast<int *>(smem + SM_FLAG);
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    if (tid == 0) *sflag = 0;
+#ifdef SB200_SKIP_FACTOR
+    __syncthreads();
+    return 0;
+#endif
+    for (int idx = tid; idx < 6 * 256; idx += NT_TILE)
+    {   // clear the strictly-upper 16x16 blocks of Li: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+        const int blk = idx >> 8, e = idx & 255;
+        const int bi = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
+        const int bj = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
+        Li[16 * bi + (e >> 4)][16 * bj + (e & 15)] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 32 && deferred_flag) st_release_gpu(deferred_flag, deferred_value);
+
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k)
+    {
+        const int c0 = 16 * k;
+        TT(8 + 4 * k);
+        if (warp == 0)
+        {
+            // ---- P(k) ------------------------------------------------------------------------------------
+            const int bad = potrf_block16_warp(Ls, Li, Tb, c0, lane);
+            if (lane == 0 && bad) atomicCAS(sflag, 0, bad);
+            __syncwarp();
+            if (k < 3)
+            {
+                named_bar_sync(2, NT_TILE);                 // T(k-1) done: A[k+1][k] and A[k+1][k+1] are current
+                // ---- N(k): X = A[k+1][k] W_k' (W lower triangular: output columns 0..7 need k < 8 only) ----
+                const int R = c0 + 16;
+                double af[2][4];
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        af[rb][kk] = Ls[R + 8 * rb + g][c0 + 4 * kk + tg];
+                double x[2][2][2] = {};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                {
+                    const double w1 = Li[c0 + 8 + g][c0 + 4 * kk + tg];
+                    if (kk < 2)
+                    {
+                        const double w0 = Li[c0 + g][c0 + 4 * kk + tg];
+                        dmma_8x8x4(x[0][0][0], x[0][0][1], af[0][kk], w0);
+                        dmma_8x8x4(x[1][0][0], x[1][0][1], af[1][kk], w0);
+                    }
+                    dmma_8x8x4(x[0][1][0], x[0][1][1], af[0][kk], w1);
+                    dmma_8x8x4(x[1][1][0], x[1][1][1], af[1][kk], w1);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+                    for (int cb = 0; cb < 2; ++cb)
+                    {
+                        Ls[R + 8 * rb + g][c0 + 8 * cb + 2 * tg] = x[rb][cb][0];
+                        Ls[R + 8 * rb + g][c0 + 8 * cb + 2 * tg + 1] = x[rb][cb][1];
+                    }
+                __syncwarp();
+                // A[k+1][k+1] -= X X' (lower 8x8 blocks (0,0), (1,0), (1,1))
+                double xa[2][4], xb[2][4];
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                    {
+                        xb[rb][kk] = Ls[R + 8 * rb + g][c0 + 4 * kk + tg];
+                        xa[rb][kk] = -xb[rb][kk];
+                    }
+                double u00[2], u10[2], u11[2];
+                u00[0] = Ls[R + g][R + 2 * tg];          u00[1] = Ls[R + g][R + 2 * tg + 1];
+                u10[0] = Ls[R + 8 + g][R + 2 * tg];      u10[1] = Ls[R + 8 + g][R + 2 * tg + 1];
+                u11[0] = Ls[R + 8 + g][R + 8 + 2 * tg];  u11[1] = Ls[R + 8 + g][R + 8 + 2 * tg + 1];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                {
+                    dmma_8x8x4(u00[0], u00[1], xa[0][kk], xb[0][kk]);
+                    dmma_8x8x4(u10[0], u10[1], xa[1][kk], xb[0][kk]);
+                    dmma_8x8x4(u11[0], u11[1], xa[1][kk], xb[1][kk]);
+                }
+                __syncwarp();
+                Ls[R + g][R + 2 * tg] = u00[0];          Ls[R + g][R + 2 * tg + 1] = u00[1];
+                Ls[R + 8 + g][R + 2 * tg] = u10[0];      Ls[R + 8 + g][R + 2 * tg + 1] = u10[1];
+                Ls[R + 8 + g][R + 8 + 2 * tg] = u11[0];  Ls[R + 8 + g][R + 8 + 2 * tg + 1] = u11[1];
+            }
+        }
+        else
+        {
+            const int w = warp - 1;                         // 0..6
+            if (k >= 1 && k <= 2)
+            {
+                const int p0 = c0 - 16;                     // panel k-1
+                // ---- R(k-1): rows p0+32..63, one 8-row block per warp ------------------------------------------
+                const int nrb = (32 - p0) >> 3;             // 4, 2
+                if (w < nrb)
+                {
+                    const int R = p0 + 32 + 8 * w;
+                    double af[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        af[kk] = Ls[R + g][p0 + 4 * kk + tg];
+                    double x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                    {
+                        if (kk < 2) dmma_8x8x4(x00, x01, af[kk], Li[p0 + g][p0 + 4 * kk + tg]);
+                        dmma_8x8x4(x10, x11, af[kk], Li[p0 + 8 + g][p0 + 4 * kk + tg]);
+                    }
+                    __syncwarp();
+                    Ls[R + g][p0 + 2 * tg] = x00;
+                    Ls[R + g][p0 + 2 * tg + 1] = x01;
+                    Ls[R + g][p0 + 8 + 2 * tg] = x10;
+                    Ls[R + g][p0 + 8 + 2 * tg + 1] = x11;
+                }
+                named_bar_sync(1, NT_TILE - 32);
+                // ---- T(k-1): 8x8 blocks (bi, bj), bi >= bj, of rows/cols r0..63 except the first 16x16 block ---
+                const int r0 = p0 + 16, nb = (64 - r0) >> 3;     // 6, 4
+                const int nblk = nb * (nb + 1) / 2 - 3;          // 18, 7
+                int ro[3], co[3];
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                {
+                    const int q = w + 7 * v + 3;                 // skip (0,0) (1,0) (1,1)
+                    int bi = 0;
+                    bi += (q >= 1) + (q >= 3) + (q >= 6) + (q >= 10) + (q >= 15);
+                    const int bj = q - bi * (bi + 1) / 2;
+                    const bool act = w + 7 * v < nblk;
+                    ro[v] = act ? r0 + 8 * bi : r0 + 16;
+                    co[v] = act ? r0 + 8 * bj : r0;
+                }
+                double af[3][4], bf[3][4], u[3][2];
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                    {
+                        af[v][kk] = -Ls[ro[v] + g][p0 + 4 * kk + tg];
+                        bf[v][kk] = Ls[co[v] + g][p0 + 4 * kk + tg];
+                    }
+                    u[v][0] = Ls[ro[v] + g][co[v] + 2 * tg];
+                    u[v][1] = Ls[ro[v] + g][co[v] + 2 * tg + 1];
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int v = 0; v < 3; ++v)
+                        dmma_8x8x4(u[v][0], u[v][1], af[v][kk], bf[v][kk]);
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                    if (w + 7 * v < nblk)
+                    {
+                        Ls[ro[v] + g][co[v] + 2 * tg] = u[v][0];
+                        Ls[ro[v] + g][co[v] + 2 * tg + 1] = u[v][1];
+                    }
+            }
+            if (k < 3)
+            {
+                __threadfence_block();
+                named_bar_arrive(2, NT_TILE);
+            }
+        }
+        __syncthreads();
+    }
+    TT(1);
+    return *sflag;
+}
+#else
 // `deferred_flag`: a publish the caller still owes (its data was stored and a block barrier has passed): a
 // thread of warp 1 releases it while warp 0 runs the first pivot chain, so the release fence (~1 us) is
 // hidden instead of delaying the caller's critical path.
@@ -312,6 +569,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
     TT(1);
     return *sflag;
 }
+#endif  // SB200_V_LOOKAHEAD
 
 // The four 16x16 diagonal blocks of Li = L^-1 (lane j of warp b computes column j of block b); the
 // strictly-upper 16x16 blocks of Li are cleared.  Ends with a block barrier.

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
-from typing import Optional
+from typing import List, Optional
 
 import numpy as np
 
@@ -294,7 +294,55 @@ def workspace_for_nodes(base: SyphaNodeSparse, max_depth: int, device: int = 0) 
     return ws
 
 
-def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecutionConfig, workspaces):
+@dataclasses.dataclass
+class NodeHeuristicResult:
+    """What ``sb200_node_heuristics`` returns per node (include/sypha_b200.h ``sb200_heur_result``)."""
+    feasible: bool
+    coverObj: float
+    nChosen: int
+    branchVar: int
+    branchFrac: float
+    roundedObj: float
+    repairSteps: int
+
+
+def node_heuristics(workspaces) -> List[NodeHeuristicResult]:
+    """Branching variable + rounding/repair incumbent of the nodes whose LPs were just solved in
+    ``workspaces`` - on the device, concurrently (reference: host loop, bnb_driver.cpp:861-1005)."""
+    lib = L.load()
+    k = len(workspaces)
+    handles = (C.c_void_p * k)(*[ws.handle for ws in workspaces])
+    out = (L.sb200_heur_result * k)()
+    rc = lib.sb200_node_heuristics(handles, k, out)
+    if rc != L.SB200_OK:
+        msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in workspaces)
+        raise Sb200Error(f"sb200_node_heuristics failed (code {rc}): {msgs}")
+    return [NodeHeuristicResult(bool(o.feasible), o.cover_obj, o.n_chosen, o.branch_var, o.branch_frac,
+                                o.rounded_obj, o.repair_steps) for o in out]
+
+
+def get_primal(workspace: IpmWorkspace, n: int) -> np.ndarray:
+    """Host copy of the resident primal iterate (length n = columns of the model as last solved)."""
+    lib = L.load()
+    x = np.empty(n)
+    rc = lib.sb200_get_iterates(workspace.handle, x.ctypes.data, None, None)
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_get_iterates failed (code {rc}): {lib.sb200_last_error(workspace.handle).decode()}")
+    return x
+
+
+def get_cover(workspace: IpmWorkspace, n_orig: int) -> np.ndarray:
+    """The 0/1 cover found by the last ``node_heuristics`` on this workspace (float64, length n_orig)."""
+    lib = L.load()
+    buf = np.empty(n_orig, dtype=np.uint8)
+    rc = lib.sb200_get_cover(workspace.handle, buf.ctypes.data)
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_get_cover failed (code {rc}): {lib.sb200_last_error(workspace.handle).decode()}")
+    return buf.astype(np.float64)
+
+
+def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecutionConfig, workspaces,
+                      fetch_solutions: bool = True):
     """B&B node body, batched and device-resident: workspace i holds the base model; node i = base + one row
     per (var, fix) decision (bnb.cpp:453-468) is formed on the device (``sb200_node_delta``) and the LPs are
     solved concurrently.  Returns one SolverExecutionResult per node (solutions have the node's dimensions)."""
@@ -315,9 +363,12 @@ def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecu
         deltas[i].var = var.ctypes.data_as(C.POINTER(C.c_int))
         deltas[i].coef = coef.ctypes.data_as(C.POINTER(C.c_double))
         deltas[i].rhs = fix.ctypes.data_as(C.POINTER(C.c_double))
-        x, y, s = np.empty(base.ncols + d), np.empty(base.nrows + d), np.empty(base.ncols + d)
-        res[i].x_host, res[i].y_host, res[i].s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data
-        bufs.append((x, y, s))
+        if fetch_solutions:
+            x, y, s = np.empty(base.ncols + d), np.empty(base.nrows + d), np.empty(base.ncols + d)
+            res[i].x_host, res[i].y_host, res[i].s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data
+            bufs.append((x, y, s))
+        else:
+            bufs.append((None, None, None))       # the iterates stay on the device (sb200_node_heuristics reads them)
     rc = lib.sb200_solve_batch(handles, k, deltas, C.byref(p), res)
     if rc != L.SB200_OK:
         msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in workspaces[:k])

@@ -37,6 +37,15 @@ def _worker(rank, world, port, q):
     out["lb"] = ex.global_lower_bound(5.0 + rank)
     out["cnt"] = ex.reduce_counters(1.0 + rank, [10 * (rank + 1), 1])
     out["part"] = ex.partition_round_robin(list(range(7)), rank, world)
+    # node donation: rank 0 has 7 open nodes (one too deep to travel), rank 1 has 1
+    if rank == 0:
+        nodes = [(tuple((10 * i + d, d % 2) for d in range(i)), 40.0 + i / 8) for i in range(6)]
+        nodes.append((tuple((d, 1) for d in range(9)), -math.inf))          # depth 9 > max_depth 8: stays
+    else:
+        nodes = [(((3, 0),), 41.5)]
+    out["rebalanced"] = ex.rebalance_frontier(nodes, max_depth=8)
+    out["balanced_again"] = ex.rebalance_frontier(out["rebalanced"][0], max_depth=8)[1:]
+    out["empty"] = ex.rebalance_frontier([], max_depth=8)[1:]
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -62,3 +71,23 @@ def test_incumbent_exchange_world2():
         assert o["lb"] == 5.0
         assert o["cnt"] == (2.0, [30.0, 2.0])
     assert res[0]["part"] == [0, 2, 4, 6] and res[1]["part"] == [1, 3, 5]
+    # 7 + 1 nodes -> 4 + 4: rank 0 gives its last three donatable nodes (i = 5, 4, 3), the deep one stays
+    n0, total0, sent0, recv0 = res[0]["rebalanced"]
+    n1, total1, sent1, recv1 = res[1]["rebalanced"]
+    assert (total0, sent0, recv0) == (8, 3, 0) and (total1, sent1, recv1) == (8, 0, 3)
+    mk = lambda i: (tuple((10 * i + d, d % 2) for d in range(i)), 40.0 + i / 8)
+    assert n0 == [mk(0), mk(1), mk(2), (tuple((d, 1) for d in range(9)), -math.inf)]
+    assert n1 == [(((3, 0),), 41.5), mk(5), mk(4), mk(3)]
+    assert res[0]["balanced_again"] == (8, 0, 0) and res[1]["balanced_again"] == (8, 0, 0)
+    assert res[0]["empty"] == (0, 0, 0)
+
+
+def test_transfer_plan_is_balanced_and_minimal():
+    from sypha_b200.bnb_exchange import plan_transfers
+    targets, moves = plan_transfers([10, 0, 3, 3])
+    assert targets == [4, 4, 4, 4]
+    assert moves == [(0, 1, 4), (0, 2, 1), (0, 3, 1)]
+    targets, moves = plan_transfers([0, 0, 0, 9, 0, 0, 0, 0])
+    assert targets == [2, 1, 1, 1, 1, 1, 1, 1] and sum(k for _, _, k in moves) == 8
+    assert all(s == 3 for s, _, _ in moves)
+    assert plan_transfers([5, 5])[1] == [] and plan_transfers([6, 5])[1] == []

@@ -93,3 +93,68 @@ def test_host_and_device_node_paths_search_the_same_tree():
         finally:
             drv.close()
     assert out[0] == out[1]
+
+
+def _check_node_heuristics(mdl, decs, max_iter):
+    """sb200_node_heuristics (device) against bnb.CoverHeuristic + the NumPy branching rule (host) on the
+    same LP points: integer work, so everything must be identical."""
+    import sypha_b200 as sb
+    from sypha_b200 import solver as S
+    env = sb.SyphaEnvironment()
+    cfg = sb.SolverExecutionConfig(maxIterations=max_iter)
+    base = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+    wss = [S.workspace_for_nodes(base, 70) for _ in decs]
+    host = bnb.CoverHeuristic(mdl)
+    n0 = mdl.n_orig
+    steps = []
+    try:
+        S.solve_batch_nodes(base, decs, cfg, wss, fetch_solutions=False)
+        got = S.node_heuristics(wss)
+        for dec, ws, h in zip(decs, wss, got):
+            x = S.get_primal(ws, mdl.n + len(dec))[:n0]
+            obj, cover = host(x, [v for v, f in dec if f == 0])
+            frac = np.abs(x - np.round(x))
+            assert h.branchVar == int(np.argmax(frac))
+            assert h.branchFrac == frac[h.branchVar]
+            assert abs(h.roundedObj - float(mdl.c[:n0] @ np.round(x))) <= 1e-9 * max(1.0, abs(h.roundedObj))
+            if cover is None:
+                assert not h.feasible
+                continue
+            assert h.feasible
+            assert h.coverObj == obj, (h, obj)
+            dev_cover = S.get_cover(ws, n0)
+            assert np.array_equal(dev_cover, cover)
+            assert h.nChosen == int(cover.sum())
+            assert np.all(host.A @ dev_cover >= 1.0)
+            steps.append(h.repairSteps)
+    finally:
+        for w in wss:
+            sb.releaseIpmWorkspace(w)
+    return steps
+
+
+def test_node_heuristics_kernel_matches_the_host_rules_at_the_lp_optimum():
+    mdl = gen_scp(120, 900, 0.04, 11)
+    decs = [(), ((5, 1), (17, 0), (400, 1)), tuple((3 * i + 1, i % 2) for i in range(40)), ((7, 0),)]
+    _check_node_heuristics(mdl, decs, 100)
+
+
+@pytest.mark.parametrize("max_iter", [1, 3])
+def test_node_heuristics_kernel_long_repairs(max_iter):
+    """An LP point far from the optimum (1 or 3 IPM iterations) rounds to almost nothing, so the cover is built
+    by the greedy repair alone: many picks, every incremental gain update exercised; unit costs give ties."""
+    mdl = gen_scp(200, 3000, 0.02, 4)
+    decs = [(), tuple((11 * i, 0) for i in range(30)), ((1, 1), (2, 0))]
+    steps = _check_node_heuristics(mdl, decs, max_iter)
+    ties = gen_scp(150, 1200, 0.03, 8)
+    ties.c[:ties.n_orig] = 1.0 + (np.arange(ties.n_orig) % 3)
+    steps += _check_node_heuristics(ties, [(), ((0, 0), (1, 0), (2, 0))], max_iter)
+    assert max(steps) >= 10, steps
+
+
+def test_node_heuristics_kernel_reports_infeasible_fixings():
+    mdl = gen_scp(40, 200, 0.08, 5)
+    row0 = mdl.inds[mdl.offs[0]:mdl.offs[1]]
+    ban = tuple((int(j), 0) for j in row0 if j < mdl.n_orig)       # every column of row 0 fixed to 0
+    assert len(ban) <= 64
+    _check_node_heuristics(mdl, [ban, ()], 100)

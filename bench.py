@@ -263,6 +263,9 @@ def run_bnb(args, rank, world, local_rank):
                       "(host node construction, upload, LP solves, heuristics, incumbent exchange)",
             "nodes": int(nodes), "lp_iterations": int(iters), "lp_device_ms_per_node": dev_ms / max(nodes, 1),
             "incumbent": drv.stats.incumbent, "root_bound": drv.stats.root_bound,
+            "rank0_rounds": {"ms": drv.stats.round_ms[-args.steps:], "sum_of_longest_lp_iterations": drv.stats.round_max_iterations,
+                             "lp_at_iteration_cap": drv.stats.maxiter_nodes, "lp_iterations_total": drv.stats.lp_iterations,
+                             "nodes_total": drv.stats.processed, "rounds_total": drv.stats.rounds},
             "incumbent_exchange_bytes_per_round": (16 + 8 * n0) if dist else 0,
             "node_donation": {"every_rounds": 4, "sent_by_rank0": drv.stats.nodes_sent, "received_by_rank0": drv.stats.nodes_received}
             if drv.rebalance is not None else None,
@@ -411,6 +414,23 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_evt.set()
     sampler.join(timeout=2)
 
+    # ---- secondary: the same resident LPs solved CONCURRENTLY (one stream each, sb200_solve_batch) -----
+    batch_block = None
+    if rank == 0 and not args.no_batch_block and N_INSTANCES > 1:
+        from sypha_b200.solver import solve_batch
+        solve_batch(nodes, cfg, wss)                                   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps, b_iters = 3, 0
+        for _ in range(reps):
+            b_iters += sum(r.iterations for r in solve_batch(nodes, cfg, wss))
+        torch.cuda.synchronize()
+        b_el = time.perf_counter() - t0
+        batch_block = {"concurrent_lps": N_INSTANCES, "value": b_iters / b_el, "unit": "iter/s",
+                       "ms_per_batch": 1e3 * b_el / reps,
+                       "note": "throughput with the instances' LPs in flight together (host clock, results read back); "
+                               "the headline value is one LP at a time"}
+
     # ---- max over ranks / sums ----------------------------------------------------------------
     if dist:
         t = torch.tensor([elapsed, e2e_elapsed, wall], device="cuda", dtype=torch.float64)
@@ -486,6 +506,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof,
             "phases": phases,
         }
+        if batch_block:
+            out["concurrent_lps"] = batch_block
         if world == 1 and not args.no_pcg_block and args.workload != "synth50k":
             try:
                 out["pcg_50kx1M"] = pcg_block(lib, sb, local_rank, peak, full_solve=not args.no_pcg_solve)
@@ -574,6 +596,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
     ap.add_argument("--no-pcg-block", action="store_true")
+    ap.add_argument("--no-batch-block", action="store_true")
     ap.add_argument("--no-pcg-solve", action="store_true", help="skip the whole 50k x 1M LP solve (about 15 s)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--cg-max-iter", type=int, default=50000)

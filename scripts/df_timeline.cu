@@ -62,7 +62,7 @@ int main(int argc, char **argv)
         const int type = tasks[t].x >> 16, i = tasks[t].x & 0xffff, j = tasks[t].y;
         const bool diag = type == 2;
         if (T > 20 && !(diag || type == 1 || i == j + 2)) continue;
-        printf("%s %3d %3d  %8.2f %8.2f %8.2f %8.2f\n", type == 1 ? "pair" : (diag ? "chain" : "tile"), i, j,
+        printf("%s %3d %3d  %8.2f %8.2f %8.2f %8.2f\n", type == 1 ? "pair" : (diag ? "chain" : (type == 4 ? "zinv" : "tile")), i, j,
                (tm[t][0] - t0) * 1e-3, type == 1 ? 0.0 : (tm[t][1] - t0) * 1e-3, diag ? (tm[t][2] - t0) * 1e-3 : 0.0,
                (tm[t][3] - t0) * 1e-3);
         if (diag && j > 0)
@@ -88,9 +88,16 @@ int main(int argc, char **argv)
         long long tt[64];
         cudaMemcpyFromSymbol(tt, g_tile_timing, sizeof tt);
         printf("# last tile factorisation (cycles): total %lld\n", tt[1] - tt[0]);
+#if SB200_V_LOOKAHEAD
+        for (int kb = 0; kb < 4; kb++)
+            printf("   step %d (cycles from step start): warps 1-7 done %lld  P done %lld  N done %lld  step end %lld\n", kb,
+                   tt[9 + 4 * kb] - tt[8 + 4 * kb], tt[10 + 4 * kb] - tt[8 + 4 * kb], kb < 3 ? tt[11 + 4 * kb] - tt[8 + 4 * kb] : 0ll,
+                   (kb < 3 ? tt[12 + 4 * kb] : tt[1]) - tt[8 + 4 * kb]);
+#else
         for (int kb = 0; kb < 4; kb++)
             printf("   panel %d: diag16 %lld  rows-below %lld  trailing %lld\n", kb, tt[9 + 4 * kb] - tt[8 + 4 * kb],
                    tt[10 + 4 * kb] - tt[9 + 4 * kb], (kb < 3 ? tt[12 + 4 * kb] : tt[1]) - tt[10 + 4 * kb]);
+#endif
     }
 #endif
     int hinfo = -1;

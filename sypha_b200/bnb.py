@@ -126,6 +126,9 @@ class BnbStats:
     root_bound: float = -math.inf
     nodes_sent: int = 0
     nodes_received: int = 0
+    maxiter_nodes: int = 0          # node LPs that stopped at the iteration cap
+    round_max_iterations: int = 0   # sum over rounds of the longest LP of the window (what a round waits for)
+    round_ms: list = dataclasses.field(default_factory=list)
 
 
 class BatchedBnb:
@@ -204,6 +207,7 @@ class BatchedBnb:
     def round(self) -> int:
         """Pop up to K nodes, solve their LPs as one batch, branch.  Returns the number processed."""
         batch: List[BnbNode] = []
+        t_round = time.perf_counter()
         while self.frontier and len(batch) < self.slots:
             nd = self.frontier.popleft()                       # FIFO, bnb.cpp:42-43
             if self._prunable(nd.parent_bound):                # bnb_driver.cpp:797
@@ -227,6 +231,8 @@ class BatchedBnb:
                 heur = None
                 self.device_nodes = self.device_heuristics = False      # the slots no longer hold the base model
             self._fold_pending()               # heuristics of the previous round (ran beside this solve)
+            self.stats.round_max_iterations += max(r.iterations for r in results)
+            self.stats.maxiter_nodes += sum(1 for r in results if r.terminationReason == TERM_MAX_ITER)
             for slot, (nd, res) in enumerate(zip(batch, results)):
                 self.stats.processed += 1
                 self.stats.lp_iterations += res.iterations
@@ -282,6 +288,7 @@ class BatchedBnb:
             self.stats.nodes_sent += sent
             self.stats.nodes_received += recv
         self.stats.rounds += 1
+        self.stats.round_ms.append(round(1e3 * (time.perf_counter() - t_round), 2))
         return len(batch)
 
     def run(self, max_nodes: int, rounds: Optional[int] = None) -> BnbStats:

@@ -215,6 +215,9 @@ struct PotrfDf
     double2 *d1tag;      // [T][D1_PAIRS]: what the next chain task needs of a factored diagonal tile, tagged
     double *gbuf;        // [T2(T2-1)/2][128][128]: G_ik = W_i L_ik, the blocks the solves stream (see k_trsv_df)
     double *gbufT;       // the same blocks transposed (backward sweep)
+    double *zbuf;        // explicit inverse Z = L^-1 (row-major, leading dimension ld) or nullptr: TASK_Z tiles
+    double *zTbuf;       // Z'
+    int *z_flag;         // [T*T]: Z tile (i,j) final
 };
 // payload of a tagged D1: the six strictly-lower 16x16 blocks of L_jj, then its four 16x16 diagonal inverses
 static constexpr int D1_PAIRS = 6 * 256 + 4 * 256;
@@ -235,7 +238,10 @@ __device__ __forceinline__ void d1_slot(int p, bool &is_l, int &r, int &c)
         c = 16 * b + (e & 15);
     }
 }
-enum { TASK_TILE = 0, TASK_PAIR = 1, TASK_CHAIN = 2, TASK_G = 3 };
+enum { TASK_TILE = 0, TASK_PAIR = 1, TASK_CHAIN = 2, TASK_G = 3, TASK_Z = 4 };
+#ifndef SB200_Z_MAX_T
+#define SB200_Z_MAX_T 20     // up to 1280 rows the factorisation also forms Z = L^-1 (see TASK_Z)
+#endif
 
 __device__ __forceinline__ void ldcg_tile_chunk(double (*S)[KP], const double *g, size_t ld, int tid)
 {   // 64 x KC block, bypassing L1 (the tile was written by another SM during this launch)
@@ -694,6 +700,75 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             continue;
         }
 
+        if (type == TASK_Z)
+        {   // ---- tile (ti, tj), ti > tj, of Z = L^-1:  Z_ij = -W_i sum_{k=j}^{i-1} L_ik Z_kj  (Z_jj = W_j, written by
+            //      chain(j)).  Left-looking like the tiles of L: the sum accumulates in registers as row i of L and
+            //      the rows above of column j of Z are published, so that after chain(i) only the product with W_i is
+            //      left.  With Z (and Z') in memory the solves M x = b are two triangular matrix-vector products
+            //      over the whole GPU, x = Z'(Z b), instead of 2 x T/2 dependent block hops.
+            const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
+            double acc[4][2][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+                    acc[i][jj][0] = acc[i][jj][1] = 0.0;
+            for (int k = tj; k < ti; ++k)
+            {
+                if (tid == 0)
+                {
+                    spin_until(P.tile_flag + ti * T + k, epoch, C.err);
+                    spin_until(k == tj ? P.d2_flag + tj : P.z_flag + k * T + tj, epoch, C.err);
+                }
+                const size_t k0 = (size_t)k * TB;
+#pragma unroll
+                for (int kc = 0; kc < TB; kc += KC)
+                {
+                    __syncthreads();
+                    ldcg_tile_chunk(As, P.A + r0 * ld + k0 + kc, ld, tid);           // L_ik[:, kc..]
+                    ldcg_tile_chunk(Bs, P.zTbuf + c0 * ld + k0 + kc, ld, tid);       // (Z_kj)'[:, kc..]
+                    __syncthreads();
+                    warp_mma<4, 2>(As, Bs, row0, col0, lane, 1.0, acc);
+                }
+            }
+            __syncthreads();
+            DFT(t, 1);
+            double(*S0)[XP] = reinterpret_cast<double(*)[XP]>(dyn_smem + SM_LS);
+            double(*S1)[XP] = reinterpret_cast<double(*)[XP]>(dyn_smem + SM_LI);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+                    *reinterpret_cast<double2 *>(&S1[row0 + i * 8 + g][col0 + jj * 8 + tg * 2]) =
+                        make_double2(acc[i][jj][0], acc[i][jj][1]);
+            if (tid == 0) spin_until(P.d2_flag + ti, epoch, C.err);
+            __syncthreads();
+            {
+                const double *Wi = P.linv + (size_t)ti * TB * TB;
+                for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
+                {
+                    const int r = idx >> 5, c2 = (idx & 31) * 2;
+                    *reinterpret_cast<double2 *>(&S0[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(Wi + r * TB + c2));
+                }
+            }
+            __syncthreads();
+            double *zo = P.zbuf + r0 * ld + c0;            // Z tile (i, j)
+            double *zt = P.zTbuf + c0 * ld + r0;           // Z' tile (j, i)
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb)
+            {   // warp w owns rows 8w..8w+7; W_i lower triangular: k < 8w + 8
+                double z0 = 0.0, z1 = 0.0;
+                for (int kk = 0; kk < 8 * w + 8; kk += 4)
+                    dmma_8x8x4(z0, z1, -S0[8 * w + g][kk + tg], S1[kk + tg][8 * nb + g]);
+                *reinterpret_cast<double2 *>(zo + (size_t)(8 * w + g) * ld + 8 * nb + 2 * tg) = make_double2(z0, z1);
+                zt[(size_t)(8 * nb + 2 * tg) * ld + 8 * w + g] = z0;
+                zt[(size_t)(8 * nb + 2 * tg + 1) * ld + 8 * w + g] = z1;
+            }
+            publish(P.z_flag + ti * T + tj, epoch);
+            DFT(t, 3);
+            continue;
+        }
+
         if (type == TASK_TILE)
         {   // ---- regular off-diagonal tile (ti >= tj + 2): left-looking accumulation, then X = acc L_jj^-T
             const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
@@ -867,6 +942,16 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             {
                 const int r = idx >> 6, c = idx & 63;
                 if ((r >> 4) > (c >> 4)) linv_j[idx] = Li[r][c];
+            }
+            if (P.zbuf)
+            {   // Z_jj = W_j (zero above the diagonal) and its transpose: the diagonal tiles of Z and Z'
+                double *zd = P.zbuf + c0 * ld + c0, *ztd = P.zTbuf + c0 * ld + c0;
+                for (int idx = tid; idx < TB * TB; idx += NT_TILE)
+                {
+                    const int r = idx >> 6, c = idx & 63;
+                    zd[(size_t)r * ld + c] = Li[r][c];
+                    ztd[(size_t)r * ld + c] = Li[c][r];
+                }
             }
             publish(P.d2_flag + j, epoch);                            // D2
             DFT(t, 3);
@@ -1082,6 +1167,36 @@ __global__ void __launch_bounds__(NT_TRSV, 1) k_trsv_df(TrsvDf P, DfCtl C)
 }
 
 // ---------------------------------------------------------------------------------------------
+// triangular matrix-vector product for the explicit-inverse solves: y = Z x over the lower triangle
+// (upper = 0: row r spans columns 0..r) or over the upper one (row r spans r..ld-1).  Four rows per CTA, 64
+// threads per row, 16-byte loads, every load of a thread independent; fixed summation order (bit-reproducible).
+// The element next to the diagonal that a 16-byte access drags in is an explicit zero of the diagonal tile.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tri_gemv(const double *__restrict__ Z, int ld, const double *__restrict__ x,
+                                                  double *__restrict__ y, int upper)
+{
+    __shared__ double part[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = 4 * blockIdx.x + (warp >> 1), t64 = (warp & 1) * 32 + lane;
+    const int lo = upper ? (r & ~1) : 0, hi = upper ? ld : ((r + 2) & ~1);
+    const double *row = Z + (size_t)r * ld;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+    for (int c = lo + 2 * t64; c < hi; c += 128)
+    {
+        const double2 z = __ldcg(reinterpret_cast<const double2 *>(row + c));
+        a0 = fma(z.x, x[c], a0);          // x: 8-byte loads (caller-owned vector, alignment not assumed)
+        a1 = fma(z.y, x[c + 1], a1);
+    }
+    double a = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) part[warp] = a;
+    __syncthreads();
+    if (tid < 4) y[4 * blockIdx.x + tid] = part[2 * tid] + part[2 * tid + 1];
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int build_task_list(ErrorSink &err, CholWork &W, int T)
@@ -1100,9 +1215,18 @@ static int build_task_list(ErrorSink &err, CholWork &W, int T)
             tasks.push_back(make_int2(i | (TASK_G << 16), tj));
     };
     int g_done = 0;                      // block rows whose G tasks are listed
+    const bool use_z = T <= SB200_Z_MAX_T;
     for (int j = 0; j < T; ++j)
     {
         tasks.push_back(make_int2(j | (TASK_CHAIN << 16), j));      // tile (j, j-1) + diagonal tile j
+        if (use_z)
+        {   // explicit inverse instead of the pair inverses and G: row j of Z follows column j of L
+            for (int i = j + 2; i < T; ++i)
+                tasks.push_back(make_int2(i | (TASK_TILE << 16), j));
+            for (int c = 0; c < j; ++c)
+                tasks.push_back(make_int2(j | (TASK_Z << 16), c));
+            continue;
+        }
         if ((j & 1) || j == T - 1)
             tasks.push_back(make_int2(TASK_PAIR << 16, j >> 1));    // j even and last: odd tile count
         for (int i = j + 2; i < T; ++i)
@@ -1114,7 +1238,7 @@ static int build_task_list(ErrorSink &err, CholWork &W, int T)
         while (T <= 20 && 2 * g_done + 3 <= j)
             push_g(g_done++);
     }
-    while (2 * g_done < T)
+    while (!use_z && 2 * g_done < T)
         push_g(g_done++);
     W.tasks = nullptr;
     SB200_CUDA_TRY(err, cudaMalloc(&W.tasks, sizeof(int2) * tasks.size()));
@@ -1135,7 +1259,7 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve)
         if (t_reserve > T) T = t_reserve;      // flags / inverse stores sized for the largest model expected
         chol_work_free(W);
         const int T2 = (T + 1) / 2;
-        const size_t nflags = (size_t)T * T + T + 3 * (size_t)T2 + 32;
+        const size_t nflags = 2 * (size_t)T * T + T + 3 * (size_t)T2 + 32;      // ... + Z tile flags at the end
         SB200_CUDA_TRY(err, cudaMalloc(&W.linv, sizeof(double) * (size_t)T * TB * TB));
         SB200_CUDA_TRY(err, cudaMemset(W.linv, 0, sizeof(double) * (size_t)T * TB * TB));
         SB200_CUDA_TRY(err, cudaMalloc(&W.linv128, sizeof(double) * (size_t)T2 * 128 * 128));
@@ -1145,6 +1269,14 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve)
             SB200_CUDA_TRY(err, cudaMemset(W.gbuf, 0, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
             SB200_CUDA_TRY(err, cudaMalloc(&W.gbufT, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
             SB200_CUDA_TRY(err, cudaMemset(W.gbufT, 0, sizeof(double) * (nblk ? nblk : 1) * 128 * 128));
+        }
+        {   // Z and Z' for models of up to SB200_Z_MAX_T tiles (the workspace may hold smaller models than T)
+            const size_t zl = (size_t)(T < SB200_Z_MAX_T ? T : SB200_Z_MAX_T) * TB;
+            SB200_CUDA_TRY(err, cudaMalloc(&W.zbuf, sizeof(double) * zl * zl));
+            SB200_CUDA_TRY(err, cudaMemset(W.zbuf, 0, sizeof(double) * zl * zl));
+            SB200_CUDA_TRY(err, cudaMalloc(&W.zTbuf, sizeof(double) * zl * zl));
+            SB200_CUDA_TRY(err, cudaMemset(W.zTbuf, 0, sizeof(double) * zl * zl));
+            SB200_CUDA_TRY(err, cudaMalloc(&W.ytmp, sizeof(double) * zl));
         }
         SB200_CUDA_TRY(err, cudaMalloc(&W.d1tag, sizeof(double2) * (size_t)T * D1_PAIRS));
         SB200_CUDA_TRY(err, cudaMemset(W.d1tag, 0, sizeof(double2) * (size_t)T * D1_PAIRS));
@@ -1178,6 +1310,9 @@ void chol_work_free(CholWork &W)
     if (W.d1tag) cudaFree(W.d1tag);
     if (W.gbuf) cudaFree(W.gbuf);
     if (W.gbufT) cudaFree(W.gbufT);
+    if (W.zbuf) cudaFree(W.zbuf);
+    if (W.zTbuf) cudaFree(W.zTbuf);
+    if (W.ytmp) cudaFree(W.ytmp);
     W = CholWork{};
 }
 
@@ -1189,7 +1324,9 @@ void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t
     const int T = ld / TB, T2 = (T + 1) / 2;
     int *ctl = W.ctl, *flags = W.ctl + 32;
     const size_t tc = (size_t)W.t_cap;
-    PotrfDf P{a, ld, T, W.linv, W.linv128, W.tasks, W.ntasks, flags, flags + tc * tc, flags + tc * tc + tc, info, W.d1tag, W.gbuf, W.gbufT};
+    const bool use_z = T <= SB200_Z_MAX_T;
+    PotrfDf P{a, ld, T, W.linv, W.linv128, W.tasks, W.ntasks, flags, flags + tc * tc, flags + tc * tc + tc, info, W.d1tag, W.gbuf, W.gbufT,
+              use_z ? W.zbuf : nullptr, use_z ? W.zTbuf : nullptr, flags + tc * tc + tc + 3 * ((tc + 1) / 2)};
     DfCtl C{ctl + 0, reinterpret_cast<unsigned *>(ctl + 1), reinterpret_cast<unsigned *>(ctl + 2), ctl + 8};
     const int cap = W.sms * W.potrf_occ;
     const int grid = W.ntasks < cap ? W.ntasks : cap;
@@ -1204,7 +1341,14 @@ void launch_potrs(CholWork &W, int n, const double *l, int ld, double *b, cudaSt
     int *ctl = W.ctl, *flags = W.ctl + 32;
     const size_t tc = (size_t)W.t_cap, tc2 = (tc + 1) / 2;
     (void)flags;
-    (void)l;     // the solves stream G = blockdiag(W) L, built by the factorisation
+    (void)l;     // the solves stream G = blockdiag(W) L (or Z = L^-1), built by the factorisation
+    if (T <= SB200_Z_MAX_T)
+    {   // x = Z'(Z b): two triangular matrix-vector products, four rows per CTA
+        k_tri_gemv<<<ld / 4, 256, 0, st>>>(W.zbuf, ld, b, W.ytmp, 0);
+        k_tri_gemv<<<ld / 4, 256, 0, st>>>(W.zTbuf, ld, W.ytmp, b, 1);
+        g_launch_count += 2;
+        return;
+    }
     TrsvDf P{W.gbuf, W.gbufT, ld, T2, W.linv128, b, W.tagged, W.tagged + tc2 * 128};
     DfCtl C{ctl + 4, reinterpret_cast<unsigned *>(ctl + 5), reinterpret_cast<unsigned *>(ctl + 6), ctl + 8};
     const int grid = 2 * T2 < W.sms ? 2 * T2 : W.sms;

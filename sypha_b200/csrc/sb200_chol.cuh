@@ -15,6 +15,11 @@ struct CholWork
     double *gbuf = nullptr;     // [T2(T2-1)/2][128][128] G_ik = W_i L_ik: the blocks the solves stream
     double2 *d1tag = nullptr;   // [T][2560] tagged hand-off of a factored diagonal tile to the next chain task
     double2 *tagged = nullptr;  // [2][ceil(T/2)*128] {value, epoch tag}: forward / backward solve hand-off
+    // explicit inverse Z = L^-1 (tile count <= SB200_Z_MAX_T): the solves become two triangular GEMVs over the
+    // whole GPU, x = Z'(Z b), instead of a chain of block hops (sb200_chol.cu, TASK_Z)
+    double *zbuf = nullptr;     // [ld][ld] row-major, lower triangle (64x64 tiles written by the factorisation)
+    double *zTbuf = nullptr;    // [ld][ld] row-major, Z' (upper triangle)
+    double *ytmp = nullptr;     // [t_cap*64]
     int *ctl = nullptr;         // epochs, task counters, error flag, then the publish flags
     int2 *tasks = nullptr;      // task list of the data-flow factorisation for tasks_T tiles
     int ntasks = 0, tasks_T = 0;

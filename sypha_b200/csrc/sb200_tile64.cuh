@@ -38,8 +38,10 @@ static constexpr int NT_TILE = 256;                               // threads of 
 // every shuffle take its slow path (measured: 19.6k instead of 3.6k cycles per 16x16 block)
 __device__ long long g_tile_timing[64];
 #define TT(i) do { if (tid == 32) g_tile_timing[i] = clock64(); } while (0)
+#define TT0(i) do { g_tile_timing[i] = clock64(); } while (0)      // whole warp 0, converged
 #else
 #define TT(i) do { } while (0)
+#define TT0(i) do { } while (0)
 #endif
 
 // One 8x8 output block of C = (+/-) A B on the FP64 tensor pipe, operands in shared memory:
@@ -225,6 +227,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
             const int bad = potrf_block16_warp(Ls, Li, Tb, c0, lane);
             if (lane == 0 && bad) atomicCAS(sflag, 0, bad);
             __syncwarp();
+            TT0(10 + 4 * k);
             if (k < 3)
             {
                 named_bar_sync(2, NT_TILE);                 // T(k-1) done: A[k+1][k] and A[k+1][k+1] are current
@@ -285,6 +288,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
                 Ls[R + g][R + 2 * tg] = u00[0];          Ls[R + g][R + 2 * tg + 1] = u00[1];
                 Ls[R + 8 + g][R + 2 * tg] = u10[0];      Ls[R + 8 + g][R + 2 * tg + 1] = u10[1];
                 Ls[R + 8 + g][R + 8 + 2 * tg] = u11[0];  Ls[R + 8 + g][R + 8 + 2 * tg + 1] = u11[1];
+                TT0(11 + 4 * k);
             }
         }
         else
@@ -358,6 +362,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
                         Ls[ro[v] + g][co[v] + 2 * tg + 1] = u[v][1];
                     }
             }
+            TT(9 + 4 * k);
             if (k < 3)
             {
                 __threadfence_block();

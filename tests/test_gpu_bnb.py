@@ -113,10 +113,13 @@ def _check_node_heuristics(mdl, decs, max_iter):
         for dec, ws, h in zip(decs, wss, got):
             x = S.get_primal(ws, mdl.n + len(dec))[:n0]
             obj, cover = host(x, [v for v, f in dec if f == 0])
-            frac = np.abs(x - np.round(x))
-            assert h.branchVar == int(np.argmax(frac))
-            assert h.branchFrac == frac[h.branchVar]
-            assert abs(h.roundedObj - float(mdl.c[:n0] @ np.round(x))) <= 1e-9 * max(1.0, abs(h.roundedObj))
+            if np.all(np.isfinite(x)):                 # (an infeasible node's LP point is not finite)
+                frac = np.abs(x - np.round(x))
+                assert h.branchVar == int(np.argmax(frac))
+                assert h.branchFrac == frac[h.branchVar]
+                assert abs(h.roundedObj - float(mdl.c[:n0] @ np.round(x))) <= 1e-9 * max(1.0, abs(h.roundedObj))
+            else:
+                assert h.branchVar == -1
             if cover is None:
                 assert not h.feasible
                 continue

@@ -231,7 +231,8 @@ def run_bnb(args, rank, world, local_rank):
     it_before = drv.stats.lp_iterations
     kl_before = drv.stats.kernels_launched
     t0 = time.perf_counter()
-    drv.run(max_nodes=10 ** 9, rounds=args.steps)          # a step = one round (window of K node LPs)
+    # a step = one round: a window of K node LPs, or (--stream-factor F) F*K nodes through the continuous batcher
+    drv.run(max_nodes=10 ** 9, rounds=args.steps, stream_nodes=args.stream_factor * args.slots)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -254,6 +255,8 @@ def run_bnb(args, rank, world, local_rank):
             "config": {"workload": "branch-and-bound on an scpnre-shaped synthetic SCP 500x5000, 10% density "
                                    "(configs[4]); a step = one round of K batched node LPs per GPU",
                        "slots_per_gpu": args.slots,
+                       "batching": (f"continuous (sb200_solve_stream), {args.stream_factor} x slots nodes per step"
+                                    if args.stream_factor > 0 else "windows of K nodes (sb200_solve_batch)"),
                        "node_heuristics": "host NumPy" if args.host_heuristics else "device kernel (sb200_node_heuristics)", "node_lp": "Mehrotra IPM to mu <= 1e-4, max_iter 100",
                        "frontier": "FIFO, most-fractional branching, round-robin split across ranks",
                        "collective": "all_reduce(MIN) of the incumbent objective + broadcast of the incumbent vector per round; "
@@ -588,6 +591,8 @@ def main():
     ap.add_argument("--slots", type=int, default=16, help="bnb: concurrent node LPs per GPU")
     ap.add_argument("--host-heuristics", action="store_true",
                     help="bnb: branching rule and rounding/repair heuristic on the host (NumPy) instead of the device kernel")
+    ap.add_argument("--stream-factor", type=int, default=0,
+                    help="bnb: > 0 = continuous batching (sb200_solve_stream), a step starts F x slots nodes; 0 = windows of K nodes")
     ap.add_argument("--no-donation", action="store_true", help="bnb, N > 1: keep the initial round-robin split (no node donation)")
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--poll-every", type=int, default=1)

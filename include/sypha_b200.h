@@ -176,6 +176,19 @@ int sb200_node_heuristics(sb200_ws **ws, int k, sb200_heur_result *out);
 /* the cover of the last sb200_node_heuristics on this workspace: n_orig bytes of 0/1 */
 int sb200_get_cover(sb200_ws *ws, unsigned char *x_host);
 
+/* Continuous batching of B&B node LPs over k workspaces that hold the same base model: whenever a slot is
+ * free `next(user, slot, &delta)` is asked for a node (return 1 with the decision list filled in - the arrays
+ * are copied before `next` returns control a second time - or 0 if there is none right now); the node's LP is
+ * solved (as sb200_set_node_delta + sb200_solve with x_host = y_host = s_host = NULL), sb200_node_heuristics
+ * runs behind it, and `done(user, slot, result, heur)` hands both records back - it may add nodes to the
+ * caller's frontier.  Returns when every slot is idle and `next` has nothing.  Callbacks run on the calling
+ * thread.  Replaces the one-node-at-a-time loop of src/sypha_solver_bnb_driver.cpp:698-1046 without a window
+ * barrier: a slot never waits for another slot's LP. */
+typedef int (*sb200_next_node_fn)(void *user, int slot, sb200_node_delta *delta);
+typedef void (*sb200_node_done_fn)(void *user, int slot, const sb200_result *result, const sb200_heur_result *heur);
+int sb200_solve_stream(sb200_ws **ws, int k, const sb200_params *params, sb200_next_node_fn next,
+                       sb200_node_done_fn done, void *user);
+
 /* per-iteration trace of the last solve: rows of SB200_TRACE_COLS doubles
  * (mu_in, mu, mu_aff, sigma, alpha_p, alpha_d, primal, dual); returns rows written */
 #define SB200_TRACE_COLS 8

@@ -8,6 +8,9 @@ mkdir -p gpurun_out
   for s in 8 16 32; do
     echo "== bnb slots $s device"; timeout 300 python bench.py --workload bnb --slots $s --steps 20 --warmup 3 2>> gpurun_out/bnb.err | tee gpurun_out/bnb_s$s.json | cut -c1-150
   done
+  for s in 16 32; do
+    echo "== bnb slots $s stream x4"; timeout 300 python bench.py --workload bnb --slots $s --steps 5 --warmup 3 --stream-factor 4 2>> gpurun_out/bnb.err | tee gpurun_out/bnb_stream_s$s.json | cut -c1-150
+  done
   echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pcg-solve 2> gpurun_out/bench_o.err | tee gpurun_out/bench_o.json | cut -c1-300
 } > gpurun_out/round23.log 2>&1
 cat gpurun_out/round23.log

@@ -54,6 +54,10 @@ class sb200_heur_result(C.Structure):
                 ("cover_obj", C.c_double), ("branch_frac", C.c_double), ("rounded_obj", C.c_double)]
 
 
+NEXT_NODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(sb200_node_delta))
+NODE_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(sb200_result), C.POINTER(sb200_heur_result))
+
+
 # every symbol include/sypha_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 SYMBOLS = {
@@ -70,6 +74,7 @@ SYMBOLS = {
                                C.POINTER(sb200_result)]),
     "sb200_node_heuristics": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_heur_result)]),
     "sb200_get_cover": (_i, [_vp, _vp]),
+    "sb200_solve_stream": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_params), NEXT_NODE_FN, NODE_DONE_FN, _vp]),
     "sb200_get_trace": (_i, [_vp, _vp, _i]),
     "sb200_get_device_iterates": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "sb200_get_iterates": (_i, [_vp, _vp, _vp, _vp]),

@@ -279,6 +279,12 @@ class BatchedBnb:
                 self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
         else:
             self._fold_pending()
+        self._collectives()
+        self.stats.rounds += 1
+        self.stats.round_ms.append(round(1e3 * (time.perf_counter() - t_round), 2))
+        return len(batch)
+
+    def _collectives(self):
         if self.exchange is not None:                          # every rank calls it once per round
             self.incumbent, self.incumbent_x = self.exchange(self.incumbent, self.incumbent_x)
         if self.rebalance is not None and self.stats.rounds % self.rebalance_every == 0:
@@ -287,11 +293,109 @@ class BatchedBnb:
                 self.frontier = collections.deque(BnbNode(d, b) for d, b in nodes)
             self.stats.nodes_sent += sent
             self.stats.nodes_received += recv
-        self.stats.rounds += 1
-        self.stats.round_ms.append(round(1e3 * (time.perf_counter() - t_round), 2))
-        return len(batch)
 
-    def run(self, max_nodes: int, rounds: Optional[int] = None) -> BnbStats:
+    def stream_round(self, node_limit: int) -> int:
+        """Continuous batching (``sb200_solve_stream``): up to ``node_limit`` nodes are started, each slot taking
+        the next open node the moment its LP and its heuristics kernel are done - no slot waits for the slowest
+        LP of a window.  Children join the frontier while other nodes are still in flight, so the ORDER of the
+        search depends on completion times (the optimum does not).  Ends with the same collectives as
+        ``round``.  Returns the number of nodes processed."""
+        import ctypes as C
+        from . import _lib as L
+        from .solver import _params_from
+        if not (self.device_nodes and self.device_heuristics):
+            raise RuntimeError("stream_round needs device-resident node models and device heuristics")
+        lib = L.load()
+        t_round = time.perf_counter()
+        p = _params_from(self.base_node, self.cfg)
+        k = self.slots
+        handles = (C.c_void_p * k)(*[ws.handle for ws in self.ws])
+        in_slot: List[Optional[BnbNode]] = [None] * k
+        keep = [None] * k                       # the decision arrays of the node in each slot
+        started = [0]
+        failure: List[BaseException] = []
+        deep: List[BnbNode] = []
+        n_orig, st = self.base.n_orig, self.stats
+
+        def next_cb(_user, slot, delta):
+            try:
+                if failure or started[0] >= node_limit:
+                    return 0
+                while self.frontier:
+                    nd = self.frontier.popleft()
+                    if self._prunable(nd.parent_bound):
+                        st.pruned_by_bound += 1
+                        continue
+                    d = len(nd.decisions)
+                    if d > self.max_depth:                     # deeper than the workspaces were sized for
+                        deep.append(nd)
+                        continue
+                    var = np.fromiter((v for v, _ in nd.decisions), dtype=np.int32, count=d)
+                    fix = np.fromiter((f for _, f in nd.decisions), dtype=np.float64, count=d)
+                    coef = np.where(fix == 0.0, -1.0, 1.0)
+                    keep[slot] = (var, coef, fix)
+                    delta[0].n_extra_rows = d
+                    delta[0].var = var.ctypes.data_as(C.POINTER(C.c_int))
+                    delta[0].coef = coef.ctypes.data_as(C.POINTER(C.c_double))
+                    delta[0].rhs = fix.ctypes.data_as(C.POINTER(C.c_double))
+                    in_slot[slot] = nd
+                    started[0] += 1
+                    st.delta_rows += d
+                    return 1
+                return 0
+            except BaseException as e:          # an exception must not unwind through the C frame
+                failure.append(e)
+                return 0
+
+        def done_cb(_user, slot, res_p, heur_p):
+            try:
+                nd, r, h = in_slot[slot], res_p[0], heur_p[0]
+                in_slot[slot] = None
+                st.processed += 1
+                st.lp_iterations += r.iterations
+                st.lp_device_ms += r.ms_start + r.ms_setup + r.ms_loop
+                st.kernels_launched += int(r.kernels_launched) + 1
+                st.maxiter_nodes += 1 if r.reason == TERM_MAX_ITER else 0
+                ok = r.status == L.SB200_OK and r.reason == TERM_CONVERGED
+                if not ok or not np.isfinite(r.dual_obj):
+                    st.infeasible += 1
+                    return
+                bound = max(nd.parent_bound, min(r.dual_obj, r.primal_obj))
+                if not nd.decisions:
+                    st.root_bound = bound
+                if self._prunable(bound):
+                    st.pruned_by_bound += 1
+                    return
+                if h.feasible and h.cover_obj < self.incumbent:
+                    self._offer(h.cover_obj, get_cover(self.ws[slot], n_orig))
+                if h.branch_var < 0 or h.branch_frac < 1e-6:
+                    st.integral += 1
+                    if h.rounded_obj < self.incumbent:
+                        self._offer(h.rounded_obj, np.round(get_primal(self.ws[slot], self.base.n + len(nd.decisions))[:n_orig]))
+                    return
+                j = h.branch_var
+                self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
+                self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+            except BaseException as e:
+                failure.append(e)
+
+        before = st.processed
+        ncb, dcb = L.NEXT_NODE_FN(next_cb), L.NODE_DONE_FN(done_cb)
+        rc = lib.sb200_solve_stream(handles, k, C.byref(p), ncb, dcb, None)
+        if failure:
+            raise failure[0]
+        if rc != L.SB200_OK:
+            msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in self.ws)
+            raise RuntimeError(f"sb200_solve_stream failed (code {rc}): {msgs}")
+        self.frontier.extendleft(reversed(deep))
+        self._collectives()
+        st.rounds += 1
+        st.round_ms.append(round(1e3 * (time.perf_counter() - t_round), 2))
+        return st.processed - before
+
+    def run(self, max_nodes: int, rounds: Optional[int] = None, stream_nodes: int = 0) -> BnbStats:
+        """``stream_nodes`` > 0: every round is a ``stream_round`` of that many nodes (continuous batching)
+        instead of one window of K nodes."""
         t0 = time.perf_counter()
         r = 0
         # with several ranks the stop test must be the same on every rank (the collectives of a round are
@@ -303,7 +407,11 @@ class BatchedBnb:
                 return self.global_open > 0
             return bool(self.frontier) and self.stats.processed < max_nodes
         while more():
-            self.round()
+            if stream_nodes > 0 and self.device_nodes and self.device_heuristics:
+                if self.stream_round(stream_nodes) == 0 and self.frontier and rounds is None:
+                    self.round()                               # only nodes deeper than max_depth are left
+            else:
+                self.round()
             r += 1
             if not self.frontier and self._pending:            # last word of the heuristics before stopping
                 self._fold_pending()

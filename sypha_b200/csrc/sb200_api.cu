@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -971,46 +972,124 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     return SB200_OK;
 }
 
+// launch the per-node branching / incumbent kernel behind the workspace's last solve and request its 40-byte
+// record (pinned); the caller waits on the stream (or an event) before reading ws->heur_out_host
+static int enqueue_node_heuristics(sb200_ws *ws)
+{
+    if (!ws || !ws->loaded) return SB200_ERR_INVALID;
+    if (ws->active) return fail(ws, SB200_ERR_INVALID, "sb200_node_heuristics: a solve is still in flight");
+    if (!ws->csr_offs || !ws->csc_colptr || ws->n_orig <= 0)
+        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_node_heuristics: the model keeps no CSR/CSC lists");
+    WS_TRY(cudaSetDevice(ws->device));
+    const int n0 = ws->n_orig;
+    if (n0 > ws->heur_cap)
+    {
+        int rc;
+        if ((rc = grow(ws, &ws->heur_list, (size_t)n0))) return rc;
+        if ((rc = grow(ws, &ws->heur_sorted, (size_t)n0))) return rc;
+        if ((rc = grow(ws, &ws->heur_cover, (size_t)n0))) return rc;
+        if (!ws->heur_out)
+        {
+            if ((rc = grow(ws, &ws->heur_out, 1))) return rc;
+            WS_TRY(cudaMallocHost(&ws->heur_out_host, sizeof(sb200_heur_result)));
+        }
+        ws->heur_cap = n0;
+    }
+    HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
+               ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out};
+    const int rc = launch_node_heuristics(a, ws->stream);
+    if (rc == SB200_ERR_UNSUPPORTED)
+        return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
+    if (rc) return fail(ws, rc, "sb200_node_heuristics: launch configuration failed");
+    WS_TRY(cudaGetLastError());
+    WS_TRY(cudaMemcpyAsync(ws->heur_out_host, ws->heur_out, sizeof(sb200_heur_result), cudaMemcpyDeviceToHost,
+                           ws->stream));
+    return SB200_OK;
+}
+
 int sb200_node_heuristics(sb200_ws **wss, int k, sb200_heur_result *out)
 {
     if (!wss || k <= 0 || !out) return SB200_ERR_INVALID;
+    int rc;
     for (int i = 0; i < k; ++i)
-    {
-        sb200_ws *ws = wss[i];
-        if (!ws || !ws->loaded) return SB200_ERR_INVALID;
-        if (ws->active) return fail(ws, SB200_ERR_INVALID, "sb200_node_heuristics: a solve is still in flight");
-        if (!ws->csr_offs || !ws->csc_colptr || ws->n_orig <= 0)
-            return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_node_heuristics: the model keeps no CSR/CSC lists");
-        WS_TRY(cudaSetDevice(ws->device));
-        const int n0 = ws->n_orig;
-        if (n0 > ws->heur_cap)
-        {
-            int rc;
-            if ((rc = grow(ws, &ws->heur_list, (size_t)n0))) return rc;
-            if ((rc = grow(ws, &ws->heur_sorted, (size_t)n0))) return rc;
-            if ((rc = grow(ws, &ws->heur_cover, (size_t)n0))) return rc;
-            if (!ws->heur_out)
-            {
-                if ((rc = grow(ws, &ws->heur_out, 1))) return rc;
-                WS_TRY(cudaMallocHost(&ws->heur_out_host, sizeof(sb200_heur_result)));
-            }
-            ws->heur_cap = n0;
-        }
-        HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
-                   ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out};
-        const int rc = launch_node_heuristics(a, ws->stream);
-        if (rc == SB200_ERR_UNSUPPORTED)
-            return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
-        if (rc) return fail(ws, rc, "sb200_node_heuristics: launch configuration failed");
-        WS_TRY(cudaGetLastError());
-        WS_TRY(cudaMemcpyAsync(ws->heur_out_host, ws->heur_out, sizeof(sb200_heur_result), cudaMemcpyDeviceToHost,
-                               ws->stream));
-    }
+        if ((rc = enqueue_node_heuristics(wss[i]))) return rc;
     for (int i = 0; i < k; ++i)
     {
         sb200_ws *ws = wss[i];
         WS_TRY(cudaStreamSynchronize(ws->stream));
         out[i] = *ws->heur_out_host;
+    }
+    return SB200_OK;
+}
+
+int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_next_node_fn next,
+                       sb200_node_done_fn done, void *user)
+{
+    // Continuous batching of B&B node LPs: a slot that finishes its node takes the next one at once instead of
+    // waiting for the slowest LP of a window (node LPs of one window differ by 2x in iterations).
+    if (!wss || k <= 0 || !params || !next || !done) return SB200_ERR_INVALID;
+    enum { IDLE = 0, SOLVING = 1, HEUR = 2 };
+    std::vector<int> state(k, IDLE);
+    std::vector<sb200_result> res(k);
+    int rc, busy = 0;
+    bool dry = false;                      // the last sweep found no node for an idle slot
+    for (;;)
+    {
+        bool progressed = false;
+        for (int i = 0; i < k; ++i)
+        {
+            sb200_ws *ws = wss[i];
+            if (state[i] == IDLE)
+            {
+                if (dry && busy) continue;             // ask again only after some node has been handed back
+                sb200_node_delta d{0, nullptr, nullptr, nullptr};
+                if (!next(user, i, &d))
+                {
+                    dry = true;
+                    continue;
+                }
+                if ((rc = apply_node_delta(ws, &d))) return rc;
+                res[i] = sb200_result{};
+                if ((rc = solve_begin(ws, params, &res[i]))) return rc;
+                if ((rc = solve_step(ws))) return rc;
+                state[i] = SOLVING;
+                ++busy;
+                progressed = true;
+            }
+            else if (state[i] == SOLVING)
+            {
+                const cudaError_t q = cudaEventQuery(ws->ev[3]);
+                if (q == cudaErrorNotReady) continue;
+                WS_TRY(q);
+                int fin = 0;
+                if ((rc = solve_poll(ws, &fin))) return rc;
+                if (!fin)
+                {
+                    if ((rc = solve_step(ws))) return rc;
+                }
+                else
+                {
+                    if ((rc = solve_finish(ws, &res[i]))) return rc;
+                    if ((rc = enqueue_node_heuristics(ws))) return rc;
+                    WS_TRY(cudaEventRecord(ws->ev[3], ws->stream));
+                    state[i] = HEUR;
+                }
+                progressed = true;
+            }
+            else
+            {
+                const cudaError_t q = cudaEventQuery(ws->ev[3]);
+                if (q == cudaErrorNotReady) continue;
+                WS_TRY(q);
+                done(user, i, &res[i], ws->heur_out_host);     // may add nodes to the caller's frontier
+                state[i] = IDLE;
+                --busy;
+                dry = false;
+                progressed = true;
+            }
+        }
+        if (busy == 0 && dry) break;
+        if (!progressed && busy) std::this_thread::yield();
     }
     return SB200_OK;
 }

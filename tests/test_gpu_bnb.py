@@ -161,3 +161,21 @@ def test_node_heuristics_kernel_reports_infeasible_fixings():
     ban = tuple((int(j), 0) for j in row0 if j < mdl.n_orig)       # every column of row 0 fixed to 0
     assert len(ban) <= 64
     _check_node_heuristics(mdl, [ban, ()], 100)
+
+
+@pytest.mark.parametrize("shape", [(30, 120, 0.1, 2), (40, 200, 0.08, 5)])
+def test_continuous_batching_reaches_the_milp_optimum(shape):
+    """sb200_solve_stream: slots take the next open node as soon as they are free; the search order then depends
+    on completion times, the optimum does not."""
+    m, n, dens, seed = shape
+    mdl = gen_scp(m, n, dens, seed)
+    opt = _milp_optimum(mdl)
+    drv = bnb.BatchedBnb(mdl, slots=4)
+    try:
+        st = drv.run(max_nodes=10 ** 6, stream_nodes=64)
+        assert st.open_nodes == 0, "search did not finish"
+        assert st.incumbent == opt, (st.incumbent, opt, st)
+        assert np.all(drv.heur.A @ drv.incumbent_x >= 1.0)
+        assert st.processed >= 1 and st.lp_iterations > 0 and st.kernels_launched > 0
+    finally:
+        drv.close()

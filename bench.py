@@ -63,12 +63,14 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.stop_evt = threading.Event()
+        self.ready = threading.Event()          # NVML is initialised (it takes driver locks: keep it out of the timed region)
         self.sm, self.maxsm, self.reasons = [], [], set()
 
     def run(self):
         """NVML in-process (no nvidia-smi process per sample: spawning it every 200 ms takes driver locks and
         slowed the host-side-heavy e2e steps several-fold); nvidia-smi only if NVML cannot be imported."""
         if os.environ.get("SB200_NO_SAMPLER"):
+            self.ready.set()
             return
         try:
             import pynvml as nv
@@ -80,6 +82,7 @@ class ClockSampler(threading.Thread):
                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             self.maxsm.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.ready.set()
             while not self.stop_evt.is_set():
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 r = int(get_reasons(h))
@@ -90,6 +93,7 @@ class ClockSampler(threading.Thread):
             return
         except Exception:
             pass
+        self.ready.set()
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -222,6 +226,7 @@ def run_bnb(args, rank, world, local_rank):
     drv.frontier.extend(mine)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(10)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -362,6 +367,7 @@ def run_ours(args, rank, world, local_rank):
         step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(10)
     barrier()
     t0 = time.perf_counter()
     results = [step(i) for i in range(args.steps)]

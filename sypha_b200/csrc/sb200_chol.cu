@@ -128,25 +128,9 @@ __device__ __forceinline__ unsigned long long df_now()
 #ifndef SB200_V_LJ
 #define SB200_V_LJ 0
 #endif
-#ifndef SB200_V_PUB
-#define SB200_V_PUB 0      // 1: released after the diagonal update, 2: by warp 1 inside the tile factorisation (both measured equal to 0)
-#endif
 #ifndef SB200_V_ST
 #define SB200_V_ST 1
 #endif
-
-// {value, epoch tag} pairs: one aligned 16-byte transaction, polled by the consumer itself (no flag, no
-// fence): 457 ns per hand-off against 978 ns for data + release flag + acquire fence (scripts/pingpong.cu)
-__device__ __forceinline__ void st_tagged(double2 *p, double v, double tag)
-{
-    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(tag) : "memory");
-}
-__device__ __forceinline__ double2 ld_tagged(const double2 *p)
-{
-    double2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-    return v;
-}
 
 // control block of one data-flow kernel family: [0] epoch, [1] next task, [2] exit count
 struct DfCtl
@@ -219,25 +203,6 @@ struct PotrfDf
     double *zTbuf;       // Z'
     int *z_flag;         // [T*T]: Z tile (i,j) final
 };
-// payload of a tagged D1: the six strictly-lower 16x16 blocks of L_jj, then its four 16x16 diagonal inverses
-static constexpr int D1_PAIRS = 6 * 256 + 4 * 256;
-__device__ __forceinline__ void d1_slot(int p, bool &is_l, int &r, int &c)
-{
-    const int q = p >> 8, e = p & 255;
-    is_l = q < 6;
-    if (is_l)
-    {
-        const int bi = q < 1 ? 1 : (q < 3 ? 2 : 3), bj = q - (bi == 1 ? 0 : (bi == 2 ? 1 : 3));
-        r = 16 * bi + (e >> 4);
-        c = 16 * bj + (e & 15);
-    }
-    else
-    {
-        const int b = q - 6;
-        r = 16 * b + (e >> 4);
-        c = 16 * b + (e & 15);
-    }
-}
 enum { TASK_TILE = 0, TASK_PAIR = 1, TASK_CHAIN = 2, TASK_G = 3, TASK_Z = 4 };
 #ifndef SB200_Z_MAX_T
 #define SB200_Z_MAX_T 20     // up to 1280 rows the factorisation also forms Z = L^-1 (see TASK_Z)
@@ -478,11 +443,56 @@ __device__ __forceinline__ void mma_tri(const double (*S)[STRIDE], int kdepth, c
 }
 
 // X = acc L_jj^-T for tile (ti, tj): block substitution with the 16x16 inverses of L_jj (each warp owns
-// 8 rows - no block barrier inside), result written to the matrix and left in Xs (stride XP).
-// Waits for D1(tj).  All threads must call; ends WITHOUT a barrier (publish() provides it).
+// 8 rows), result written to the matrix and left in Xs (stride XP).
+// TAGGED: the chain's hand-off - L_jj arrives one 16-column PANEL at a time (d1_emit_panel), while chain(tj)
+//   is still factoring the panels to the right; step b of the substitution runs as soon as panel b is here, so
+//   only the last step (and the last quarter of the diagonal update, `acc2`) follows the end of that factorisation.
+//   With `acc2` (the chain's diagonal-tile accumulator) the update acc2 -= X_b X_b' is applied panel by panel
+//   for b = 0..2 here; the caller applies panel 3 after publishing X.
+// !TAGGED: waits for the D1 flag of tile tj and reads L_jj and the inverses with plain loads.
+// All threads must call; ends WITHOUT a barrier (publish() provides it).
+__device__ __forceinline__ void trsm_step(double (*Xs)[XP], const double (*Lj)[XP], const double (*Wd)[16][17], int b, int R,
+                                          int g, int tg)
+{
+    double cc[2][2];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+    {
+        const double2 v = *reinterpret_cast<const double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]);
+        cc[nb][0] = v.x;
+        cc[nb][1] = v.y;
+    }
+    for (int kk = 0; kk < 16 * b; kk += 4)
+    {
+        const double a = -Xs[R + g][kk + tg];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+            dmma_8x8x4(cc[nb][0], cc[nb][1], a, Lj[16 * b + 8 * nb + g][kk + tg]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+        *reinterpret_cast<double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]) = make_double2(cc[nb][0], cc[nb][1]);
+    __syncwarp();
+    double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4)
+    {
+        const double a = Xs[R + g][16 * b + kk + tg];
+        if (kk < 8) dmma_8x8x4(o[0][0], o[0][1], a, Wd[b][g][kk + tg]);     // W lower: k <= n
+        dmma_8x8x4(o[1][0], o[1][1], a, Wd[b][8 + g][kk + tg]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+        *reinterpret_cast<double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]) = make_double2(o[nb][0], o[nb][1]);
+    __syncwarp();
+}
+
 template <bool TAGGED>
 __device__ __forceinline__ void trsm_tile(unsigned char *dyn_smem, const PotrfDf &P, const DfCtl &C, int epoch,
-                                          int ti, int tj, const double acc[4][2][2], int t_dbg = 8191)
+                                          int ti, int tj, const double acc[4][2][2], int t_dbg = 8191,
+                                          double (*acc2)[2] = nullptr, const TriMap *tm = nullptr)
 {
     double(*Xs)[XP] = reinterpret_cast<double(*)[XP]>(dyn_smem + SM_LS);
     double(*Lj)[XP] = reinterpret_cast<double(*)[XP]>(dyn_smem + SM_LI);
@@ -491,6 +501,7 @@ __device__ __forceinline__ void trsm_tile(unsigned char *dyn_smem, const PotrfDf
     const int row0 = (w >> 2) * 32, col0 = (w & 3) * 16, g = lane >> 2, tg = lane & 3;
     const int T = P.T, ld = P.ld;
     const size_t r0 = (size_t)ti * TB, c0 = (size_t)tj * TB;
+    const int R = 8 * w;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -498,136 +509,79 @@ __device__ __forceinline__ void trsm_tile(unsigned char *dyn_smem, const PotrfDf
             *reinterpret_cast<double2 *>(&Xs[row0 + i * 8 + g][col0 + j * 8 + tg * 2]) =
                 make_double2(acc[i][j][0], acc[i][j][1]);
     if (TAGGED)
-    {   // the chain's hand-off: poll the tagged payload of diagonal tile tj straight into shared memory
-        const double2 *src = P.d1tag + (size_t)tj * D1_PAIRS;
+    {
         const double tag = (double)epoch;
-        double2 v[D1_PAIRS / NT_TILE];
-        int spins = 0;
-        for (;;)
-        {
-            bool ok = true;
 #pragma unroll
-            for (int u = 0; u < D1_PAIRS / NT_TILE; ++u)
+        for (int b = 0; b < 4; ++b)
+        {   // poll panel b straight into shared memory
+            const double2 *src = P.d1tag + (size_t)tj * D1_PAIRS + d1_panel_off(b);
+            double2 v[4];
+            int spins = 0;
+            for (;;)
             {
-                v[u] = ld_tagged(src + tid + u * NT_TILE);
-                ok = ok && (v[u].y == tag);
-            }
-            if (ok) break;
-            if ((++spins & 255) == 0)
-            {
-                if (ld_volatile(C.err)) break;
-                if (spins > (1 << 20))
+                bool ok = true;
+#pragma unroll
+                for (int u = 0; u < 4 - b; ++u)
                 {
-                    atomicExch(C.err, 1);
-                    break;
+                    v[u] = ld_tagged(src + tid + u * NT_TILE);
+                    ok = ok && (v[u].y == tag);
+                }
+                if (ok) break;
+                if ((++spins & 255) == 0)
+                {
+                    if (ld_volatile(C.err)) break;
+                    if (spins > (1 << 20))
+                    {
+                        atomicExch(C.err, 1);
+                        break;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < D1_PAIRS / NT_TILE; ++u)
-        {
-            bool is_l;
-            int r, c;
-            d1_slot(tid + u * NT_TILE, is_l, r, c);
-            if (is_l)
-                Lj[r][c] = v[u].x;
-            else
-                Wd[r >> 4][r & 15][c & 15] = v[u].x;
+            for (int u = 0; u < 4 - b; ++u)
+            {
+                bool is_l;
+                int r, c;
+                d1_panel_slot(b, tid + u * NT_TILE, is_l, r, c);
+                if (is_l)
+                    Lj[r][c] = v[u].x;
+                else
+                    Wd[b][r & 15][c & 15] = v[u].x;
+            }
+            __syncthreads();                    // panel b staged (b = 0: also the accumulator tile in Xs)
+            if (b == 0) DFT(t_dbg, 8);
+            if (b == 3) DFT(t_dbg, 9);
+            trsm_step(Xs, Lj, Wd, b, R, g, tg);
+            if (acc2 && b < 3)
+            {   // diagonal update with the 16 columns just finished (every warp's rows are needed)
+                __syncthreads();
+                mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(&Xs[0][16 * b]), 16, *tm, lane, acc2);
+            }
         }
-        __syncthreads();
-        DFT(t_dbg, 8);
     }
     else
     {
-    if (tid == 0) spin_until(P.tile_flag + tj * T + tj, epoch, C.err);
-    __syncthreads();
-    DFT(t_dbg, 8);
-    const double *Ljj = P.A + c0 * ld + c0;
-    const double *Wj = P.linv + (size_t)tj * TB * TB;
-#if SB200_V_LJ
-    {   // issue every load first (one L2 round trip), then stage
-        double2 lv[8];
-        double wv[4];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
+        if (tid == 0) spin_until(P.tile_flag + tj * T + tj, epoch, C.err);
+        __syncthreads();
+        DFT(t_dbg, 8);
+        const double *Ljj = P.A + c0 * ld + c0;
+        const double *Wj = P.linv + (size_t)tj * TB * TB;
+        for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
         {
-            const int idx = tid + u * NT_TILE, r = idx >> 5, c2 = (idx & 31) * 2;
-            if (c2 <= r)      // the strictly-upper part of L_jj is never read
-                lv[u] = __ldcg(reinterpret_cast<const double2 *>(Ljj + (size_t)r * ld + c2));
+            const int r = idx >> 5, c2 = (idx & 31) * 2;
+            if (c2 <= r)      // the strictly-upper part of L_jj is never read (stale memory there)
+                *reinterpret_cast<double2 *>(&Lj[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(Ljj + (size_t)r * ld + c2));
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int idx = tid; idx < 4 * 16 * 16; idx += NT_TILE)
         {
-            const int idx = tid + u * NT_TILE, b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
-            wv[u] = __ldcg(Wj + (size_t)(16 * b + r) * TB + 16 * b + c);
+            const int b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+            Wd[b][r][c] = __ldcg(Wj + (size_t)(16 * b + r) * TB + 16 * b + c);
         }
+        __syncthreads();
+        DFT(t_dbg, 9);
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-        {
-            const int idx = tid + u * NT_TILE, r = idx >> 5, c2 = (idx & 31) * 2;
-            if (c2 <= r) *reinterpret_cast<double2 *>(&Lj[r][c2]) = lv[u];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-        {
-            const int idx = tid + u * NT_TILE, b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
-            Wd[b][r][c] = wv[u];
-        }
-    }
-    __syncthreads();
-#else
-    for (int idx = tid; idx < TB * TB / 2; idx += NT_TILE)
-    {
-        const int r = idx >> 5, c2 = (idx & 31) * 2;
-        if (c2 <= r)      // the strictly-upper part of L_jj is never read (stale memory there)
-            *reinterpret_cast<double2 *>(&Lj[r][c2]) = __ldcg(reinterpret_cast<const double2 *>(Ljj + (size_t)r * ld + c2));
-    }
-    for (int idx = tid; idx < 4 * 16 * 16; idx += NT_TILE)
-    {
-        const int b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
-        Wd[b][r][c] = __ldcg(Wj + (size_t)(16 * b + r) * TB + 16 * b + c);
-    }
-    __syncthreads();
-#endif
-    }
-    DFT(t_dbg, 9);
-    const int R = 8 * w;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-    {
-        double cc[2][2];
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-        {
-            const double2 v = *reinterpret_cast<const double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]);
-            cc[nb][0] = v.x;
-            cc[nb][1] = v.y;
-        }
-        for (int kk = 0; kk < 16 * b; kk += 4)
-        {
-            const double a = -Xs[R + g][kk + tg];
-#pragma unroll
-            for (int nb = 0; nb < 2; ++nb)
-                dmma_8x8x4(cc[nb][0], cc[nb][1], a, Lj[16 * b + 8 * nb + g][kk + tg]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-            *reinterpret_cast<double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]) = make_double2(cc[nb][0], cc[nb][1]);
-        __syncwarp();
-        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-        for (int kk = 0; kk < 16; kk += 4)
-        {
-            const double a = Xs[R + g][16 * b + kk + tg];
-            if (kk < 8) dmma_8x8x4(o[0][0], o[0][1], a, Wd[b][g][kk + tg]);     // W lower: k <= n
-            dmma_8x8x4(o[1][0], o[1][1], a, Wd[b][8 + g][kk + tg]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-            *reinterpret_cast<double2 *>(&Xs[R + g][16 * b + 8 * nb + 2 * tg]) = make_double2(o[nb][0], o[nb][1]);
-        __syncwarp();
+        for (int b = 0; b < 4; ++b)
+            trsm_step(Xs, Lj, Wd, b, R, g, tg);
     }
     // each warp writes its own 8 rows (coalesced 512 B rows)
     DFT(t_dbg, 10);
@@ -855,29 +809,14 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
             }
             __syncthreads();
             DFT(t, 1);
-#if SB200_V_PUB == 2
-            trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
-            __syncthreads();                                    // Xs complete, X stored
-            DFT(t, 4);
-            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), TB, tm, lane, acc2);
-            __syncthreads();
-            deferred = P.tile_flag + j * T + jm;                // released inside the factorisation (warp 1)
-#elif SB200_V_PUB
-            trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
-            __syncthreads();                                    // Xs complete
-            DFT(t, 4);
-            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), TB, tm, lane, acc2);
-            // tile (j, j-1) is published after the update and by a thread of warp 1: the release fence
-            // then overlaps the pivot chain (warp 0) instead of delaying it; its consumers have a whole
-            // tile factorisation of slack
-            publish(P.tile_flag + j * T + jm, epoch, 32);
-#else
-            trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t);
+            // substitution against L_(j-1)(j-1) panel by panel as chain(j-1) emits them, with the diagonal update of
+            // panels 0..2 inside; what follows the end of that factorisation is one substitution step and a quarter
+            // of the update
+            trsm_tile<true>(dyn_smem, P, C, epoch, j, jm, acc1, t, acc2, &tm);
             publish(P.tile_flag + j * T + jm, epoch);           // barrier inside: Xs complete
             DFT(t, 4);
-            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS), TB, tm, lane, acc2);
+            mma_tri<XP>(reinterpret_cast<const double(*)[XP]>(dyn_smem + SM_LS + 48 * sizeof(double)), 16, tm, lane, acc2);
             __syncthreads();
-#endif
             DFT(t, 5);
         }
         {   // ---- diagonal tile ----------------------------------------------------------------------
@@ -893,21 +832,10 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
                     Ls[tm.ro[sl] + g][tm.co[sl] + tg * 2 + 1] = acc2[sl][1];
                 }
             __syncthreads();
-            const int fail = potrf_tile64_factor(dyn_smem, tid, deferred, epoch);
+            // chain(j+1) is polling for this tile's panels already: they leave from inside the factorisation
+            const int fail = potrf_tile64_factor(dyn_smem, tid, deferred, epoch,
+                                                 j + 1 < T ? P.d1tag + (size_t)j * D1_PAIRS : nullptr, (double)epoch);
             DFT(t, 6);
-            if (j + 1 < T)
-            {   // what chain(j+1) needs, as tagged pairs: it is polling for them already
-                double2 *dst = P.d1tag + (size_t)j * D1_PAIRS;
-                const double tag = (double)epoch;
-#pragma unroll
-                for (int u = 0; u < D1_PAIRS / NT_TILE; ++u)
-                {
-                    bool is_l;
-                    int r, c;
-                    d1_slot(tid + u * NT_TILE, is_l, r, c);
-                    st_tagged(dst + tid + u * NT_TILE, is_l ? Ls[r][c] : Li[r][c], tag);
-                }
-            }
             DFT(t, 7);
             double *Atile = P.A + c0 * ld + c0;
             double *linv_j = P.linv + (size_t)j * TB * TB;

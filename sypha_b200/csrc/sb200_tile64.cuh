@@ -115,6 +115,44 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// {value, epoch tag} pairs: one aligned 16-byte transaction, polled by the consumer itself (no flag, no
+// fence): 457 ns per hand-off against 978 ns for data + release flag + acquire fence (scripts/pingpong.cu)
+__device__ __forceinline__ void st_tagged(double2 *p, double v, double tag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(tag) : "memory");
+}
+__device__ __forceinline__ double2 ld_tagged(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// What the next chain task needs of a factored diagonal tile travels as tagged pairs, one PANEL (16 columns) at
+// a time, as soon as the panel is final: panel b = the 16x16 blocks (b+1..3, b) of L_jj, then W_b = L_bb^-1.
+// The consumer substitutes against panel b while the producer is still factoring panels b+1..3.
+static constexpr int D1_PAIRS = 6 * 256 + 4 * 256;
+__device__ __forceinline__ int d1_panel_off(int b) { return b == 0 ? 0 : (b == 1 ? 1024 : (b == 2 ? 1792 : 2304)); }
+__device__ __forceinline__ void d1_panel_slot(int b, int q, bool &is_l, int &r, int &c)
+{
+    const int blk = q >> 8, e = q & 255;
+    is_l = blk < 3 - b;
+    r = (is_l ? 16 * (b + 1 + blk) : 16 * b) + (e >> 4);
+    c = 16 * b + (e & 15);
+}
+__device__ __forceinline__ void d1_emit_panel(double2 *dst, double tag, int b, const double (*Ls)[LP], const double (*Li)[LP],
+                                              int t, int nthreads)
+{
+    double2 *out = dst + d1_panel_off(b);
+    for (int q = t; q < (4 - b) * 256; q += nthreads)
+    {
+        bool is_l;
+        int r, c;
+        d1_panel_slot(b, q, is_l, r, c);
+        st_tagged(out + q, is_l ? Ls[r][c] : Li[r][c], tag);
+    }
+}
+
 #ifndef SB200_V_LOOKAHEAD
 #define SB200_V_LOOKAHEAD 1  // the pivot-chain warp also applies a finished 16-column panel to the NEXT 16x16 diagonal
                              // block (all its next chain needs); the other seven warps apply it to the rest of the
@@ -193,7 +231,10 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
 // element still receives its panel updates in panel order with the same DMMA sequences as the phased form.
 //   barriers per step: named 1 (warps 1..7, between R and T), named 2 (warps 1..7 arrive after T, warp 0 waits
 //   before N), block barrier at the end of the step (W_k, L[k+1][k] visible to warps 1..7).
-__device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_flag = nullptr, int deferred_value = 0)
+// `d1dst` (may be null): warps 1..7 send panel k-1 of the tagged hand-off (d1_emit_panel) in step k, once their
+// share of the step is done - the next chain task substitutes against it while this tile is still being factored.
+__device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_flag = nullptr, int deferred_value = 0,
+                                   double2 *d1dst = nullptr, double d1tag = 0.0)
 {
     TT(0);
     double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
@@ -368,9 +409,11 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
                 __threadfence_block();
                 named_bar_arrive(2, NT_TILE);
             }
+            if (d1dst && k >= 1) d1_emit_panel(d1dst, d1tag, k - 1, Ls, Li, tid - 32, NT_TILE - 32);
         }
         __syncthreads();
     }
+    if (d1dst) d1_emit_panel(d1dst, d1tag, 3, Ls, Li, tid, NT_TILE);
     TT(1);
     return *sflag;
 }
@@ -378,7 +421,8 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
 // `deferred_flag`: a publish the caller still owes (its data was stored and a block barrier has passed): a
 // thread of warp 1 releases it while warp 0 runs the first pivot chain, so the release fence (~1 us) is
 // hidden instead of delaying the caller's critical path.
-__device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_flag = nullptr, int deferred_value = 0)
+__device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_flag = nullptr, int deferred_value = 0,
+                                   double2 *d1dst = nullptr, double d1tag = 0.0)
 {
     TT(0);
     double(*Ls)[LP] = reinterpret_cast<double(*)[LP]>(smem + SM_LS);
@@ -571,6 +615,8 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
     }
 #endif
     __syncthreads();
+    if (d1dst)
+        for (int b = 0; b < 4; ++b) d1_emit_panel(d1dst, d1tag, b, Ls, Li, tid, NT_TILE);
     TT(1);
     return *sflag;
 }

@@ -215,15 +215,17 @@ def run_bnb(args, rank, world, local_rank):
         return bnb_exchange.rebalance_frontier(nodes, max_depth=64, min_imbalance=args.slots // 2)
 
     drv = bnb.BatchedBnb(mdl, slots=args.slots, device=local_rank, exchange=exchange,
-                         device_heuristics=not args.host_heuristics,
+                         device_heuristics=not args.host_heuristics, share_gpu=not args.no_share,
                          rebalance=rebalance if (dist is not None and not args.no_donation) else None, rebalance_every=4)
     # every rank expands the same first levels (deterministic), then keeps its round-robin share
     while len(drv.frontier) < world * args.slots and drv.frontier:
         drv.round()
-    warm_nodes = drv.stats.processed
     mine = bnb_exchange.partition_round_robin(list(drv.frontier), rank, world)
     drv.frontier.clear()
     drv.frontier.extend(mine)
+    for _ in range(args.warmup):                   # untimed full windows: every slot has solved a node before t0
+        drv.round()
+    warm_nodes = drv.stats.processed
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.ready.wait(10)
@@ -255,7 +257,7 @@ def run_bnb(args, rank, world, local_rank):
     if rank == 0:
         out = {
             "metric": "bnb_nodes_per_sec", "value": nodes / elapsed, "unit": "nodes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warm_nodes, "ms_per_step": 1e3 * elapsed / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "warmup_nodes": warm_nodes, "ms_per_step": 1e3 * elapsed / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "branch-and-bound on an scpnre-shaped synthetic SCP 500x5000, 10% density "
                                    "(configs[4]); a step = one round of K batched node LPs per GPU",
@@ -599,6 +601,7 @@ def main():
                     help="bnb: branching rule and rounding/repair heuristic on the host (NumPy) instead of the device kernel")
     ap.add_argument("--stream-factor", type=int, default=0,
                     help="bnb: > 0 = continuous batching (sb200_solve_stream), a step starts F x slots nodes; 0 = windows of K nodes")
+    ap.add_argument("--no-share", action="store_true", help="bnb: keep the single-LP launch geometry (one CTA per task) in every slot")
     ap.add_argument("--no-donation", action="store_true", help="bnb, N > 1: keep the initial round-robin split (no node donation)")
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--poll-every", type=int, default=1)

@@ -176,6 +176,12 @@ int sb200_node_heuristics(sb200_ws **ws, int k, sb200_heur_result *out);
 /* the cover of the last sb200_node_heuristics on this workspace: n_orig bytes of 0/1 */
 int sb200_get_cover(sb200_ws *ws, unsigned char *x_host);
 
+/* Throughput hint for workspaces that solve LPs CONCURRENTLY (B&B slots): the data-flow factorisation then
+ * launches about (2 x SMs) / concurrent_lps CTAs instead of one per task - a CTA that waits for a dependency
+ * holds its SM slot, which is free latency hiding for one LP and lost throughput for sixteen.  0 or 1 restores
+ * the single-LP geometry.  Cached iteration graphs are dropped. */
+int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps);
+
 /* Continuous batching of B&B node LPs over k workspaces that hold the same base model: whenever a slot is
  * free `next(user, slot, &delta)` is asked for a node (return 1 with the decision list filled in - the arrays
  * are copied before `next` returns control a second time - or 0 if there is none right now); the node's LP is

@@ -90,9 +90,9 @@ int main(int argc, char **argv)
         printf("# last tile factorisation (cycles): total %lld\n", tt[1] - tt[0]);
 #if SB200_V_LOOKAHEAD
         for (int kb = 0; kb < 4; kb++)
-            printf("   step %d (cycles from step start): warps 1-7 done %lld  P done %lld  N done %lld  step end %lld\n", kb,
-                   tt[9 + 4 * kb] - tt[8 + 4 * kb], tt[10 + 4 * kb] - tt[8 + 4 * kb], kb < 3 ? tt[11 + 4 * kb] - tt[8 + 4 * kb] : 0ll,
-                   (kb < 3 ? tt[12 + 4 * kb] : tt[1]) - tt[8 + 4 * kb]);
+            printf("   step %d (cycles from step start): warps 1-7 done %lld  emitted %lld  P done %lld  N done %lld  step end %lld\n", kb,
+                   tt[9 + 4 * kb] - tt[8 + 4 * kb], tt[24 + kb] - tt[8 + 4 * kb], tt[10 + 4 * kb] - tt[8 + 4 * kb],
+                   kb < 3 ? tt[11 + 4 * kb] - tt[8 + 4 * kb] : 0ll, (kb < 3 ? tt[12 + 4 * kb] : tt[1]) - tt[8 + 4 * kb]);
 #else
         for (int kb = 0; kb < 4; kb++)
             printf("   panel %d: diag16 %lld  rows-below %lld  trailing %lld\n", kb, tt[9 + 4 * kb] - tt[8 + 4 * kb],

@@ -136,7 +136,8 @@ class BatchedBnb:
 
     def __init__(self, base: ScpModel, slots: int = 8, device: int = 0, max_iter: int = 100,
                  exchange=None, integer_costs: bool = True, device_nodes: bool = True, max_depth: int = 64,
-                 heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1):
+                 heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1,
+                 share_gpu: bool = True):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
@@ -159,6 +160,10 @@ class BatchedBnb:
                 w = IpmWorkspace()
                 initializeIpmWorkspace(w, device=device)
                 self.ws.append(w)
+        if share_gpu and slots > 1:              # K LPs in flight: fewer CTAs per factorisation (throughput over latency)
+            from . import _lib as L
+            for w in self.ws:
+                L.load().sb200_set_concurrency_hint(w.handle, slots)
         self.heur = CoverHeuristic(base)
         self.frontier: collections.deque = collections.deque([BnbNode((), -math.inf)])
         self.incumbent = math.inf

@@ -1108,6 +1108,25 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
     return SB200_OK;
 }
 
+int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps)
+{
+    if (!ws || concurrent_lps < 0) return SB200_ERR_INVALID;
+    int limit = 0;
+    if (concurrent_lps > 1)
+    {
+        const int slots = 2 * (ws->chol.sms > 0 ? ws->chol.sms : 148);
+        limit = std::max(4, slots / concurrent_lps);
+    }
+    if (limit != ws->chol.grid_limit)
+    {
+        WS_TRY(cudaSetDevice(ws->device));
+        WS_TRY(cudaStreamSynchronize(ws->stream));
+        drop_graphs(ws);                       // the launch geometry is part of the captured iteration
+        ws->chol.grid_limit = limit;
+    }
+    return SB200_OK;
+}
+
 int sb200_get_cover(sb200_ws *ws, unsigned char *x_host)
 {
     if (!ws || !ws->loaded || !x_host || !ws->heur_cover) return SB200_ERR_INVALID;

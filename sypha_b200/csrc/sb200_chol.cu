@@ -831,6 +831,9 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
                     Ls[tm.ro[sl] + g][tm.co[sl] + tg * 2] = acc2[sl][0];
                     Ls[tm.ro[sl] + g][tm.co[sl] + tg * 2 + 1] = acc2[sl][1];
                 }
+#if defined(SB200_TILE_TIMING) && defined(SB200_TT_TILE)
+            if (tid == 0) g_tt_on = (j == SB200_TT_TILE);
+#endif
             __syncthreads();
             // chain(j+1) is polling for this tile's panels already: they leave from inside the factorisation
             const int fail = potrf_tile64_factor(dyn_smem, tid, deferred, epoch,
@@ -1221,6 +1224,9 @@ int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve)
         int occ = 0;
         SB200_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_potrf_df, NT_TILE, SM_TOTAL));
         W.potrf_occ = occ < 1 ? 1 : occ;
+#ifdef SB200_POTRF_OCC
+        W.potrf_occ = SB200_POTRF_OCC;      // A/B: CTAs per SM the data-flow factorisation may use
+#endif
     }
     if (T_now != W.tasks_T) return build_task_list(err, W, T_now);
     return SB200_OK;
@@ -1256,7 +1262,10 @@ void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t
     PotrfDf P{a, ld, T, W.linv, W.linv128, W.tasks, W.ntasks, flags, flags + tc * tc, flags + tc * tc + tc, info, W.d1tag, W.gbuf, W.gbufT,
               use_z ? W.zbuf : nullptr, use_z ? W.zTbuf : nullptr, flags + tc * tc + tc + 3 * ((tc + 1) / 2)};
     DfCtl C{ctl + 0, reinterpret_cast<unsigned *>(ctl + 1), reinterpret_cast<unsigned *>(ctl + 2), ctl + 8};
-    const int cap = W.sms * W.potrf_occ;
+    // with the Z tasks in the list (T <= SB200_Z_MAX_T) one CTA per SM is faster than two: a chain task that shares
+    // its SM loses issue slots, DMMA cycles and instruction cache to its neighbour (m = 1000: 270 -> 248 us)
+    int cap = W.sms * (use_z ? 1 : W.potrf_occ);
+    if (W.grid_limit > 0 && W.grid_limit < cap) cap = W.grid_limit;
     const int grid = W.ntasks < cap ? W.ntasks : cap;
     k_potrf_df<<<grid, NT_TILE, SM_TOTAL, st>>>(P, C);
     ++g_launch_count;

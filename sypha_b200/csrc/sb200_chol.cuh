@@ -27,6 +27,8 @@ struct CholWork
     int t_cap = 0;
     int sms = 148, potrf_occ = 1;
     int max_coop_grid = 148;
+    int grid_limit = 0;         // > 0: CTAs the data-flow kernels may launch (B&B: K LPs share the GPU, and a CTA
+                                // that waits for a dependency holds its SM slot; see sb200_set_concurrency_hint)
 };
 
 int chol_work_ensure(ErrorSink &err, CholWork &W, int n_pad, int n_pad_reserve = 0);

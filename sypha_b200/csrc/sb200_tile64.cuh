@@ -37,8 +37,9 @@ static constexpr int NT_TILE = 256;                               // threads of 
 // stamped by thread 32 (warp 1): a stamp inside warp 0 leaves the pivot-chain warp diverged and makes
 // every shuffle take its slow path (measured: 19.6k instead of 3.6k cycles per 16x16 block)
 __device__ long long g_tile_timing[64];
-#define TT(i) do { if (tid == 32) g_tile_timing[i] = clock64(); } while (0)
-#define TT0(i) do { g_tile_timing[i] = clock64(); } while (0)      // whole warp 0, converged
+__device__ int g_tt_on = 1;          // the chain task switches the stamps on for the tile it wants timed
+#define TT(i) do { if (tid == 32 && g_tt_on) g_tile_timing[i] = clock64(); } while (0)
+#define TT0(i) do { if (g_tt_on) g_tile_timing[i] = clock64(); } while (0)      // whole warp 0, converged
 #else
 #define TT(i) do { } while (0)
 #define TT0(i) do { } while (0)
@@ -171,7 +172,15 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count)
 // The 16x16 diagonal block at c0 of Ls factored by ONE warp (see potrf_tile64_factor below): lanes 0..15 hold
 // the rows, lanes 16..31 the columns of the identity (-> W = L_dd^-1 in Li).  Returns the 1-based tile-local
 // index of the first non-positive pivot, or 0.
+#ifndef SB200_V_P_NOINLINE
+#define SB200_V_P_NOINLINE 1   // one copy of the 16-column chain in the kernel: inlined, the compiler peels the panel loop
+                               // and the second copy is a second set of cold instruction-cache lines per tile
+#endif
+#if SB200_V_P_NOINLINE
+__device__ __noinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)[LP], double *Tb, int c0, int lane)
+#else
 __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)[LP], double *Tb, int c0, int lane)
+#endif
 {
     const int r = lane & 15;
     const bool inv_lane = lane >= 16;
@@ -410,6 +419,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
                 named_bar_arrive(2, NT_TILE);
             }
             if (d1dst && k >= 1) d1_emit_panel(d1dst, d1tag, k - 1, Ls, Li, tid - 32, NT_TILE - 32);
+            TT(24 + k);
         }
         __syncthreads();
     }

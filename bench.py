@@ -490,7 +490,8 @@ def run_ours(args, rank, world, local_rank):
                                             "has no FP64 entry; nominal 40 TFLOP/s)",
                              "hbm_gbs": ph["gbs"], "hbm_frac": ph["frac_hbm"],
                              "note": "latency-bound at m = 1000: 16 dependent 64-column steps (pivot chain + one "
-                                     "hand-off each); see profiles/ for the per-step timeline"})
+                                     "hand-off each); see profiles/ for the per-step timeline. For m <= 1280 the same launch "
+                                     "also forms Z = L^-1 for the solves (another m^3/3 flops, NOT counted in `flops`)"})
             tr = read_traffic().get(dom)
             if tr is not None:
                 roof["traffic"] = tr

@@ -230,7 +230,10 @@ void launch_affine_mu(const IpmVecs &V, cudaStream_t st)
 // are ONE single-CTA kernel - no partials, no last-block ticket, one launch instead of two.  Not beyond a
 // few thousand columns: one SM pulls ~126 GB/s from L2, and at n = 11000 the single-CTA pair measured
 // 19.1 us against 6.4 + 4.3 us for the multi-CTA kernels.
-static constexpr int kSingleCtaMax = 4096;
+#ifndef SB200_SINGLE_CTA_MAX
+#define SB200_SINGLE_CTA_MAX 4096
+#endif
+static constexpr int kSingleCtaMax = SB200_SINGLE_CTA_MAX;
 static constexpr int kSingleCtaThreads = 1024;
 __global__ void __launch_bounds__(kSingleCtaThreads) k_affine_corrector(IpmVecs V)
 {

@@ -179,3 +179,26 @@ def test_continuous_batching_reaches_the_milp_optimum(shape):
         assert st.processed >= 1 and st.lp_iterations > 0 and st.kernels_launched > 0
     finally:
         drv.close()
+
+
+def test_concurrency_hint_changes_the_launch_geometry_not_the_result():
+    """sb200_set_concurrency_hint caps the CTAs of the data-flow factorisation (B&B slots share the GPU): the
+    arithmetic is the same, so the LP must come out bit-identical."""
+    import sypha_b200 as sb
+    from sypha_b200 import _lib as L, solver as S
+    mdl = gen_scp(300, 2500, 0.04, 21)
+    env = sb.SyphaEnvironment()
+    cfg = sb.SolverExecutionConfig(maxIterations=100)
+    base = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+    ws = S.workspace_for_nodes(base, 8)
+    try:
+        out = []
+        for hint in (0, 32, 0):
+            assert L.load().sb200_set_concurrency_hint(ws.handle, hint) == L.SB200_OK
+            r = S.solve_batch_nodes(base, [((3, 1), (40, 0))], cfg, [ws])[0]
+            out.append((r.iterations, r.primalObj, r.dualObj, r.primalSolution.copy()))
+        for o in out[1:]:
+            assert o[0] == out[0][0] and o[1] == out[0][1] and o[2] == out[0][2]
+            assert np.array_equal(o[3], out[0][3])
+    finally:
+        sb.releaseIpmWorkspace(ws)

@@ -141,6 +141,22 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz,
                      const int *csr_offs, const int *csr_inds, const double *csr_vals,
                      const double *c, const double *b, int ptrs_on_device, int strategy_hint);
 
+/* Host side of the model: an OR-Library set-covering text file read straight into the standard form
+ * A = [A0 | -I] (surplus entry last in its row), b = 1, c = [c0; 0] - what
+ * model_reader_read_scp_file_sparse_csr builds (src/model_reader.cpp:90-174), in one pass over the file.  The
+ * arrays are owned by the library until sb200_free_scp; they are what sb200_load_model takes. */
+typedef struct sb200_scp_model {
+    int m, n, n_orig;
+    long long nnz;
+    int *csr_offs;       /* [m + 1] */
+    int *csr_inds;       /* [nnz] */
+    double *csr_vals;    /* [nnz] */
+    double *c;           /* [n] */
+    double *b;           /* [m] */
+} sb200_scp_model;
+int sb200_read_scp(const char *path, sb200_scp_model *out);
+void sb200_free_scp(sb200_scp_model *mdl);
+
 /* ---- solve ---------------------------------------------------------------------------------- */
 int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result);
 /* Turn the resident BASE model into the model of one B&B node (base + appended branch rows,

@@ -54,6 +54,12 @@ class sb200_heur_result(C.Structure):
                 ("cover_obj", C.c_double), ("branch_frac", C.c_double), ("rounded_obj", C.c_double)]
 
 
+class sb200_scp_model(C.Structure):
+    _fields_ = [("m", C.c_int), ("n", C.c_int), ("n_orig", C.c_int), ("nnz", C.c_longlong),
+                ("csr_offs", C.POINTER(C.c_int)), ("csr_inds", C.POINTER(C.c_int)), ("csr_vals", C.POINTER(C.c_double)),
+                ("c", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double))]
+
+
 NEXT_NODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(sb200_node_delta))
 NODE_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(sb200_result), C.POINTER(sb200_heur_result))
 
@@ -67,6 +73,8 @@ SYMBOLS = {
     "sb200_ws_destroy": (_i, [_vp]),
     "sb200_last_error": (C.c_char_p, [_vp]),
     "sb200_default_params": (None, [C.POINTER(sb200_params)]),
+    "sb200_read_scp": (_i, [C.c_char_p, C.POINTER(sb200_scp_model)]),
+    "sb200_free_scp": (None, [C.POINTER(sb200_scp_model)]),
     "sb200_load_model": (_i, [_vp, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "sb200_solve": (_i, [_vp, C.POINTER(sb200_params), C.POINTER(sb200_result)]),
     "sb200_set_node_delta": (_i, [_vp, C.POINTER(sb200_node_delta)]),

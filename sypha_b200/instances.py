@@ -42,6 +42,28 @@ def _standard_form(m, n, row_cols, row_cnt, costs, name):
     return ScpModel(m, n + m, n, offs.astype(np.int32), inds, vals, c, np.ones(m), name)
 
 
+def read_scp_native(path) -> ScpModel:
+    """The library's reader (``sb200_read_scp``, csrc/sb200_io.cu): one pass over the file, arrays written at
+    their final size.  Same result as ``read_scp`` below."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load()
+    mdl = L.sb200_scp_model()
+    rc = lib.sb200_read_scp(str(path).encode(), C.byref(mdl))
+    if rc != L.SB200_OK:
+        raise ValueError(f"sb200_read_scp({path}) failed with code {rc}")
+    try:
+        out = ScpModel(mdl.m, mdl.n, mdl.n_orig,
+                       np.ctypeslib.as_array(mdl.csr_offs, (mdl.m + 1,)).copy(),
+                       np.ctypeslib.as_array(mdl.csr_inds, (mdl.nnz,)).copy(),
+                       np.ctypeslib.as_array(mdl.csr_vals, (mdl.nnz,)).copy(),
+                       np.ctypeslib.as_array(mdl.c, (mdl.n,)).copy(),
+                       np.ctypeslib.as_array(mdl.b, (mdl.m,)).copy(), str(path))
+    finally:
+        lib.sb200_free_scp(C.byref(mdl))
+    return out
+
+
 def read_scp(path) -> ScpModel:
     tok = np.array(open(path).read().split(), dtype=np.int64)
     m, n = int(tok[0]), int(tok[1])

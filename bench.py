@@ -215,7 +215,7 @@ def run_bnb(args, rank, world, local_rank):
         return bnb_exchange.rebalance_frontier(nodes, max_depth=64, min_imbalance=args.slots // 2)
 
     drv = bnb.BatchedBnb(mdl, slots=args.slots, device=local_rank, exchange=exchange,
-                         device_heuristics=not args.host_heuristics, share_gpu=not args.no_share,
+                         device_heuristics=not args.host_heuristics, share_gpu=not args.no_share, poll_every=args.poll_every,
                          rebalance=rebalance if (dist is not None and not args.no_donation) else None, rebalance_every=4)
     # every rank expands the same first levels (deterministic), then keeps its round-robin share
     while len(drv.frontier) < world * args.slots and drv.frontier:
@@ -261,7 +261,7 @@ def run_bnb(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "branch-and-bound on an scpnre-shaped synthetic SCP 500x5000, 10% density "
                                    "(configs[4]); a step = one round of K batched node LPs per GPU",
-                       "slots_per_gpu": args.slots,
+                       "slots_per_gpu": args.slots, "poll_every": args.poll_every,
                        "batching": (f"continuous (sb200_solve_stream), {args.stream_factor} x slots nodes per step"
                                     if args.stream_factor > 0 else "windows of K nodes (sb200_solve_batch)"),
                        "node_heuristics": "host NumPy" if args.host_heuristics else "device kernel (sb200_node_heuristics)", "node_lp": "Mehrotra IPM to mu <= 1e-4, max_iter 100",

@@ -137,14 +137,16 @@ class BatchedBnb:
     def __init__(self, base: ScpModel, slots: int = 8, device: int = 0, max_iter: int = 100,
                  exchange=None, integer_costs: bool = True, device_nodes: bool = True, max_depth: int = 64,
                  heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1,
-                 share_gpu: bool = True):
+                 share_gpu: bool = True, poll_every: int = 1):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
         # branching variable + rounding/repair incumbent per node on the device, behind the node's LP on its own
         # stream (sb200_node_heuristics); False: the host-side NumPy versions on a host copy of x
         self.device_heuristics = device_heuristics and device_nodes
-        self.env = SyphaEnvironment(cudaDeviceId=device)
+        # poll_every > 1: the host enqueues that many iterations per LP before it reads the scalar block back
+        # (kernels of an LP that has finished return at once), halving the host work per iteration of a window
+        self.env = SyphaEnvironment(cudaDeviceId=device, pollEvery=max(1, poll_every))
         # The reference runs node LPs with a gap-stagnation early exit (bnb_driver.cpp:835-837) and prunes with
         # whatever dual objective the LP stopped at - not a bound before convergence (53.08 vs the
         # LP optimum 48.12 on scpnrh1).  Here node LPs run to mu <= mu_tol and only converged LPs bound.

@@ -949,6 +949,19 @@ int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result)
     return solve_finish(ws, result);
 }
 
+// an error in one slot must not leave the other slots of a batch marked "solve in flight"
+static int abort_batch(sb200_ws **wss, int k, int rc)
+{
+    for (int i = 0; i < k; ++i)
+        if (wss[i] && wss[i]->active)
+        {
+            cudaSetDevice(wss[i]->device);
+            cudaStreamSynchronize(wss[i]->stream);
+            wss[i]->active = false;
+        }
+    return rc;
+}
+
 int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, const sb200_params *params,
                       sb200_result *results)
 {
@@ -959,25 +972,25 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     int rc, remaining = 0;
     if (deltas)
         for (int i = 0; i < k; ++i)
-            if ((rc = apply_node_delta(wss[i], &deltas[i]))) return rc;
+            if ((rc = apply_node_delta(wss[i], &deltas[i]))) return abort_batch(wss, k, rc);
     for (int i = 0; i < k; ++i)
     {
-        if ((rc = solve_begin(wss[i], params, &results[i]))) return rc;
+        if ((rc = solve_begin(wss[i], params, &results[i]))) return abort_batch(wss, k, rc);
         live[i] = 1;
         ++remaining;
     }
     while (remaining)
     {
         for (int i = 0; i < k; ++i)
-            if (live[i] && (rc = solve_step(wss[i]))) return rc;
+            if (live[i] && (rc = solve_step(wss[i]))) return abort_batch(wss, k, rc);
         for (int i = 0; i < k; ++i)
             if (live[i])
             {
                 int fin = 0;
-                if ((rc = solve_poll(wss[i], &fin))) return rc;
+                if ((rc = solve_poll(wss[i], &fin))) return abort_batch(wss, k, rc);
                 if (fin)
                 {
-                    if ((rc = solve_finish(wss[i], &results[i]))) return rc;
+                    if ((rc = solve_finish(wss[i], &results[i]))) return abort_batch(wss, k, rc);
                     live[i] = 0;
                     --remaining;
                 }
@@ -1062,10 +1075,10 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
                     dry = true;
                     continue;
                 }
-                if ((rc = apply_node_delta(ws, &d))) return rc;
+                if ((rc = apply_node_delta(ws, &d))) return abort_batch(wss, k, rc);
                 res[i] = sb200_result{};
-                if ((rc = solve_begin(ws, params, &res[i]))) return rc;
-                if ((rc = solve_step(ws))) return rc;
+                if ((rc = solve_begin(ws, params, &res[i]))) return abort_batch(wss, k, rc);
+                if ((rc = solve_step(ws))) return abort_batch(wss, k, rc);
                 state[i] = SOLVING;
                 ++busy;
                 progressed = true;
@@ -1076,15 +1089,15 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
                 if (q == cudaErrorNotReady) continue;
                 WS_TRY(q);
                 int fin = 0;
-                if ((rc = solve_poll(ws, &fin))) return rc;
+                if ((rc = solve_poll(ws, &fin))) return abort_batch(wss, k, rc);
                 if (!fin)
                 {
-                    if ((rc = solve_step(ws))) return rc;
+                    if ((rc = solve_step(ws))) return abort_batch(wss, k, rc);
                 }
                 else
                 {
-                    if ((rc = solve_finish(ws, &res[i]))) return rc;
-                    if ((rc = enqueue_node_heuristics(ws))) return rc;
+                    if ((rc = solve_finish(ws, &res[i]))) return abort_batch(wss, k, rc);
+                    if ((rc = enqueue_node_heuristics(ws))) return abort_batch(wss, k, rc);
                     WS_TRY(cudaEventRecord(ws->ev[3], ws->stream));
                     state[i] = HEUR;
                 }

@@ -15,6 +15,7 @@
 //   products) per term + 4 B per entry pointer + 8 B per written entry.
 // Dense path: FP64 tensor-core SYRK C = A diag(d) A' on a dense copy of A (64x64 tiles, DMMA).
 #include "sb200_kernels.cuh"
+#include <algorithm>
 #include "sb200_dmma.cuh"
 
 #include <cub/cub.cuh>
@@ -471,7 +472,11 @@ k_assemble_normal16_smem(long long n_pairs, int m_rows, const unsigned int *__re
 void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, int ld, cudaStream_t st)
 {
     const int grid = grid_for(P.n_pairs, 256, 148 * 64);
-    if (P.term16 && P.pad_id >= 0 && (size_t)(P.pad_id + 1) * 8 <= 200 * 1024 && P.n_pairs >= 148ll * ASM_SMEM_THREADS)
+#ifndef SB200_ASM_SMEM_MIN_CTAS
+#define SB200_ASM_SMEM_MIN_CTAS 32     // entries for at least this many CTAs of 1024 threads: below, staging d per CTA costs more than it saves
+#endif
+    if (P.term16 && P.pad_id >= 0 && (size_t)(P.pad_id + 1) * 8 <= 200 * 1024 &&
+        P.n_pairs >= (long long)SB200_ASM_SMEM_MIN_CTAS * ASM_SMEM_THREADS)
     {
         static bool attr_set = false;
         if (!attr_set)
@@ -480,7 +485,9 @@ void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, 
             attr_set = true;
         }
         const int nd = P.pad_id + 1;
-        k_assemble_normal16_smem<<<148, ASM_SMEM_THREADS, sizeof(double) * (size_t)nd, st>>>(
+        // one entry per thread and trip at least: m = 500 (scpnre / scpnrf, B&B nodes) fills 123 CTAs, m >= 550 all 148
+        const int ctas = (int)std::min<long long>(148, (P.n_pairs + ASM_SMEM_THREADS - 1) / ASM_SMEM_THREADS);
+        k_assemble_normal16_smem<<<ctas, ASM_SMEM_THREADS, sizeof(double) * (size_t)nd, st>>>(
             P.n_pairs, P.m, P.chunk_ptr, reinterpret_cast<const uint4 *>(P.term16), d, nd, M, ld);
         ++g_launch_count;
         return;

@@ -261,6 +261,9 @@ __device__ __noinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)[LP
     return bad;
 }
 #else
+#ifndef SB200_V_SHFL_NEXT
+#define SB200_V_SHFL_NEXT 0   // 1 measured no faster (3550-3900 against 3450-3600 cycles per panel in situ): off
+#endif
 #ifndef SB200_V_P_NOINLINE
 #define SB200_V_P_NOINLINE 1   // one copy of the 16-column chain in the kernel: inlined, the compiler peels the panel loop
                                // and the second copy is a second set of cold instruction-cache lines per tile
@@ -297,10 +300,16 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
         {
             d = __shfl_sync(0xffffffffu, dg, c + 1);
             inv = SB200_RSQ(d);
+#if SB200_V_SHFL_NEXT
+            // the entry the NEXT column scales first, a[c+1], gets L[c+1][c] by shuffle (26 cycles) instead of through
+            // the shared-memory column buffer (store -> syncwarp -> load: 70 cycles alone, more beside the other
+            // warps' fragment loads), so that path never overtakes the rsqrt chain
+            a[c + 1] -= l * __shfl_sync(0xffffffffu, l, c + 1);
+#endif
         }
         __syncwarp();
 #pragma unroll
-        for (int c2 = c + 1; c2 < 16; ++c2)
+        for (int c2 = c + 1 + SB200_V_SHFL_NEXT; c2 < 16; ++c2)
             a[c2] -= l * Cb[c][c2];
     }
     if (!inv_lane)

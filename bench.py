@@ -605,7 +605,9 @@ def main():
     ap.add_argument("--no-share", action="store_true", help="bnb: keep the single-LP launch geometry (one CTA per task) in every slot")
     ap.add_argument("--no-donation", action="store_true", help="bnb, N > 1: keep the initial round-robin split (no node donation)")
     ap.add_argument("--strategy", default="auto")
-    ap.add_argument("--poll-every", type=int, default=1)
+    ap.add_argument("--poll-every", type=int, default=None,
+                    help="iterations enqueued per read-back of the device scalar block (default: 2 for the LP workloads - "
+                         "measured 2955 vs 2909 iter/s at 1, 2929 at 4 - and 1 for bnb, where extra launches cost throughput)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -617,6 +619,8 @@ def main():
     ap.add_argument("--cg-max-iter", type=int, default=50000)
     ap.add_argument("--cg-tol", type=float, default=1e-8)
     args = ap.parse_args()
+    if args.poll_every is None:
+        args.poll_every = 1 if args.workload == "bnb" else 2
     args.warmup = max(args.warmup, 0)
     # stdout carries exactly ONE JSON line: libraries (NCCL banner, ...) are diverted to stderr
     real_stdout = os.dup(1)

@@ -1,8 +1,9 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
 {
-  for v in tt tt_nosh; do echo "== $v"; timeout 120 scripts/bin/df_timeline_$v 1000 | grep -E "^rep|^info|step [0-3]|last tile"; done
-  echo "== pytest gpu kernels+solve"; timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_solve.py -x -q -m gpu 2>&1 | tail -4
-  echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pcg-block --no-batch-block 2> gpurun_out/bench_o.err | tee gpurun_out/bench_o.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['e2e']['value']), {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()})"
-} > gpurun_out/round33.log 2>&1
-cat gpurun_out/round33.log
+  echo "== pytest gpu all"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+  echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pcg-block 2> gpurun_out/bench_o.err | tee gpurun_out/bench_o.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['e2e']['value'],1), d['gpu_launches'], {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()}, d['concurrent_lps']['value'])"
+  echo "== bnb slots 32"; timeout 300 python bench.py --workload bnb --slots 32 --steps 20 --warmup 3 2>> gpurun_out/bnb.err | tee gpurun_out/bnb_m_s32.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), d['nodes'], round(d['lp_device_ms_per_node'],2), d['lp_iterations'])"
+  echo "== bnb slots 16"; timeout 300 python bench.py --workload bnb --slots 16 --steps 20 --warmup 3 2>> gpurun_out/bnb.err | tee gpurun_out/bnb_m_s16.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), d['nodes'], round(d['lp_device_ms_per_node'],2), d['lp_iterations'])"
+} > gpurun_out/round35.log 2>&1
+cat gpurun_out/round35.log

@@ -395,11 +395,6 @@ k_assemble_normal16(long long n_pairs, const unsigned int *__restrict__ chunk_pt
 // sector request (up to 32 per warp instruction), 14 M of them per launch.  From shared memory the same
 // gather is ~6 wavefronts per warp instruction; d (88 KB at n = 11000) is staged once per CTA.
 static constexpr int ASM_SMEM_THREADS = 1024;
-__device__ __forceinline__ double chunk_gather8_s(uint4 v, const double *ds)
-{
-    return ((ds[v.x & 0xffffu] + ds[v.x >> 16]) + (ds[v.y & 0xffffu] + ds[v.y >> 16])) +
-           ((ds[v.z & 0xffffu] + ds[v.z >> 16]) + (ds[v.w & 0xffffu] + ds[v.w >> 16]));
-}
 __global__ void __launch_bounds__(ASM_SMEM_THREADS, 1)
 k_assemble_normal16_smem(long long n_pairs, int m_rows, const unsigned int *__restrict__ chunk_ptr,
                          const uint4 *__restrict__ term8, const double *__restrict__ d, int nd, double *__restrict__ M, int ld)
@@ -478,12 +473,9 @@ void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, 
     if (P.term16 && P.pad_id >= 0 && (size_t)(P.pad_id + 1) * 8 <= 200 * 1024 &&
         P.n_pairs >= (long long)SB200_ASM_SMEM_MIN_CTAS * ASM_SMEM_THREADS)
     {
-        static bool attr_set = false;
-        if (!attr_set)
-        {
+        static unsigned long long attr_seen = 0;
+        if (first_use_on_device(attr_seen))
             cudaFuncSetAttribute(k_assemble_normal16_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
         const int nd = P.pad_id + 1;
         // one entry per thread and trip at least: m = 500 (scpnre / scpnrf, B&B nodes) fills 123 CTAs, m >= 550 all 148
         const int ctas = (int)std::min<long long>(148, (P.n_pairs + ASM_SMEM_THREADS - 1) / ASM_SMEM_THREADS);

@@ -279,12 +279,11 @@ k_blk_rows_reduce(BlockedPattern B, const double *__restrict__ z, double *__rest
 
 static void launch_blk_rows(const BlockedPattern &B, bool abs_mode, const double *v, const int *skip, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set)
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_device(attr_seen))
     {
         cudaFuncSetAttribute(k_blk_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16386 * 8);
         cudaFuncSetAttribute(k_blk_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16386 * 8);
-        attr_set = true;
     }
     // row chunks so that (vector blocks x chunks) fills the SMs about once
     int chunks = (148 + B.nblk - 1) / B.nblk;
@@ -433,12 +432,9 @@ template <int MODE>
 static void launch_blk_cols_mode(const BlockedPattern &B, const double *v, const double *z, double *out, double alpha,
                                  double beta, const IpmVecs &V, const double *dscale, const Scalars *sc, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set)
-    {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_device(attr_seen))
         cudaFuncSetAttribute(k_blk_cols<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13314 * 8);
-        attr_set = true;
-    }
     const int nchunks = (B.majors + BLK_COL_CHUNK - 1) / BLK_COL_CHUNK;
     const int grid = nchunks < 148 * 2 ? nchunks : 148 * 2;
     k_blk_cols<MODE><<<grid, BLK_COL_THREADS, sizeof(double) * ((size_t)B.nb + 2), st>>>(B, v, z, out, alpha, beta, V, dscale, sc);

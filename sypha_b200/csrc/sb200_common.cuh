@@ -205,6 +205,27 @@ inline int grid_for(long long n, int block, int cap = SB200_MAX_PARTIAL_BLOCKS)
     return (int)g;
 }
 
+// eight 2-byte column ids of one 16-byte chunk of the compact normal-matrix pattern: sum of d over them, d in shared
+// memory (fixed association: the assembly kernel and the factorisation's in-task assembly give the same bits)
+__device__ __forceinline__ double chunk_gather8_s(uint4 v, const double *ds)
+{
+    return ((ds[v.x & 0xffffu] + ds[v.x >> 16]) + (ds[v.y & 0xffffu] + ds[v.y >> 16])) +
+           ((ds[v.z & 0xffffu] + ds[v.z >> 16]) + (ds[v.w & 0xffffu] + ds[v.w >> 16]));
+}
+
+// Function attributes (opt-in shared memory) are per DEVICE: a process that holds workspaces on several GPUs must
+// set them once on each.  `seen` is a caller-owned bit mask (devices 0..63); returns true on the first call for
+// the current device.
+inline bool first_use_on_device(unsigned long long &seen)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
 
 } // namespace sb200

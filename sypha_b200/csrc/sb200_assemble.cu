@@ -400,6 +400,7 @@ k_assemble_normal16_smem(long long n_pairs, int m_rows, const unsigned int *__re
                          const uint4 *__restrict__ term8, const double *__restrict__ d, int nd, double *__restrict__ M, int ld)
 {
     extern __shared__ __align__(16) double ds[];
+    pdl_wait();
     for (int i = threadIdx.x; i < nd; i += ASM_SMEM_THREADS)
         ds[i] = d[i];
     __syncthreads();
@@ -479,8 +480,8 @@ void launch_assemble_normal(const NormalPattern &P, const double *d, double *M, 
         const int nd = P.pad_id + 1;
         // one entry per thread and trip at least: m = 500 (scpnre / scpnrf, B&B nodes) fills 123 CTAs, m >= 550 all 148
         const int ctas = (int)std::min<long long>(148, (P.n_pairs + ASM_SMEM_THREADS - 1) / ASM_SMEM_THREADS);
-        k_assemble_normal16_smem<<<ctas, ASM_SMEM_THREADS, sizeof(double) * (size_t)nd, st>>>(
-            P.n_pairs, P.m, P.chunk_ptr, reinterpret_cast<const uint4 *>(P.term16), d, nd, M, ld);
+        launch_pdl(k_assemble_normal16_smem, ctas, ASM_SMEM_THREADS, sizeof(double) * (size_t)nd, st,
+                   P.n_pairs, P.m, P.chunk_ptr, reinterpret_cast<const uint4 *>(P.term16), d, nd, M, ld);
         ++g_launch_count;
         return;
     }

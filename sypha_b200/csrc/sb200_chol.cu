@@ -602,6 +602,7 @@ __global__ void __launch_bounds__(NT_TILE, 2) k_potrf_df(PotrfDf P, DfCtl C)
     const int row0 = (w >> 2) * 32, col0 = (w & 3) * 16;     // 8 warps: 2 x 4, warp tile 32 x 16
     const int g = lane >> 2, tg = lane & 3;
     const int T = P.T, ld = P.ld;
+    pdl_wait(false);      // no early trigger: CTAs of the successor waiting on the SMs slow the pivot chains (measured)
     const int epoch = ld_volatile(C.epoch) + 1;
 
     auto load_acc = [&](double acc[4][2][2], size_t r0, size_t c0) {
@@ -1107,6 +1108,7 @@ __global__ void __launch_bounds__(256) k_tri_gemv(const double *__restrict__ Z, 
                                                   double *__restrict__ y, int upper)
 {
     __shared__ double part[8];
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = 4 * blockIdx.x + (warp >> 1), t64 = (warp & 1) * 32 + lane;
     const int lo = upper ? (r & ~1) : 0, hi = upper ? ld : ((r + 2) & ~1);
@@ -1348,7 +1350,7 @@ void launch_potrf(CholWork &W, int n, double *a, int ld, int *info, cudaStream_t
     int cap = W.sms * (use_z ? 1 : W.potrf_occ);
     if (W.grid_limit > 0 && W.grid_limit < cap) cap = W.grid_limit;
     const int grid = W.ntasks < cap ? W.ntasks : cap;
-    k_potrf_df<<<grid, NT_TILE, SM_TOTAL, st>>>(P, C);
+    launch_pdl(k_potrf_df, grid, NT_TILE, SM_TOTAL, st, P, C);
     ++g_launch_count;
 }
 
@@ -1369,8 +1371,8 @@ void launch_potrs(CholWork &W, int n, const double *l, int ld, double *b, cudaSt
         k_tri_gemv2<<<grid, 256, 0, st>>>(W.zbuf, W.zTbuf, ld, b, W.ytmp, C, ctl + 10);
         ++g_launch_count;
 #else
-        k_tri_gemv<<<ld / 4, 256, 0, st>>>(W.zbuf, ld, b, W.ytmp, 0);
-        k_tri_gemv<<<ld / 4, 256, 0, st>>>(W.zTbuf, ld, W.ytmp, b, 1);
+        launch_pdl(k_tri_gemv, ld / 4, 256, 0, st, W.zbuf, ld, b, W.ytmp, 0);
+        launch_pdl(k_tri_gemv, ld / 4, 256, 0, st, W.zTbuf, ld, W.ytmp, b, 1);
         g_launch_count += 2;
 #endif
         return;

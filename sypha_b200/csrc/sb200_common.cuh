@@ -205,6 +205,53 @@ inline int grid_for(long long n, int block, int cap = SB200_MAX_PARTIAL_BLOCKS)
     return (int)g;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the ~12 kernels of an IPM iteration are each tens of microseconds or less, and
+// a plain stream (or graph) edge costs the launch latency of every one of them after its predecessor has drained.
+// Launched with the programmatic-serialization attribute a kernel's CTAs are dispatched while the predecessor is
+// still running; `pdl_wait()` - the FIRST statement of every kernel launched that way - blocks until the
+// predecessor grid has completed and its writes are visible, so only the dispatch overlaps, never the data.
+// `pdl_trigger()` right behind it lets the successor be dispatched in turn.  Kernels without these calls, and
+// launches without the attribute, keep plain stream order.
+// ---------------------------------------------------------------------------------------------
+// MEASURED (B200, scpnrh shape, iteration replayed from a CUDA graph with programmatic edges - 13 kernel nodes):
+// stand-alone launch groups get shorter (one solve 14.4 -> 12.2 us, fused vector kernels 14.9 -> 11.4 us) but the
+// whole loop gets LONGER: 14.4 -> 15.2 ms per LP (2958 -> 2803 iter/s), and 15.4 ms when the factorisation also
+// triggers early (successor CTAs parked on the SMs slow its pivot chains); B&B 1671 -> 1647 / 1347 nodes/s.
+// Off by default; the calls below compile to nothing and launch_pdl is a plain launch.
+#ifndef SB200_V_PDL
+#define SB200_V_PDL 0
+#endif
+__device__ __forceinline__ void pdl_wait(bool trigger = true)
+{
+#if SB200_V_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#else
+    (void)trigger;
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+#if SB200_V_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+#else
+    kernel<<<grid, block, smem, st>>>(KArgs(args)...);
+    return cudaGetLastError();
+#endif
+}
+
 // eight 2-byte column ids of one 16-byte chunk of the compact normal-matrix pattern: sum of d over them, d in shared
 // memory (fixed association: the assembly kernel and the factorisation's in-task assembly give the same bits)
 __device__ __forceinline__ double chunk_gather8_s(uint4 v, const double *ds)

@@ -22,6 +22,7 @@ k_spmv_csr(int m, const int *__restrict__ offs, const int *__restrict__ inds,
            const double *__restrict__ vals, const double *__restrict__ x,
            const double *__restrict__ z, double *__restrict__ out, double alpha, double beta)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < m; row += gridDim.x * wpb)
@@ -60,7 +61,7 @@ void launch_spmv_csr(const CsrView &A, const double *x, const double *z, double 
 {
     if (A.blk) return launch_blk_spmv_rows(*A.blk, x, z, out, alpha, beta, st);
     const int grid = grid_for((long long)A.m * 32, 256, 148 * 16);
-    k_spmv_csr<0><<<grid, 256, 0, st>>>(A.m, A.offs, A.inds, A.vals, x, z, out, alpha, beta);
+    launch_pdl(k_spmv_csr<0>, grid, 256, 0, st, A.m, A.offs, A.inds, A.vals, x, z, out, alpha, beta);
     ++g_launch_count;
 }
 void launch_jacobi_diag(const CsrView &A, const double *d, double *diag, cudaStream_t st)
@@ -99,6 +100,7 @@ k_spmv_csc(int n, const int *__restrict__ colptr, const int *__restrict__ rows,
            IpmVecs V)
 {
     __shared__ double sh[32];
+    pdl_wait();
     if (MODE == CSC_RECOVER)
         if (V.sc->done) return;
     const int gl = threadIdx.x & (G - 1);
@@ -187,8 +189,8 @@ static void launch_csc_g(const CscView &A, int mode, const double *v, const doub
     const int grid = grid_for((long long)A.n * G, 256, 148 * 16);
 #define SB200_CSC_CASE(M)                                                                          \
     case M:                                                                                        \
-        k_spmv_csc<G, M><<<grid, 256, 0, st>>>(A.n, A.colptr, A.rows, A.vals, v, z, out, alpha,   \
-                                                beta, V);                                         \
+        launch_pdl(k_spmv_csc<G, M>, grid, 256, 0, st, A.n, A.colptr, A.rows, A.vals, v, z, out,  \
+                   alpha, beta, V);                                                               \
         break;
     switch (mode)
     {

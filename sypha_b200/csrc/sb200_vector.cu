@@ -197,6 +197,7 @@ void launch_init_mu(const IpmVecs &V, const DevParams *P, cudaStream_t st)
 // affine step lengths, mu_aff and sigma     (sypha_solver.cpp:596-622)
 __global__ void k_affine_mu(IpmVecs V)
 {
+    pdl_wait();
     __shared__ double sh[32];
     Scalars *sc = V.sc;
     if (sc->done) return;
@@ -222,7 +223,7 @@ __global__ void k_affine_mu(IpmVecs V)
 }
 void launch_affine_mu(const IpmVecs &V, cudaStream_t st)
 {
-    k_affine_mu<<<grid_for(V.n, kBlock), kBlock, 0, st>>>(V);
+    launch_pdl(k_affine_mu, grid_for(V.n, kBlock), kBlock, 0, st, V);
     ++g_launch_count;
 }
 
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kSingleCtaThreads) k_affine_corrector(IpmVecs 
 // resXS += -dxa.*dsa + sigma*mu ; t = (x.*resC - resXS)/s      (sypha_solver.cpp:625-629)
 __global__ void k_corrector(IpmVecs V)
 {
+    pdl_wait();
     const Scalars *sc = V.sc;
     if (sc->done) return;
     const double sm = sc->sigma * sc->mu;
@@ -283,7 +285,7 @@ __global__ void k_corrector(IpmVecs V)
 }
 void launch_corrector(const IpmVecs &V, cudaStream_t st)
 {
-    k_corrector<<<grid_for(V.n, kBlock), kBlock, 0, st>>>(V);
+    launch_pdl(k_corrector, grid_for(V.n, kBlock), kBlock, 0, st, V);
     ++g_launch_count;
 }
 void launch_affine_corrector(const IpmVecs &V, cudaStream_t st)
@@ -302,6 +304,7 @@ void launch_affine_corrector(const IpmVecs &V, cudaStream_t st)
 // (sypha_solver.cpp:693-769 and :505 of the following iteration)
 __global__ void k_update(IpmVecs V, const DevParams *__restrict__ Pp)
 {
+    pdl_wait();
     __shared__ double sh[32];
     Scalars *sc = V.sc;
     if (sc->done) return;
@@ -406,7 +409,7 @@ void launch_update(const IpmVecs &V, const DevParams *P, cudaStream_t st)
     if (lim <= kSingleCtaMax)       // one CTA: the "last block" is the only block
         k_update<<<1, kSingleCtaThreads, 0, st>>>(V, P);
     else
-        k_update<<<grid_for(lim, kBlock), kBlock, 0, st>>>(V, P);
+        launch_pdl(k_update, grid_for(lim, kBlock), kBlock, 0, st, V, P);
     ++g_launch_count;
 }
 

@@ -1127,7 +1127,10 @@ int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps)
     int limit = 0;
     if (concurrent_lps > 1)
     {
-        const int slots = 2 * (ws->chol.sms > 0 ? ws->chol.sms : 148);
+        // CTA slots shared out: 2 per SM by default (SB200_SHARE_FACTOR overrides, for experiments)
+        const char *fs = getenv("SB200_SHARE_FACTOR");
+        const int factor = fs ? std::max(1, atoi(fs)) : 2;
+        const int slots = factor * (ws->chol.sms > 0 ? ws->chol.sms : 148);
         limit = std::max(4, slots / concurrent_lps);
     }
     if (limit != ws->chol.grid_limit)

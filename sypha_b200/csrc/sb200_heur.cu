@@ -134,40 +134,44 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics(HeurArgs a)
             if (v >= 0 && v < n0) state[v] = ST_BANNED;
         }
     __syncthreads();
-    // cover_i = number of chosen columns in row i (warp per row)
-    for (int i = warp; i < m0; i += HW)
+    // cover_i = number of chosen columns in row i.  Through the CSC lists of the CHOSEN columns (a few dozen), not
+    // through all rows of the CSR copy: one CTA reading the whole matrix twice (cover counts by rows, gains by
+    // columns) was most of this kernel's 350 us.
+    for (int j = tid; j < n0; j += HT)
+        if (state[j] & ST_X) a.list[atomicAdd(&s_chosen, 1)] = j;
+    __syncthreads();
     {
-        int cnt = 0;
-        for (int p = a.row_ptr[i] + lane; p < a.row_ptr[i + 1]; p += 32)
+        const int nsel = s_chosen;
+        for (int q = warp; q < nsel; q += HW)
         {
-            const int j = a.row_cols[p];
-            if (j < n0 && (state[j] & ST_X)) ++cnt;
-        }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0)
-        {
-            cover[i] = cnt;
-            if (cnt == 0) atomicAdd(&s_unc, 1);
+            const int j = a.list[q];
+            for (int p = a.col_ptr[j] + lane; p < a.col_ptr[j + 1]; p += 32)
+            {
+                const int i = a.col_rows[p];
+                if (i < m0) atomicAdd(&cover[i], 1);
+            }
         }
     }
+    __syncthreads();
+    for (int i = tid; i < m0; i += HT)
+        if (cover[i] == 0) atomicAdd(&s_unc, 1);
+    if (tid == 0) s_chosen = 0;                 // reused by the redundancy pass
     __syncthreads();
 
     // ---- 2. greedy repair ------------------------------------------------------------------------------
     int feasible = 1;
     if (s_unc > 0)
     {
-        // gain_j = uncovered rows column j would cover (warp per column)
-        for (int j = warp; j < n0; j += HW)
-        {
-            int g = 0;
-            for (int p = a.col_ptr[j] + lane; p < a.col_ptr[j + 1]; p += 32)
-            {
-                const int i = a.col_rows[p];
-                if (i < m0 && cover[i] == 0) ++g;
-            }
-            g = __reduce_add_sync(0xffffffffu, g);
-            if (lane == 0) gain[j] = g;
-        }
+        // gain_j = uncovered rows column j would cover: every uncovered row (few) adds one to the columns it holds
+        for (int j = tid; j < n0; j += HT) gain[j] = 0;
+        __syncthreads();
+        for (int i = warp; i < m0; i += HW)
+            if (cover[i] == 0)
+                for (int p = a.row_ptr[i] + lane; p < a.row_ptr[i + 1]; p += 32)
+                {
+                    const int j = a.row_cols[p];
+                    if (j < n0) atomicAdd(&gain[j], 1);
+                }
         __syncthreads();
         while (true)
         {

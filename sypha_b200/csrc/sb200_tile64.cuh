@@ -154,6 +154,9 @@ __device__ __forceinline__ void d1_emit_panel(double2 *dst, double tag, int b, c
     }
 }
 
+#ifndef SB200_V_IDLE_WARP4
+#define SB200_V_IDLE_WARP4 1
+#endif
 #ifndef SB200_V_LOOKAHEAD
 #define SB200_V_LOOKAHEAD 1  // the pivot-chain warp also applies a finished 16-column panel to the NEXT 16x16 diagonal
                              // block (all its next chain needs); the other seven warps apply it to the rest of the
@@ -442,13 +445,23 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
         }
         else
         {
+#if SB200_V_IDLE_WARP4
+            // warp 4 shares its scheduler (SM sub-partition 0) with the pivot-chain warp: it only keeps the barrier
+            // counts and leaves the issue slots to warp 0; the other six warps split the work
+            const bool worker = warp != 4;
+            const int w = warp - 1 - (warp > 4 ? 1 : 0);    // 0..5 for the workers
+            constexpr int NWORK = 6;
+#else
+            const bool worker = true;
             const int w = warp - 1;                         // 0..6
+            constexpr int NWORK = 7;
+#endif
             if (k >= 1 && k <= 2)
             {
                 const int p0 = c0 - 16;                     // panel k-1
                 // ---- R(k-1): rows p0+32..63, one 8-row block per warp ------------------------------------------
                 const int nrb = (32 - p0) >> 3;             // 4, 2
-                if (w < nrb)
+                if (worker && w < nrb)
                 {
                     const int R = p0 + 32 + 8 * w;
                     double af[4];
@@ -469,47 +482,50 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
                     Ls[R + g][p0 + 8 + 2 * tg + 1] = x11;
                 }
                 named_bar_sync(1, NT_TILE - 32);
+                if (worker)
+                {
                 // ---- T(k-1): 8x8 blocks (bi, bj), bi >= bj, of rows/cols r0..63 except the first 16x16 block ---
-                const int r0 = p0 + 16, nb = (64 - r0) >> 3;     // 6, 4
-                const int nblk = nb * (nb + 1) / 2 - 3;          // 18, 7
-                int ro[3], co[3];
-#pragma unroll
-                for (int v = 0; v < 3; ++v)
-                {
-                    const int q = w + 7 * v + 3;                 // skip (0,0) (1,0) (1,1)
-                    int bi = 0;
-                    bi += (q >= 1) + (q >= 3) + (q >= 6) + (q >= 10) + (q >= 15);
-                    const int bj = q - bi * (bi + 1) / 2;
-                    const bool act = w + 7 * v < nblk;
-                    ro[v] = act ? r0 + 8 * bi : r0 + 16;
-                    co[v] = act ? r0 + 8 * bj : r0;
-                }
-                double af[3][4], bf[3][4], u[3][2];
-#pragma unroll
-                for (int v = 0; v < 3; ++v)
-                {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                    {
-                        af[v][kk] = -Ls[ro[v] + g][p0 + 4 * kk + tg];
-                        bf[v][kk] = Ls[co[v] + g][p0 + 4 * kk + tg];
-                    }
-                    u[v][0] = Ls[ro[v] + g][co[v] + 2 * tg];
-                    u[v][1] = Ls[ro[v] + g][co[v] + 2 * tg + 1];
-                }
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
+                    const int r0 = p0 + 16, nb = (64 - r0) >> 3;     // 6, 4
+                    const int nblk = nb * (nb + 1) / 2 - 3;          // 18, 7
+                    int ro[3], co[3];
+    #pragma unroll
                     for (int v = 0; v < 3; ++v)
-                        dmma_8x8x4(u[v][0], u[v][1], af[v][kk], bf[v][kk]);
-                __syncwarp();
-#pragma unroll
-                for (int v = 0; v < 3; ++v)
-                    if (w + 7 * v < nblk)
                     {
-                        Ls[ro[v] + g][co[v] + 2 * tg] = u[v][0];
-                        Ls[ro[v] + g][co[v] + 2 * tg + 1] = u[v][1];
+                        const int q = w + NWORK * v + 3;             // skip (0,0) (1,0) (1,1)
+                        int bi = 0;
+                        bi += (q >= 1) + (q >= 3) + (q >= 6) + (q >= 10) + (q >= 15);
+                        const int bj = q - bi * (bi + 1) / 2;
+                        const bool act = worker && w + NWORK * v < nblk;
+                        ro[v] = act ? r0 + 8 * bi : r0 + 16;
+                        co[v] = act ? r0 + 8 * bj : r0;
                     }
+                    double af[3][4], bf[3][4], u[3][2];
+    #pragma unroll
+                    for (int v = 0; v < 3; ++v)
+                    {
+    #pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                        {
+                            af[v][kk] = -Ls[ro[v] + g][p0 + 4 * kk + tg];
+                            bf[v][kk] = Ls[co[v] + g][p0 + 4 * kk + tg];
+                        }
+                        u[v][0] = Ls[ro[v] + g][co[v] + 2 * tg];
+                        u[v][1] = Ls[ro[v] + g][co[v] + 2 * tg + 1];
+                    }
+    #pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+    #pragma unroll
+                        for (int v = 0; v < 3; ++v)
+                            dmma_8x8x4(u[v][0], u[v][1], af[v][kk], bf[v][kk]);
+                    __syncwarp();
+    #pragma unroll
+                    for (int v = 0; v < 3; ++v)
+                        if (worker && w + NWORK * v < nblk)
+                        {
+                            Ls[ro[v] + g][co[v] + 2 * tg] = u[v][0];
+                            Ls[ro[v] + g][co[v] + 2 * tg + 1] = u[v][1];
+                        }
+                }
             }
             TT(9 + 4 * k);
             if (k < 3)
@@ -517,7 +533,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
                 __threadfence_block();
                 named_bar_arrive(2, NT_TILE);
             }
-            if (d1dst && k >= 1) d1_emit_panel(d1dst, d1tag, k - 1, Ls, Li, tid - 32, NT_TILE - 32);
+            if (d1dst && k >= 1 && worker) d1_emit_panel(d1dst, d1tag, k - 1, Ls, Li, 32 * w + lane, 32 * NWORK);
             TT(24 + k);
         }
         __syncthreads();

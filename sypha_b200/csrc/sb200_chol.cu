@@ -1129,87 +1129,6 @@ __global__ void __launch_bounds__(256) k_tri_gemv(const double *__restrict__ Z, 
     if (tid < 4) y[4 * blockIdx.x + tid] = part[2 * tid] + part[2 * tid + 1];
 }
 
-#ifndef SB200_V_GEMV_FUSED
-#define SB200_V_GEMV_FUSED 0     // 1: both products of a solve in ONE launch (below).  Measured slower than two plain
-                                 // launches: 19.0 against 14.3 us per solve at m = 1000 (2833 against 2955 iter/s), B&B
-                                 // 1595 against 1671 nodes/s - task claiming and the wait for the y counter cost more
-                                 // than a kernel boundary inside a graph.  Off.
-#endif
-// x = Z'(Z b) in one launch: tasks 0..R-1 are the 4-row blocks of y = Z b, tasks R..2R-1 the blocks of
-// x = Z' y, claimed in that order (every y task is owned by a running CTA before any x task exists, so the x
-// tasks' wait for "all R blocks of y done" cannot deadlock, whatever else shares the GPU).  Saves the second
-// launch and its ramp; the counters are re-armed by the last CTA out (graph replay).
-__global__ void __launch_bounds__(256) k_tri_gemv2(const double *__restrict__ Z, const double *__restrict__ ZT, int ld,
-                                                   double *b, double *ytmp, DfCtl C, int *y_done)
-{
-    __shared__ int s_task;
-    __shared__ double part[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int R = ld >> 2, t64 = (warp & 1) * 32 + lane;
-    for (;;)
-    {
-        const int t = claim_task(C, &s_task);
-        if (t >= 2 * R) break;
-        const bool upper = t >= R;
-        const int blk = upper ? t - R : t;
-        if (upper)
-        {
-            if (tid == 0)
-            {
-                int spins = 0;
-                while (ld_relaxed(y_done) != R)
-                    if ((++spins & 255) == 0 && (ld_volatile(C.err) || spins > (1 << 21)))
-                    {
-                        atomicExch(C.err, 1);
-                        break;
-                    }
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            }
-            __syncthreads();
-        }
-        const int r = 4 * blk + (warp >> 1);
-        const int lo = upper ? (r & ~1) : 0, hi = upper ? ld : ((r + 2) & ~1);
-        const double *row = (upper ? ZT : Z) + (size_t)r * ld;
-        const double *x = upper ? ytmp : b;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
-        for (int c = lo + 2 * t64; c < hi; c += 128)
-        {
-            const double2 z = __ldcg(reinterpret_cast<const double2 *>(row + c));
-            a0 = fma(z.x, __ldcg(x + c), a0);
-            a1 = fma(z.y, __ldcg(x + c + 1), a1);
-        }
-        double a = a0 + a1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) part[warp] = a;
-        __syncthreads();
-        if (tid < 4) (upper ? b : ytmp)[4 * blk + tid] = part[2 * tid] + part[2 * tid + 1];
-        if (!upper)
-        {
-            __syncthreads();                       // the four stores above precede thread 0's release
-            if (tid == 0)
-            {
-                __threadfence();
-                atomicAdd(y_done, 1);
-            }
-        }
-    }
-    __syncthreads();
-    if (tid == 0)
-    {
-        __threadfence();
-        const unsigned e = atomicAdd(C.exits, 1u);
-        if (e == gridDim.x - 1)
-        {
-            *C.exits = 0u;
-            *C.next_task = 0u;
-            *y_done = 0;
-            __threadfence();
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1364,17 +1283,9 @@ void launch_potrs(CholWork &W, int n, const double *l, int ld, double *b, cudaSt
     (void)l;     // the solves stream G = blockdiag(W) L (or Z = L^-1), built by the factorisation
     if (T <= SB200_Z_MAX_T)
     {   // x = Z'(Z b): two triangular matrix-vector products, four rows per CTA
-#if SB200_V_GEMV_FUSED
-        DfCtl C{ctl + 4, reinterpret_cast<unsigned *>(ctl + 5), reinterpret_cast<unsigned *>(ctl + 6), ctl + 8};
-        int grid = ld / 4;                       // the y tasks; they go on to claim the x tasks
-        if (W.grid_limit > 0 && 4 * W.grid_limit < grid) grid = 4 * W.grid_limit;
-        k_tri_gemv2<<<grid, 256, 0, st>>>(W.zbuf, W.zTbuf, ld, b, W.ytmp, C, ctl + 10);
-        ++g_launch_count;
-#else
         launch_pdl(k_tri_gemv, ld / 4, 256, 0, st, W.zbuf, ld, b, W.ytmp, 0);
         launch_pdl(k_tri_gemv, ld / 4, 256, 0, st, W.zTbuf, ld, W.ytmp, b, 1);
         g_launch_count += 2;
-#endif
         return;
     }
     TrsvDf P{W.gbuf, W.gbufT, ld, T2, W.linv128, b, W.tagged, W.tagged + tc2 * 128};

@@ -175,98 +175,6 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count)
 // The 16x16 diagonal block at c0 of Ls factored by ONE warp (see potrf_tile64_factor below): lanes 0..15 hold
 // the rows, lanes 16..31 the columns of the identity (-> W = L_dd^-1 in Li).  Returns the 1-based tile-local
 // index of the first non-positive pivot, or 0.
-#ifndef SB200_V_PIV2
-#define SB200_V_PIV2 0       // 1: 2x2 pivot blocks in the 16-column chain (below).  Measured on B200 inside k_potrf_df
-                             // (clock64 stamps of a mid-matrix tile, m = 1000): 3200-3700 cycles per 16 columns, the
-                             // same as the column-at-a-time chain (3000-3400), although its dependent latency is
-                             // 8 x 177 instead of 16 x 109 cycles; a LOOPED form of it (register array shifted by two
-                             // per pair, body of 4.5 KB that fits the L0 instruction cache) took 5300-5900.  So the
-                             // chain is bound neither by the rsqrt latency nor by instruction fetch but by the issue
-                             // of its ~500 dependent-ish instructions from ONE warp; kept for the record, off.
-#endif
-#if SB200_V_PIV2
-// The same 16x16 factorisation + inverse with 2x2 pivot blocks.  For the pair of columns (c, c+1) with
-// [a b; b e] the current 2x2 diagonal block, l_cc = sqrt(a), l_(c+1)c = b / sqrt(a) and l_(c+1)(c+1) =
-// sqrt(e - b^2/a) = sqrt(det / a), det = a e - b^2: the reciprocal roots of a and of det do not depend on each
-// other, so the two long-latency rsqrt chains of a pair run in parallel - 1/l_(c+1)(c+1) = rsqrt(det) * sqrt(a).
-// One shuffle round per pair broadcasts what the next pair needs (the two lanes' updated diagonals, their two
-// new column entries and the raw off-diagonal entry; every lane forms b redundantly), so the dependent chain is
-//   dg' (2 DFMA) -> shuffles -> b (2 DFMA) -> det (2) -> rsqrt x2 in parallel -> 1/l22 (2) -> l2 (2)
-// ~ 177 cycles per PAIR against 2 x 109 for the column-at-a-time chain (rsqrt 67, shuffle 26, DFMA 8).
-__device__ __noinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)[LP], double *Tb, int c0, int lane)
-{
-    const int r = lane & 15;
-    const bool inv_lane = lane >= 16;
-    const unsigned full = 0xffffffffu;
-    double(*Cb)[17] = reinterpret_cast<double(*)[17]>(Tb);
-    double a[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-        a[j] = inv_lane ? (j == r ? 1.0 : 0.0) : Ls[c0 + r][c0 + j];
-    double dg = a[0];
-#pragma unroll
-    for (int j = 1; j < 16; ++j)
-        dg = (r == j) ? a[j] : dg;
-    int bad = 0;
-    double A = __shfl_sync(full, dg, 0), E = __shfl_sync(full, dg, 1), B = __shfl_sync(full, a[0], 1);
-#pragma unroll
-    for (int c = 0; c < 16; c += 2)
-    {
-        const double det = fma(A, E, -(B * B));
-        if (bad == 0)
-        {
-            if (!(A > 0.0)) bad = c0 + c + 1;
-            else if (!(det > 0.0)) bad = c0 + c + 2;
-        }
-        const double inv1 = SB200_RSQ(A), invd = SB200_RSQ(det);
-        const double l21 = B * inv1;
-        const double inv2 = invd * (A * inv1);
-        // rows: L[r][c], L[r][c+1];  inverse lanes: z_c, z_(c+1) of the forward substitution
-        double l1 = a[c] * inv1, t = a[c + 1];
-        if (!inv_lane && r == c) l1 = A * inv1;
-        if (!inv_lane && r == c + 1) { l1 = l21; t = E; }
-        double l2 = fma(-l1, l21, t) * inv2;
-        if (!inv_lane && r == c) l2 = 0.0;                 // above the diagonal
-        a[c] = l1;
-        a[c + 1] = l2;
-        dg = fma(-l2, l2, fma(-l1, l1, dg));
-        if (!inv_lane)
-        {
-            Cb[c][r] = l1;
-            Cb[c + 1][r] = l2;
-        }
-        if (c < 14)
-        {   // the next pair's 2x2 block, formed by every lane from one round of shuffles
-            const double p1 = __shfl_sync(full, l1, c + 2), p2 = __shfl_sync(full, l2, c + 2);
-            const double q1 = __shfl_sync(full, l1, c + 3), q2 = __shfl_sync(full, l2, c + 3);
-            const double raw = __shfl_sync(full, a[c + 2], c + 3);
-            A = __shfl_sync(full, dg, c + 2);
-            E = __shfl_sync(full, dg, c + 3);
-            B = fma(-q2, p2, fma(-q1, p1, raw));
-        }
-        __syncwarp();
-#pragma unroll
-        for (int c2 = c + 2; c2 < 16; ++c2)
-            a[c2] = fma(-l2, Cb[c + 1][c2], fma(-l1, Cb[c][c2], a[c2]));
-    }
-    if (!inv_lane)
-    {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            Ls[c0 + r][c0 + j] = (j <= r) ? a[j] : 0.0;
-    }
-    else
-    {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            Li[c0 + j][c0 + r] = a[j];
-    }
-    return bad;
-}
-#else
-#ifndef SB200_V_SHFL_NEXT
-#define SB200_V_SHFL_NEXT 0   // 1 measured no faster (3550-3900 against 3450-3600 cycles per panel in situ): off
-#endif
 #ifndef SB200_V_P_NOINLINE
 #define SB200_V_P_NOINLINE 1   // one copy of the 16-column chain in the kernel: inlined, the compiler peels the panel loop
                                // and the second copy is a second set of cold instruction-cache lines per tile
@@ -303,16 +211,10 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
         {
             d = __shfl_sync(0xffffffffu, dg, c + 1);
             inv = SB200_RSQ(d);
-#if SB200_V_SHFL_NEXT
-            // the entry the NEXT column scales first, a[c+1], gets L[c+1][c] by shuffle (26 cycles) instead of through
-            // the shared-memory column buffer (store -> syncwarp -> load: 70 cycles alone, more beside the other
-            // warps' fragment loads), so that path never overtakes the rsqrt chain
-            a[c + 1] -= l * __shfl_sync(0xffffffffu, l, c + 1);
-#endif
         }
         __syncwarp();
 #pragma unroll
-        for (int c2 = c + 1 + SB200_V_SHFL_NEXT; c2 < 16; ++c2)
+        for (int c2 = c + 1; c2 < 16; ++c2)
             a[c2] -= l * Cb[c][c2];
     }
     if (!inv_lane)
@@ -329,7 +231,6 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
     }
     return bad;
 }
-#endif  // SB200_V_PIV2
 
 #if SB200_V_LOOKAHEAD
 // Look-ahead form of the tile factorisation.  With 16x16 blocks A[i][j] (i >= j) of the tile and panel k =

@@ -1,9 +1,11 @@
 #!/usr/bin/env bash
-# last check of the round: the GPU suite, smoke() and one bench line with the library as committed
+# refresh of the ncu --set full captures for the two kernels that changed after the r1_k evidence pass
 mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pcg-block --no-e2e --no-phases --no-batch-block"
 {
-  echo "== pytest gpu all"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-  echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-  echo "== bench (default flags)"; timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; python -c "import json; d=json.load(open('gpurun_out/bench_final.json')); print(round(d['value'],1), round(d['e2e']['value'],1), d['gpu_launches'], d['roofline']['frac'], d['cpu_baseline']['value'], d['pcg_50kx1M']['lp_solve']['time_to_lp_opt_s'], d['clocks'])"
-} > gpurun_out/round44.log 2>&1
-cat gpurun_out/round44.log
+  $CMD > gpurun_out/plain_m.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_potrf_df|k_tri_gemv" -s 20 -c 3 -o gpurun_out/prof_m $CMD > gpurun_out/ncu_m.log 2>&1; tail -1 gpurun_out/ncu_m.log | cut -c1-160
+  python scripts/ncu_summary.py gpurun_out/prof_m.ncu-rep > gpurun_out/ncu_m_summary.txt 2>&1
+  timeout 300 ncu --set full --clock-control none -k "regex:k_node_heuristics" -s 20 -c 3 -o gpurun_out/prof_m_heur python bench.py --workload bnb --slots 8 --steps 6 --warmup 1 > gpurun_out/ncu_m3.log 2>&1; python scripts/ncu_summary.py gpurun_out/prof_m_heur.ncu-rep >> gpurun_out/ncu_m_summary.txt 2>&1
+  grep -E "Kernel Name|gpu__time_duration|dram__bytes_read|pipe_tensor|stall" gpurun_out/ncu_m_summary.txt | cut -c1-150
+} > gpurun_out/round45.log 2>&1
+cat gpurun_out/round45.log

@@ -211,6 +211,22 @@ class BatchedBnb:
         if x is not None and obj < self.incumbent:
             self.incumbent, self.incumbent_x = obj, x
 
+    def _branch_from_device(self, nd: BnbNode, slot: int, bound: float, feasible: bool, cover_obj: float,
+                            branch_var: int, branch_frac: float, rounded_obj: float):
+        """What follows a converged, unpruned node LP when the heuristics ran on the device: incumbent offers
+        (the cover, and c.rint(x) for an integral LP point) and the two children.  Shared by the window and the
+        continuous drivers."""
+        if feasible and cover_obj < self.incumbent:
+            self._offer(cover_obj, get_cover(self.ws[slot], self.base.n_orig))
+        if branch_var < 0 or branch_frac < 1e-6:           # integral LP point
+            self.stats.integral += 1
+            if rounded_obj < self.incumbent:
+                x = get_primal(self.ws[slot], self.base.n + len(nd.decisions))[:self.base.n_orig]
+                self._offer(rounded_obj, np.round(x))
+            return
+        self.frontier.append(BnbNode(nd.decisions + ((branch_var, 0),), bound))
+        self.frontier.append(BnbNode(nd.decisions + ((branch_var, 1),), bound))
+
     def round(self) -> int:
         """Pop up to K nodes, solve their LPs as one batch, branch.  Returns the number processed."""
         batch: List[BnbNode] = []
@@ -258,17 +274,8 @@ class BatchedBnb:
                 if heur is not None:                           # same rules, computed on the device
                     h = heur[slot]
                     self.stats.kernels_launched += 1
-                    if h.feasible and h.coverObj < self.incumbent:
-                        self._offer(h.coverObj, get_cover(self.ws[slot], self.base.n_orig))
-                    if h.branchVar < 0 or h.branchFrac < 1e-6:     # integral LP point
-                        self.stats.integral += 1
-                        if h.roundedObj < self.incumbent:
-                            self._offer(h.roundedObj, np.round(get_primal(self.ws[slot], self.base.n + len(nd.decisions))
-                                                               [:self.base.n_orig]))
-                        continue
-                    j = h.branchVar
-                    self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
-                    self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+                    self._branch_from_device(nd, slot, bound, h.feasible, h.coverObj, h.branchVar, h.branchFrac,
+                                             h.roundedObj)
                     continue
                 x = res.primalSolution[:self.base.n_orig]
                 zero_fixed = [v for v, f in nd.decisions if f == 0]
@@ -322,7 +329,7 @@ class BatchedBnb:
         started = [0]
         failure: List[BaseException] = []
         deep: List[BnbNode] = []
-        n_orig, st = self.base.n_orig, self.stats
+        st = self.stats
 
         def next_cb(_user, slot, delta):
             try:
@@ -373,16 +380,8 @@ class BatchedBnb:
                 if self._prunable(bound):
                     st.pruned_by_bound += 1
                     return
-                if h.feasible and h.cover_obj < self.incumbent:
-                    self._offer(h.cover_obj, get_cover(self.ws[slot], n_orig))
-                if h.branch_var < 0 or h.branch_frac < 1e-6:
-                    st.integral += 1
-                    if h.rounded_obj < self.incumbent:
-                        self._offer(h.rounded_obj, np.round(get_primal(self.ws[slot], self.base.n + len(nd.decisions))[:n_orig]))
-                    return
-                j = h.branch_var
-                self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
-                self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+                self._branch_from_device(nd, slot, bound, bool(h.feasible), h.cover_obj, h.branch_var, h.branch_frac,
+                                         h.rounded_obj)
             except BaseException as e:
                 failure.append(e)
 

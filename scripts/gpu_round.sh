@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
-# source-level capture of the factorisation with the shortest sampling interval: what does the pivot-chain warp wait for?
+# last check of the round: the GPU suite, smoke() and one bench line with the library as committed
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-pcg-block --no-e2e --no-phases --no-batch-block"
 {
-  timeout 600 ncu --set full --warp-sampling-interval 0 --warp-sampling-buffer-size 536870912 --clock-control none --import-source on -k "regex:k_potrf_df" -s 30 -c 1 -o gpurun_out/prof_chain $CMD > gpurun_out/ncu_chain.log 2>&1; tail -1 gpurun_out/ncu_chain.log | cut -c1-160
-  ncu -i gpurun_out/prof_chain.ncu-rep --page source --csv --kernel-name regex:k_potrf_df > gpurun_out/potrf_chain_source.csv 2>/dev/null; wc -l gpurun_out/potrf_chain_source.csv
-} > gpurun_out/round47.log 2>&1
-cat gpurun_out/round47.log
+  echo "== pytest gpu all"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+  echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+  echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pcg-block 2> gpurun_out/bench_o.err | tee gpurun_out/bench_o.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['e2e']['value'],1), round(d['loop_ms_per_lp'],3), {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()}, d['concurrent_lps']['value'])"
+} > gpurun_out/round48.log 2>&1
+cat gpurun_out/round48.log

@@ -192,18 +192,18 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
 #pragma unroll
     for (int j = 0; j < 16; ++j)
         a[j] = inv_lane ? (j == r ? 1.0 : 0.0) : Ls[c0 + r][c0 + j];
-    double dg = a[0];
-#pragma unroll
-    for (int j = 1; j < 16; ++j)
-        dg = (r == j) ? a[j] : dg;
-    int bad = 0;
+    double dg = Ls[c0 + r][c0 + r];            // this lane's own diagonal entry (one load instead of 15 selects; the
+                                               // inverse lanes never contribute theirs)
+    unsigned badmask = 0;                      // bit c: pivot c not positive (the index is worked out after the chain)
     double d = __shfl_sync(0xffffffffu, dg, 0);
     double inv = SB200_RSQ(d);
 #pragma unroll
     for (int c = 0; c < 16; ++c)
     {
-        if (!(d > 0.0) && bad == 0) bad = c0 + c + 1;
-        const double l = (!inv_lane && r == c) ? d * inv : a[c] * inv;
+        if (!(d > 0.0)) badmask |= 1u << c;
+        // rows: L[r][c] (for r == c the row's own a[c] has received exactly the updates of dg, so a[c] * inv is
+        // d * inv = sqrt(d) without a special case);  inverse lanes: z_c = z[c] / L[c][c]
+        const double l = a[c] * inv;
         a[c] = l;
         dg -= l * l;
         if (!inv_lane) Cb[c][r] = l;
@@ -229,7 +229,7 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
         for (int j = 0; j < 16; ++j)
             Li[c0 + j][c0 + r] = a[j];
     }
-    return bad;
+    return badmask ? c0 + __ffs(badmask) : 0;
 }
 
 #if SB200_V_LOOKAHEAD

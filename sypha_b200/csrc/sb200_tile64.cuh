@@ -189,9 +189,17 @@ __device__ __forceinline__ int potrf_block16_warp(double (*Ls)[LP], double (*Li)
     const bool inv_lane = lane >= 16;
     double(*Cb)[17] = reinterpret_cast<double(*)[17]>(Tb);
     double a[16];
+    {   // rows of the block, or (inverse lanes) rows of the 16x16 identity kept behind the column buffer: one
+        // pointer select and eight 16-byte loads instead of a compare-and-select per entry
+        const double *src = inv_lane ? Tb + 512 + 16 * r : &Ls[c0 + r][c0];
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-        a[j] = inv_lane ? (j == r ? 1.0 : 0.0) : Ls[c0 + r][c0 + j];
+        for (int j = 0; j < 16; j += 2)
+        {
+            const double2 v = *reinterpret_cast<const double2 *>(src + j);
+            a[j] = v.x;
+            a[j + 1] = v.y;
+        }
+    }
     double dg = Ls[c0 + r][c0 + r];            // this lane's own diagonal entry (one load instead of 15 selects; the
                                                // inverse lanes never contribute theirs)
     unsigned badmask = 0;                      // bit c: pivot c not positive (the index is worked out after the chain)
@@ -259,6 +267,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
     __syncthreads();
     return 0;
 #endif
+    Tb[512 + tid] = ((tid >> 4) == (tid & 15)) ? 1.0 : 0.0;      // 16x16 identity for the inverse lanes (NT_TILE = 256)
     for (int idx = tid; idx < 6 * 256; idx += NT_TILE)
     {   // clear the strictly-upper 16x16 blocks of Li: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
         const int blk = idx >> 8, e = idx & 255;
@@ -461,6 +470,7 @@ __device__ int potrf_tile64_factor(unsigned char *smem, int tid, int *deferred_f
     __syncthreads();
     return 0;
 #endif
+    Tb[512 + tid] = ((tid >> 4) == (tid & 15)) ? 1.0 : 0.0;      // 16x16 identity for the inverse lanes (NT_TILE = 256)
     // clear the strictly-upper 16x16 blocks of Li: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
     for (int idx = tid; idx < 6 * 256; idx += NT_TILE)
     {

@@ -92,6 +92,11 @@ typedef struct sb200_params {
     const volatile int *stop_flag;  /* host flag polled between iterations (logger watchdog), may be NULL */
     int poll_every;             /* host reads the device scalar block every k iterations (>=1) */
     int use_graph;              /* 1 = replay one captured CUDA graph per iteration */
+    /* live stop test, asked every time the host looks at the scalar block (every poll_every iterations): the
+     * reference polls node.env->getLogger()->isStopRequested() once per iteration (src/sypha_solver.cpp:498-502),
+     * an std::atomic<bool> behind a getter that no plain int pointer can mirror.  May be NULL. */
+    int (*stop_cb)(void *user);
+    void *stop_user;
 } sb200_params;
 
 typedef struct sb200_result {

@@ -108,11 +108,13 @@ SyphaStatus solver_sparse_mehrotra_run(SyphaNodeSparse &node, const SolverExecut
     p.cg_tol_final = env->getKrylovCgTolFinal();
     p.cg_tol_decay = env->getKrylovCgTolDecayRate();
 
-    // the logger's watchdog flag (sypha_solver.cpp:498-502) is an std::atomic<bool> behind a getter:
-    // mirror it into an int the library can poll between iterations
-    volatile int stop = 0;
-    p.stop_flag = &stop;
-    if (env->getLogger() && env->getLogger()->isStopRequested()) stop = 1;
+    // the logger's watchdog flag (sypha_solver.cpp:498-502) is an std::atomic<bool> behind a getter: the
+    // library asks it through a callback every time it looks at the LP's scalar block (every iteration)
+    if (env->getLogger())
+    {
+        p.stop_cb = [](void *lg) -> int { return static_cast<SyphaLogger *>(lg)->isStopRequested() ? 1 : 0; };
+        p.stop_user = env->getLogger();
+    }
 
     node.hX.resize(node.ncols);
     node.hY.resize(node.nrows);

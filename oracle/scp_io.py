@@ -81,6 +81,25 @@ def load_scp(path, name="") -> ScpInstance:
     return to_standard_form(m, n, costs, rows, name or str(path))
 
 
+def write_scp_text(inst: ScpInstance, path) -> None:
+    """Write the OR-Library text form (``m n``, the costs, then per row ``k idx_1..idx_k`` 1-based) of a
+    standard-form instance whose last entry per row is the surplus column - the inverse of ``load_scp``; it is how
+    the committed fixtures (tests/golden/*.npz) reach the reference's own binaries (oracle/_ref) on the GPU box,
+    where /root/reference/data does not exist.  Integer costs are written as integers, like the originals."""
+    n0 = inst.n_orig
+    costs = inst.c[:n0]
+    with open(path, "w") as fh:
+        fh.write(f" {inst.m} {n0}\n")
+        as_int = np.all(costs == np.round(costs))
+        for a in range(0, n0, 12):
+            fh.write(" " + " ".join(str(int(v)) if as_int else repr(float(v)) for v in costs[a:a + 12]) + "\n")
+        for i in range(inst.m):
+            cols = inst.inds[inst.offs[i]:inst.offs[i + 1] - 1] + 1
+            fh.write(f" {len(cols)}\n")
+            for a in range(0, len(cols), 12):
+                fh.write(" " + " ".join(map(str, cols[a:a + 12])) + "\n")
+
+
 def gen_scp(m, n, density, seed) -> ScpInstance:
     """Synthetic random SCP, SURVEY.md Appendix C (RNG call order is part of the spec).
 

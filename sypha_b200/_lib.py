@@ -30,6 +30,7 @@ class sb200_params(C.Structure):
         ("cg_max_iter", C.c_int), ("cg_tol_initial", C.c_double), ("cg_tol_final", C.c_double),
         ("cg_tol_decay", C.c_double),
         ("stop_flag", C.POINTER(C.c_int)), ("poll_every", C.c_int), ("use_graph", C.c_int),
+        ("stop_cb", C.c_void_p), ("stop_user", C.c_void_p),
     ]
 
 

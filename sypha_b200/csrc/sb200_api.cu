@@ -646,7 +646,8 @@ int solve_step(sb200_ws *ws)
 int solve_poll(sb200_ws *ws, int *finished)
 {
     WS_TRY(cudaEventSynchronize(ws->ev[3]));
-    const bool stop = ws->params.stop_flag && *ws->params.stop_flag;
+    const bool stop = (ws->params.stop_flag && *ws->params.stop_flag) ||
+                      (ws->params.stop_cb && ws->params.stop_cb(ws->params.stop_user));
     *finished = (ws->sc_host->done || ws->enqueued >= ws->params.max_iter || stop) ? 1 : 0;
     return SB200_OK;
 }
@@ -739,6 +740,8 @@ void sb200_default_params(sb200_params *p)
     p->cg_tol_final = 1e-8;
     p->cg_tol_decay = 0.5;
     p->stop_flag = nullptr;
+    p->stop_cb = nullptr;
+    p->stop_user = nullptr;
     p->poll_every = 1;
     p->use_graph = 1;
 }

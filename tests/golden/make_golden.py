@@ -35,6 +35,8 @@ sys.path.insert(0, str(REF / "python"))
 SMALL = ["demo00", "scp_demo06", "scp_demo_tiny03", "scp41", "scp42", "scp46", "scp48", "scp49",
          "scp410", "scp51", "scpclr10", "scpcyc06", "scpa1", "scpb1"]
 LARGE = ["scpnre1", "scpnrf1", "scpnrg1", "scpnrh1", "scpclr13"]
+# the rest of the families BASELINE.json configs[1] / configs[4] name (bench.py's default workloads)
+LARGE += [f"scpnr{f}{i}" for f in "ehg" for i in range(2, 6)]
 
 
 def known_lp_optima():

@@ -32,20 +32,75 @@ import numpy as np
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
+# OR-Library workloads: the real instances, shipped as compact archives (tests/golden/<name>.npz, written from the
+# reference's data/ files by tests/golden/make_golden.py).  name: (instances, description)
+ORLIB = {
+    "scpnrh": ([f"scpnrh{i}" for i in range(1, 6)],
+               "OR-Library scpnrh1-5 LP relaxations (1000x10000, 5% density), BASELINE.json configs[1]"),
+    "scp4": (["scp41", "scp42", "scp46", "scp48", "scp49", "scp410"],
+             "OR-Library scp41/42/46/48/49/410 LP relaxations (200x1000, 2% density), configs[0]"),
+    "scpnre": ([f"scpnre{i}" for i in range(1, 6)], "OR-Library scpnre1-5 LP relaxations (500x5000, 10% density)"),
+    "scpnrg": ([f"scpnrg{i}" for i in range(1, 6)], "OR-Library scpnrg1-5 LP relaxations (1000x10000, 2% density)"),
+    "scpnrf": (["scpnrf1"], "OR-Library scpnrf1 LP relaxation (500x5000, 20% density), configs[2]"),
+    "scpclr13": (["scpclr13"], "OR-Library scpclr13 LP relaxation (4095x715, 511 entries per column), configs[2]"),
+}
 WORKLOADS = {
-    # name: (m, n_orig, density, description)
-    "scpnrh": (1000, 10000, 0.05, "scpnrh-shaped synthetic SCP LP relaxation 1000x10000, 5% density (configs[1])"),
-    "scp4": (200, 1000, 0.02, "scp4x-shaped synthetic SCP LP relaxation 200x1000, 2% density (configs[0])"),
-    "scpnrf": (500, 5000, 0.20, "scpnrf-shaped synthetic SCP LP relaxation 500x5000, 20% density (configs[2])"),
-    "scpclr13": (4095, 715, 0.125, "scpclr13-shaped synthetic SCP LP relaxation 4095x715, 12.5% density (configs[2])"),
+    # synthetic look-alikes: name: (m, n_orig, density, description)
+    "scpnrh-synth": (1000, 10000, 0.05, "scpnrh-shaped synthetic SCP LP relaxation 1000x10000, 5% density"),
+    "scp4-synth": (200, 1000, 0.02, "scp4x-shaped synthetic SCP LP relaxation 200x1000, 2% density"),
+    "scpnrf-synth": (500, 5000, 0.20, "scpnrf-shaped synthetic SCP LP relaxation 500x5000, 20% density"),
+    "scpclr13-synth": (4095, 715, 0.125, "scpclr13-shaped synthetic SCP LP relaxation 4095x715, 12.5% density"),
     "synth5k": (5000, 100000, 0.001, "synthetic SCP 5000x100000, 0.1% density (configs[3] ladder rung)"),
     "synth50k": (50000, 1000000, 0.001, "synthetic SCP 50000x1000000, 0.1% density (configs[3])"),
 }
 N_INSTANCES = 5
 MAX_ITER = 100
-# FP64 tensor-pipe (DMMA) peak measured on this pool with scripts/dfma (33.2 TFLOP/s; nominal 40):
-# MEASURED_PEAKS.json carries no FP64 entry
-FP64_DMMA_TFLOPS = 33.2
+# FP64 denominators: MEASURED_PEAKS.json carries no FP64 entry.  bench.py measures a cuBLAS DGEMM 8192^3 live
+# (SURVEY.md 8d names it as the FP64 tensor denominator) and quotes scripts/fp64_peak.cu's committed numbers
+# (profiles/r2_a_fp64_peaks.json: DMMA issue rate 37.2, DGEMM 35.9 TFLOP/s) as the fallback
+FP64_FALLBACK_TFLOPS = 35.9
+
+
+def load_models(workload, rank=0):
+    """-> (models, description, data) for a workload name."""
+    if workload in ORLIB:
+        from sypha_b200.instances import load_npz
+        names, desc = ORLIB[workload]
+        return [load_npz(REPO / "tests" / "golden" / f"{nm}.npz") for nm in names], desc, "orlib"
+    from sypha_b200.instances import gen_scp
+    m, n0, dens, desc = WORKLOADS[workload]
+    k = 1 if workload == "synth50k" else N_INSTANCES     # 1.3 GB of structure per instance: larger than L2 on its own
+    return [gen_scp(m, n0, dens, 1000 * rank + i + 1) for i in range(k)], desc, "synthetic"
+
+
+def base_config(workload, models, desc):
+    """The part of `config` both arms share."""
+    mdl = models[0]
+    return {"workload": desc, "instances": len(models), "m": int(mdl.m), "n_orig": int(mdl.n_orig),
+            "nnz": int(mdl.nnz), "max_iter": MAX_ITER, "eta": 0.95, "mu_tol": 1e-4}
+
+
+def measure_fp64_dgemm(n=8192, reps=4):
+    """cuBLAS DGEMM n^3 through torch.matmul(float64) on the current device, best of `reps` (CUDA events)."""
+    import torch
+    try:
+        a = torch.rand((n, n), dtype=torch.float64, device="cuda") - 0.5
+        b = torch.rand((n, n), dtype=torch.float64, device="cuda") - 0.5
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / best / 1e9, f"cuBLAS DGEMM {n}^3 measured live by bench.py (torch.matmul float64, best of {reps})"
+    except Exception as e:           # never lose the line to the denominator
+        return FP64_FALLBACK_TFLOPS, f"fallback: profiles/r2_a_fp64_peaks.json cuBLAS DGEMM 8192^3 ({e!r})"
 
 
 def read_peaks():
@@ -185,111 +240,129 @@ def pcg_block(lib, sb, local_rank, peak, full_solve=True):
         sb.releaseIpmWorkspace(ws)
 
 
-def run_bnb(args, rank, world, local_rank):
-    """B&B nodes/s (BASELINE.json configs[4]): scpnre-shaped synthetic instance, batched node LPs on every
-    GPU, ranks work on disjoint parts of the frontier, NCCL carries only the incumbent."""
+def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, slots, stream_factor=0):
+    """B&B nodes/s (BASELINE.json configs[4]) on one OR-Library instance: the reference's prelude (greedy
+    incumbent, columns dearer than it dropped), then batched node LPs on every GPU with the reference's node LP
+    configuration; ranks work on disjoint parts of the frontier, NCCL carries only the incumbent bound (an
+    asynchronous 24-byte all_gather per round, collected two rounds later) and, when the frontier sizes drift
+    apart, donated nodes.  Returns this rank-0 view of the measurement (None on the other ranks)."""
     import torch
-    import sypha_b200 as sb
     from sypha_b200 import bnb, bnb_exchange
-    from sypha_b200.instances import gen_scp
+    from sypha_b200.instances import load_npz
 
+    mdl = load_npz(REPO / "tests" / "golden" / f"{instance}.npz")      # same instance on every rank
+    ax = bnb_exchange.AsyncBoundExchange(lag=2) if dist is not None else None
+
+    def rebalance(nodes):
+        return bnb_exchange.rebalance_frontier(nodes, max_depth=64, min_imbalance=slots // 2)
+
+    drv = bnb.BatchedBnb.with_reference_presolve(
+        mdl, slots=slots, device=local_rank, device_heuristics=not args.host_heuristics, share_gpu=not args.no_share,
+        poll_every=1, node_lp=args.node_lp, async_exchange=ax,
+        rebalance=rebalance if (dist is not None and not args.no_donation) else None)
+    red = drv.base
+    # every rank expands the same first levels (deterministic, no exchange yet), then keeps its round-robin share
+    drv.async_exchange = None
+    while len(drv.frontier) < world * slots and drv.frontier:
+        drv.round()
+    mine = bnb_exchange.partition_round_robin(list(drv.frontier), rank, world)
+    drv.frontier.clear()
+    drv.frontier.extend(mine)
+    for _ in range(warmup):                        # untimed full windows: every slot has solved a node before t0
+        drv.round()
+    drv.async_exchange = ax
+    warm_nodes = drv.stats.processed
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    st = drv.stats
+    before = (st.processed, st.lp_iterations, st.lp_device_ms, st.kernels_launched, st.delta_rows, st.rounds)
+    t0 = time.perf_counter()
+    # a step = one round: a window of K node LPs, or (stream_factor F) F*K nodes through the continuous batcher
+    drv.run(max_nodes=10 ** 9, rounds=steps, stream_nodes=stream_factor * slots)
+    torch.cuda.synchronize()
+    busy = time.perf_counter() - t0               # this rank's own time for its K rounds
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    nodes, iters, dev_ms, launches, drows, rounds = (st.processed - before[0], st.lp_iterations - before[1],
+                                                     st.lp_device_ms - before[2], st.kernels_launched - before[3],
+                                                     st.delta_rows - before[4], st.rounds - before[5])
+    idle_ms, wait_ms = 1e3 * (elapsed - busy), st.exchange_wait_ms
+    per_rank = None
+    if dist:
+        drv.finish_exchange()
+        g = torch.tensor([nodes, 1e3 * busy, wait_ms, len(drv.frontier)], dtype=torch.float64, device="cuda")
+        allg = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(allg, g)
+        per_rank = [[round(float(v), 2) for v in t.tolist()] for t in allg]
+        elapsed, (nodes, iters, dev_ms, launches, drows) = bnb_exchange.reduce_counters(elapsed, [nodes, iters, dev_ms, launches, drows])
+    out = None
+    if rank == 0:
+        out = {
+            "instance": instance, "value": nodes / elapsed, "unit": "nodes/s", "n_gpus": world, "rounds": steps,
+            "warmup_rounds": warmup, "warmup_nodes": warm_nodes, "ms_per_round": 1e3 * elapsed / steps,
+            "nodes": int(nodes), "lp_iterations": int(iters), "lp_iterations_per_node": iters / max(nodes, 1),
+            "lp_device_ms_per_node": dev_ms / max(nodes, 1), "gpu_launches": int(launches),
+            "model": {"m": int(red.m), "n_orig": int(red.n_orig), "n_orig_input": int(mdl.n_orig), "nnz": int(red.nnz),
+                      "greedy_incumbent": drv.stats.greedy_incumbent},
+            "incumbent": drv.incumbent, "root_bound": drv.stats.root_bound,
+            "slots_per_gpu": slots, "node_lp": args.node_lp,
+            "batching": (f"continuous (sb200_solve_stream), {stream_factor} x slots nodes per round"
+                         if stream_factor > 0 else "windows of K nodes (sb200_solve_batch)"),
+            "exchange": ({"kind": "asynchronous all_gather of (incumbent objective, open nodes, processed nodes) per "
+                                  "round, collected 2 rounds later; incumbent vector fetched once at the end; node "
+                                  "donation (blocking) only when the gathered frontier sizes differ by > slots/2",
+                          "bytes_per_round_per_rank": 24, "posted": ax.posted,
+                          "per_rank_[nodes, busy_ms, exchange_wait_ms, open_nodes]": per_rank,
+                          "rank0_idle_at_final_barrier_ms": idle_ms,
+                          "nodes_sent_by_rank0": st.nodes_sent, "nodes_received_by_rank0": st.nodes_received}
+                         if dist else None),
+            "rank0": {"round_ms": st.round_ms[-steps:], "lp_at_iteration_cap": st.maxiter_nodes,
+                      "lp_gap_stalled": st.gap_stalled_nodes, "lp_failed": st.infeasible, "pruned": st.pruned_by_bound,
+                      "integral": st.integral},
+            "h2d_bytes_per_round": int(20 * drows / max(steps, 1)),
+            "d2h_bytes_per_round": int(slots * world * (8 * (2 * red.n + red.m) if args.host_heuristics else 40 + 96)),
+        }
+    drv.close()
+    return out
+
+
+def run_bnb(args, rank, world, local_rank):
+    """--workload bnb: the B&B measurement as the headline line."""
+    import torch
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    m, n0, dens = 500, 5000, 0.10
-    mdl = gen_scp(m, n0, dens, 77)                 # same instance on every rank
-    exch_bytes = [0]
-
-    def exchange(obj, x):
-        if dist is None:
-            return obj, x
-        xt = None if x is None else torch.from_numpy(np.asarray(x, dtype=np.float64))
-        best, bx, owner = bnb_exchange.exchange_incumbent(obj, xt, n0)
-        exch_bytes[0] += 16 + 8 * n0
-        return best, (None if bx is None else bx.cpu().numpy())
-
-    def rebalance(nodes):
-        return bnb_exchange.rebalance_frontier(nodes, max_depth=64, min_imbalance=args.slots // 2)
-
-    drv = bnb.BatchedBnb(mdl, slots=args.slots, device=local_rank, exchange=exchange,
-                         device_heuristics=not args.host_heuristics, share_gpu=not args.no_share, poll_every=args.poll_every,
-                         rebalance=rebalance if (dist is not None and not args.no_donation) else None, rebalance_every=4)
-    # every rank expands the same first levels (deterministic), then keeps its round-robin share
-    while len(drv.frontier) < world * args.slots and drv.frontier:
-        drv.round()
-    mine = bnb_exchange.partition_round_robin(list(drv.frontier), rank, world)
-    drv.frontier.clear()
-    drv.frontier.extend(mine)
-    for _ in range(args.warmup):                   # untimed full windows: every slot has solved a node before t0
-        drv.round()
-    warm_nodes = drv.stats.processed
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.ready.wait(10)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-        torch.cuda.synchronize()
-    before = drv.stats.processed
-    dev_before = drv.stats.lp_device_ms
-    it_before = drv.stats.lp_iterations
-    kl_before = drv.stats.kernels_launched
-    t0 = time.perf_counter()
-    # a step = one round: a window of K node LPs, or (--stream-factor F) F*K nodes through the continuous batcher
-    drv.run(max_nodes=10 ** 9, rounds=args.steps, stream_nodes=args.stream_factor * args.slots)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-        torch.cuda.synchronize()
-    elapsed = time.perf_counter() - t0
+    blk = bnb_measure(args, rank, world, local_rank, dist, args.bnb_instance, args.steps, args.warmup, args.slots,
+                      args.stream_factor)
     sampler.stop_evt.set()
     sampler.join(timeout=2)
-    nodes = drv.stats.processed - before
-    iters = drv.stats.lp_iterations - it_before
-    dev_ms = drv.stats.lp_device_ms - dev_before
-    launches = drv.stats.kernels_launched - kl_before
-    if dist:
-        elapsed, (nodes, iters, dev_ms, launches) = bnb_exchange.reduce_counters(elapsed, [nodes, iters, dev_ms, launches])
     out = None
     if rank == 0:
         out = {
-            "metric": "bnb_nodes_per_sec", "value": nodes / elapsed, "unit": "nodes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "warmup_nodes": warm_nodes, "ms_per_step": 1e3 * elapsed / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "branch-and-bound on an scpnre-shaped synthetic SCP 500x5000, 10% density "
-                                   "(configs[4]); a step = one round of K batched node LPs per GPU",
-                       "slots_per_gpu": args.slots, "poll_every": args.poll_every,
-                       "batching": (f"continuous (sb200_solve_stream), {args.stream_factor} x slots nodes per step"
-                                    if args.stream_factor > 0 else "windows of K nodes (sb200_solve_batch)"),
-                       "node_heuristics": "host NumPy" if args.host_heuristics else "device kernel (sb200_node_heuristics)", "node_lp": "Mehrotra IPM to mu <= 1e-4, max_iter 100",
-                       "frontier": "FIFO, most-fractional branching, round-robin split across ranks",
-                       "collective": "all_reduce(MIN) of the incumbent objective + broadcast of the incumbent vector per round; "
-                                     "every 4 rounds an all_gather of the frontier sizes and, when they differ by more than "
-                                     "half a window, node donation (decision lists, 536 B per node)"},
+            "metric": "bnb_nodes_per_sec", "value": blk["value"], "unit": "nodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": blk["ms_per_round"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "orlib",
+            "config": {"workload": f"branch-and-bound on OR-Library {args.bnb_instance} (configs[4]); a step = one round "
+                                   "of K batched node LPs per GPU", "slots_per_gpu": args.slots, "node_lp": args.node_lp},
             "timing": "wall clock between device synchronisations around the K rounds, max over ranks "
-                      "(host node construction, upload, LP solves, heuristics, incumbent exchange)",
-            "nodes": int(nodes), "lp_iterations": int(iters), "lp_device_ms_per_node": dev_ms / max(nodes, 1),
-            "incumbent": drv.stats.incumbent, "root_bound": drv.stats.root_bound,
-            "rank0_rounds": {"ms": drv.stats.round_ms[-args.steps:], "sum_of_longest_lp_iterations": drv.stats.round_max_iterations,
-                             "lp_at_iteration_cap": drv.stats.maxiter_nodes, "lp_iterations_total": drv.stats.lp_iterations,
-                             "nodes_total": drv.stats.processed, "rounds_total": drv.stats.rounds},
-            "incumbent_exchange_bytes_per_round": (16 + 8 * n0) if dist else 0,
-            "node_donation": {"every_rounds": 4, "sent_by_rank0": drv.stats.nodes_sent, "received_by_rank0": drv.stats.nodes_received}
-            if drv.rebalance is not None else None,
-            "e2e": {"value": nodes / elapsed, "unit": "nodes/s",
-                    "h2d_bytes_per_step": int(20 * drv.stats.delta_rows / max(args.steps, 1)),
-                    "d2h_bytes_per_step": int(args.slots * (8 * (2 * mdl.n + mdl.m) if args.host_heuristics else 40 + 96)),
-                    "note": "the base model is resident; every round sends the K decision lists (20 B per branch row) "
-                            "and reads back, per node, the LP result scalars and the 40-byte branching / incumbent "
-                            "record of sb200_node_heuristics (x, y, s of every node with --host-heuristics) inside "
-                            "the timed region: value IS end to end"},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+                      "(node deltas, LP solves, heuristics kernel, host loop, exchange)",
+            "e2e": {"value": blk["value"], "unit": "nodes/s", "h2d_bytes_per_step": blk["h2d_bytes_per_round"],
+                    "d2h_bytes_per_step": blk["d2h_bytes_per_round"],
+                    "note": "the base model is resident; every round sends the K decision lists (20 B per branch row) and "
+                            "reads back, per node, the LP result scalars and the 40-byte branching / incumbent record "
+                            "inside the timed region: value IS end to end"},
+            "gpu_launches": blk["gpu_launches"], "clocks": sampler.summary(), "bnb": blk,
         }
-    drv.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -322,7 +395,6 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import sypha_b200 as sb
     from sypha_b200 import _lib as L
-    from sypha_b200.instances import gen_scp
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -331,12 +403,11 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = L.load()
-    m, n0, dens, desc = WORKLOADS[args.workload]
     strategy = args.strategy
     global N_INSTANCES
-    if args.workload == "synth50k":
-        N_INSTANCES = 1           # 1.3 GB of structure per instance: larger than L2 on its own
-    models = [gen_scp(m, n0, dens, 1000 * rank + i + 1) for i in range(N_INSTANCES)]
+    models, desc, data_kind = load_models(args.workload, rank)
+    N_INSTANCES = len(models)
+    fp64_peak, fp64_src = measure_fp64_dgemm() if rank == 0 else (FP64_FALLBACK_TFLOPS, "")
 
     env = sb.SyphaEnvironment(cudaDeviceId=local_rank, linearSolverStrategy=strategy,
                               pollEvery=args.poll_every, useGraph=not args.no_graph,
@@ -365,6 +436,8 @@ def run_ours(args, rank, world, local_rank):
             raise RuntimeError(f"LP {i} failed: reason {res.terminationReason}")
         return res
 
+    for i in range(N_INSTANCES):                   # set-up: every instance's iteration graph is built once
+        step(i)
     for i in range(args.warmup):
         step(i)
     sampler = ClockSampler(local_rank)
@@ -377,6 +450,7 @@ def run_ours(args, rank, world, local_rank):
     elapsed = time.perf_counter() - t0
     wall = elapsed
     iters = sum(r.iterations for r in results)
+    iters_rank0 = iters
     launches = sum(r.kernelsLaunched for r in results)
     # timed on the device: CUDA events on the workspace stream around every LP (start point, initial
     # residuals, loop); LPs run back to back, so the sum is this rank's device time for the K steps
@@ -444,6 +518,19 @@ def run_ours(args, rank, world, local_rank):
                        "note": "throughput with the instances' LPs in flight together (host clock, results read back); "
                                "the headline value is one LP at a time"}
 
+    # ---- secondary: B&B nodes/s on scpnre1 and scpnrg1 at THIS N (configs[4]; every rank takes part) ----
+    bnb_block = None
+    if not args.no_bnb_block and args.workload in ORLIB:
+        bnb_block = {}
+        for inst_name in ("scpnre1", "scpnrg1"):
+            try:
+                bnb_block[inst_name] = bnb_measure(args, rank, world, local_rank, dist, inst_name, args.bnb_rounds, 3,
+                                                   args.slots, 0)
+            except Exception as e:                  # never lose the headline line to a secondary measurement
+                if world > 1:
+                    raise
+                bnb_block[inst_name] = {"error": repr(e)}
+
     # ---- max over ranks / sums ----------------------------------------------------------------
     if dist:
         t = torch.tensor([elapsed, e2e_elapsed, wall], device="cuda", dtype=torch.float64)
@@ -474,7 +561,7 @@ def run_ours(args, rank, world, local_rank):
                     # FP64 tensor-pipe kernels: m^3/3 (Cholesky), m^2 n (SYRK on the lower tiles)
                     fl = info["m"] ** 3 / 3.0 if nm == "potrf" else float(info["m"]) ** 2 * info["n"]
                     phases[nm].update({"flops": fl, "tflops": fl / ms.value / 1e9,
-                                       "frac_fp64_tensor": fl / ms.value / 1e9 / FP64_DMMA_TFLOPS})
+                                       "frac_fp64_tensor": fl / ms.value / 1e9 / fp64_peak})
         roof = None
         if phases:
             dom = max(phases, key=lambda k: phases[k]["ms"] * phases[k]["per_iteration"])
@@ -486,10 +573,11 @@ def run_ours(args, rank, world, local_rank):
                 # the factorisation runs on the FP64 tensor pipe (DMMA): m^3/3 flops per launch
                 flops = info["m"] ** 3 / 3.0
                 tf = flops / ph["ms"] / 1e9
-                roof.update({"bound": "tensor", "achieved": tf, "peak": FP64_DMMA_TFLOPS, "unit": "TFLOP/s",
-                             "frac": tf / FP64_DMMA_TFLOPS, "flops": flops,
-                             "peak_source": "FP64 DMMA rate measured on this pool with scripts/dfma (MEASURED_PEAKS.json "
-                                            "has no FP64 entry; nominal 40 TFLOP/s)",
+                roof.update({"bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": tf / fp64_peak, "flops": flops,
+                             "peak_source": fp64_src + "; MEASURED_PEAKS.json has no FP64 entry; scripts/fp64_peak.cu on "
+                                            "this pool: DMMA issue rate 37.2, DGEMM 8192^3 35.9 TFLOP/s "
+                                            "(profiles/r2_a_fp64_peaks.json); nominal 40",
                              "hbm_gbs": ph["gbs"], "hbm_frac": ph["frac_hbm"],
                              "note": "latency-bound at m = 1000: 16 dependent 64-column steps (pivot chain + one "
                                      "hand-off each); see profiles/ for the per-step timeline. For m <= 1280 the same launch "
@@ -497,16 +585,28 @@ def run_ours(args, rank, world, local_rank):
             tr = read_traffic().get(dom)
             if tr is not None:
                 roof["traffic"] = tr
+            # the whole iteration against SURVEY.md 8(d)'s algorithmic bytes of the direct path:
+            # 5 * 12 * nnz + 2 * 8 * m^2 + 4 * 8 * m^2 / 2 + 24 * 8 * n, over the measured loop time per iteration
+            mm, nn, zz = info["m"], info["n"], info["nnz"]
+            it_bytes = 5 * 12 * zz + 16 * mm * mm + 16 * mm * mm + 24 * 8 * nn
+            it_us = 1e3 * loop_ms / max(iters_rank0, 1)
+            roof["whole_iteration"] = {"algorithmic_bytes": it_bytes, "us_per_iteration": it_us,
+                                       "achieved_gbs": it_bytes / it_us / 1e3, "frac_hbm": it_bytes / it_us / 1e3 / peak,
+                                       "us_at_hbm_peak": it_bytes / peak / 1e3,
+                                       "note": "SURVEY.md 8(d) per-iteration bytes / measured loop time per iteration "
+                                               "(CUDA events); launches and dependent latency, not bandwidth, bound this shape"}
         out = {
             "metric": "ipm_iterations_per_sec", "value": iters / elapsed, "unit": "iter/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "instances": N_INSTANCES, "m": m, "n_orig": n0, "density": dens,
-                       "max_iter": MAX_ITER, "eta": 0.95, "mu_tol": 1e-4,
-                       "strategy": {1: "cholesky", 2: "syrk", 3: "pcg"}.get(info["strategy"], "?"),
-                       "l2": f"{N_INSTANCES} rotating instances, working set > 126 MB L2 (no flush needed)",
-                       "poll_every": args.poll_every, "graph": not args.no_graph},
+            "data": data_kind,
+            "config": dict(base_config(args.workload, models, desc),
+                           strategy={1: "cholesky", 2: "syrk", 3: "pcg"}.get(info["strategy"], "?"),
+                           l2=(f"{N_INSTANCES} rotating instances, ~75 MB of resident structure each: working set > 126 MB L2 "
+                               "(no flush needed)" if N_INSTANCES > 1 else
+                               "one instance; its resident structure exceeds the 126 MB L2" if models[0].nnz > 10 ** 7 else
+                               "one instance, L2-resident between steps (stated, not flushed)"),
+                           poll_every=args.poll_every, graph=not args.no_graph),
             "time_to_lp_opt_ms": 1e3 * elapsed / args.steps,
             "timing": "CUDA events on the workspace stream around every LP, summed over the K steps, max over ranks",
             "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -522,6 +622,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if batch_block:
             out["concurrent_lps"] = batch_block
+        if bnb_block:
+            out["bnb"] = bnb_block
         if world == 1 and not args.no_pcg_block and args.workload != "synth50k":
             try:
                 out["pcg_50kx1M"] = pcg_block(lib, sb, local_rank, peak, full_solve=not args.no_pcg_solve)
@@ -561,34 +663,88 @@ def cpu_baseline(mdl, budget_s=25.0, solver="ne"):
             "seconds": secs, "probe_seconds": t_probe}
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle restatement of the reference's solver, rank 0 only."""
-    if rank != 0:
-        return None
-    from sypha_b200.instances import gen_scp
-    m, n0, dens, desc = WORKLOADS[args.workload]
-    models = [gen_scp(m, n0, dens, i + 1) for i in range(N_INSTANCES)]
+def run_reference_port(args, models, desc, data_kind, world):
+    """CPU arm of last resort: the oracle restatement of the reference's solver (oracle/, NumPy + SciPy)."""
     budget = max(2.0, 170.0 / (args.steps + args.warmup))
     samples = []
     for i in range(args.warmup):
-        cpu_baseline(models[i % N_INSTANCES], budget)
+        cpu_baseline(models[i % len(models)], budget)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        samples.append(cpu_baseline(models[i % N_INSTANCES], budget))
+        samples.append(cpu_baseline(models[i % len(models)], budget))
     elapsed = time.perf_counter() - t0
     iters_s = sum(s["value"] * s["seconds"] for s in samples) / sum(s["seconds"] for s in samples)
     return {
         "impl": "reference", "metric": "ipm_iterations_per_sec", "value": iters_s, "unit": "iter/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "instances": N_INSTANCES, "m": m, "n_orig": n0, "density": dens,
-                   "max_iter": MAX_ITER, "eta": 0.95, "mu_tol": 1e-4},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": data_kind,
+        "config": base_config(args.workload, models, desc),
         "cpu_baseline": {"value": iters_s, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": samples[0]["sample"] + f"; {args.steps} such steps, {budget:.0f} s budget each"},
         "e2e": {"value": iters_s, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU restatement (oracle/) of the reference's solver: the reference's CUDA build needs GSL, "
-                "Boost and cuSOLVER/cuSPARSE and does not compile here; its Python prototype cannot travel",
+        "note": "CPU restatement (oracle/) of the reference's solver: oracle/_ref/sypha_ref (the reference's own CUDA "
+                "build, `make -C oracle`) is not present in this checkout",
+    }
+
+
+def run_reference(args, rank, world):
+    """The reference arm, rank 0 only: the reference's OWN solver, unmodified - its CLI (src/main.cpp) over its
+    CUDA implementation (dense LU of the KKT matrix with cuSOLVER, cuSPARSE, cuBLAS), built for sm_100a by
+    oracle/Makefile into oracle/_ref/sypha_ref - on the same instances, one process per step, on this box's GPU 0.
+    A step is a bounded sample: the first `--ref-iters` iterations of the LP (every iteration of the reference does
+    the same work: one LU of the (2n+m)^2 KKT matrix and two solves).  value = iterations / the reference's own loop
+    timer (`solver` in its "Time (s)" line = node.timeSolver*, src/sypha_solver.cpp:487,821 - the same span our
+    ms_loop covers), summed over the K steps."""
+    if rank != 0:
+        return None
+    import re
+    import tempfile
+    models, desc, data_kind = load_models(args.workload, 0)
+    binary = REPO / "oracle" / "_ref" / "sypha_ref"
+    if not binary.exists() or models[0].m * 3 + 2 * models[0].n_orig > 110000:     # dense KKT must fit (SURVEY 8d)
+        return run_reference_port(args, models, desc, data_kind, world)
+    from sypha_b200.instances import write_scp
+    tmp = Path(tempfile.mkdtemp(prefix="sb200_ref_"))
+    files = []
+    for i, mdl in enumerate(models):
+        files.append(tmp / f"inst{i}.txt")
+        write_scp(mdl, files[-1])
+
+    def one(i):
+        t0 = time.perf_counter()
+        r = subprocess.run([str(binary), "--model", "scp", "--input-file", str(files[i % len(files)]),
+                            "--mehrotra-max-iter", str(args.ref_iters), "--disable-bnb", "--verbosity", "5"],
+                           capture_output=True, text=True, timeout=900)
+        out = r.stdout + r.stderr
+        if r.returncode != 0:
+            raise RuntimeError(f"reference binary failed ({r.returncode}): {out[-800:]}")
+        it = int(re.search(r"Iterations:\s+(\d+)", out).group(1))
+        tm = re.search(r"start\s+([0-9.]+)\s+pre\s+([0-9.]+)\s+solver\s+([0-9.]+)\s+total\s+([0-9.]+)", out)
+        return it, float(tm.group(3)), float(tm.group(1)), float(tm.group(2)), time.perf_counter() - t0
+
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    runs = [one(i) for i in range(args.steps)]
+    elapsed = time.perf_counter() - t0
+    iters, loop_s = sum(r[0] for r in runs), sum(r[1] for r in runs)
+    val = iters / max(loop_s, 1e-9)
+    sample = (f"first {args.ref_iters} iterations of each LP, one process per step ({args.steps} steps, instances in "
+              f"rotation); loop timer {loop_s:.2f} s for {iters} iterations; per step also start point "
+              f"{np.mean([r[2] for r in runs]):.2f} s (host, the GSL stand-in with OpenMP) + set-up "
+              f"{np.mean([r[3] for r in runs]):.2f} s + process start, {np.mean([r[4] for r in runs]):.1f} s wall")
+    return {
+        "impl": "reference", "metric": "ipm_iterations_per_sec", "value": val, "unit": "iter/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": data_kind,
+        "config": base_config(args.workload, models, desc),
+        "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 1, "kind": "reference", "sample": sample,
+                         "what": "the reference's own CUDA solver (unmodified sources, oracle/Makefile, release flags) "
+                                 "driven through its CLI by one host thread, GPU 0 of this box; not a CPU run"},
+        "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "gpu_launches counts OUR kernels: none run in this arm (cuSOLVER/cuSPARSE/cuBLAS + the reference's own)",
     }
 
 
@@ -598,8 +754,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="scpnrh", choices=sorted(WORKLOADS) + ["bnb"])
-    ap.add_argument("--slots", type=int, default=16, help="bnb: concurrent node LPs per GPU")
+    ap.add_argument("--workload", default="scpnrh", choices=sorted(ORLIB) + sorted(WORKLOADS) + ["bnb"])
+    ap.add_argument("--ref-iters", type=int, default=6,
+                    help="--impl reference: iterations of each LP the reference's CUDA solver is sampled over")
+    ap.add_argument("--slots", type=int, default=32, help="bnb: concurrent node LPs per GPU")
+    ap.add_argument("--bnb-instance", default="scpnre1", help="bnb: OR-Library instance (tests/golden/<name>.npz)")
+    ap.add_argument("--node-lp", default="reference", choices=["reference", "converged"],
+                    help="bnb: node LP configuration - the reference's (gap-stagnation exit, window 5, 1 %%) or to mu <= 1e-4")
+    ap.add_argument("--no-bnb-block", action="store_true", help="skip the B&B block of the default line")
+    ap.add_argument("--bnb-rounds", type=int, default=8, help="rounds per instance in the B&B block of the default line")
     ap.add_argument("--host-heuristics", action="store_true",
                     help="bnb: branching rule and rounding/repair heuristic on the host (NumPy) instead of the device kernel")
     ap.add_argument("--stream-factor", type=int, default=0,

@@ -1,9 +1,24 @@
 #!/usr/bin/env bash
-# last check of the round: the GPU suite, smoke() and one bench line with the library as committed
+# One GPU pass: the GPU suite, smoke(), the reference arm (short) and one default bench line.
+#   bash scripts/gpu_round.sh <tag> [bench args...]
+tag=${1:-round}; shift || true
 mkdir -p gpurun_out
 {
-  echo "== pytest gpu all"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+  echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu --durations=8 2>&1 | tail -16
   echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-  echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pcg-block 2> gpurun_out/bench_o.err | tee gpurun_out/bench_o.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['e2e']['value'],1), round(d['loop_ms_per_lp'],3), {k:round(v['ms']*1e3,1) for k,v in d['phases'].items()}, d['concurrent_lps']['value'])"
-} > gpurun_out/round48.log 2>&1
-cat gpurun_out/round48.log
+  echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2> gpurun_out/${tag}_ref.err | tee gpurun_out/${tag}_ref.json | cut -c1-600
+  echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 "$@" 2> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench.json | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'loop_ms',round(d['loop_ms_per_lp'],3), d['config']['workload'])
+print({k:round(v['ms']*1e3,1) for k,v in d['phases'].items()})
+print('roofline',{k:(round(v,4) if isinstance(v,float) else v) for k,v in d['roofline'].items() if k in ('kernel','achieved','peak','frac','peak_source')})
+print('whole_iteration',d['roofline'].get('whole_iteration'))
+print('concurrent',d.get('concurrent_lps',{}).get('value'))
+for k,v in (d.get('bnb') or {}).items(): print('bnb',k,{a:v.get(a) for a in ('value','nodes','lp_iterations_per_node','lp_device_ms_per_node','incumbent','root_bound','model','error')}, v.get('rank0'))
+print('pcg',{k:d.get('pcg_50kx1M',{}).get(k) for k in ('cg_iteration_us','lp_solve','error')})
+print('cpu',d.get('cpu_baseline'))
+"
+  tail -5 gpurun_out/${tag}_bench.err
+} > gpurun_out/${tag}.log 2>&1
+cat gpurun_out/${tag}.log

@@ -48,6 +48,53 @@ def build_branch_model(base: ScpModel, decisions: Sequence[Tuple[int, int]]) -> 
                     np.concatenate([base.c, np.zeros(k)]), np.concatenate([base.b, fix]), base.name + f"+{k}br")
 
 
+def greedy_cover(base: ScpModel) -> Tuple[float, Optional[np.ndarray]]:
+    """The reference's first incumbent (greedy_set_cover_heuristic, sypha_preprocessor.cpp:11-96): columns sorted
+    by (cost ascending, rows covered descending) - full ties here by column index, the reference leaves them to
+    std::sort - and scanned once; a column is taken when it covers a row that is still uncovered."""
+    m, n0 = base.m, base.n_orig
+    mask = (base.inds < n0) & (base.vals > 0.0)
+    rows = np.repeat(np.arange(m), np.diff(base.offs))[mask]
+    cols = base.inds[mask]
+    order = np.argsort(cols, kind="stable")
+    col_rows, col_ptr = rows[order], np.concatenate([[0], np.cumsum(np.bincount(cols, minlength=n0))])
+    cnt = np.diff(col_ptr)
+    covered = np.zeros(m, dtype=bool)
+    left, total, x = m, 0.0, np.zeros(n0)
+    for j in np.lexsort((np.arange(n0), -cnt, base.c[:n0])):
+        if left <= 0:
+            break
+        r = col_rows[col_ptr[j]:col_ptr[j + 1]]
+        new = r[~covered[r]]
+        if len(new):
+            covered[new] = True
+            left -= len(new)
+            total += float(base.c[j])
+            x[j] = 1.0
+    return (total, x) if left == 0 else (math.inf, None)
+
+
+def reduce_by_incumbent(base: ScpModel, incumbent: float, tol: float = 1e-12) -> Tuple[ScpModel, np.ndarray]:
+    """Drop every original column whose cost alone reaches the incumbent (SyphaNodeSparse::reduceByIncumbent,
+    sypha_node_sparse.cpp:284-332, called at bnb_driver.cpp:297-306): the node LPs of configs[4] are solved on
+    this model, not on the file's (scpnre1: 5000 -> 1775 columns).  Returns (reduced model, kept -> original
+    column index)."""
+    n0, m = base.n_orig, base.m
+    keep = np.nonzero(base.c[:n0] + tol < incumbent)[0]
+    if len(keep) == n0 or len(keep) == 0 or not math.isfinite(incumbent):
+        return base, np.arange(n0)
+    new_of = np.full(base.n, -1, dtype=np.int64)
+    new_of[keep] = np.arange(len(keep))
+    new_of[n0:] = len(keep) + np.arange(base.n - n0)
+    ent_keep = new_of[base.inds] >= 0
+    row_of = np.repeat(np.arange(m), np.diff(base.offs))
+    offs = np.concatenate([[0], np.cumsum(np.bincount(row_of[ent_keep], minlength=m))]).astype(np.int32)
+    red = ScpModel(m, len(keep) + (base.n - n0), len(keep), offs, new_of[base.inds[ent_keep]].astype(np.int32),
+                   base.vals[ent_keep].copy(), np.concatenate([base.c[keep], base.c[n0:]]), base.b.copy(),
+                   base.name + f"[{len(keep)} of {n0} columns]")
+    return red, keep
+
+
 class CoverHeuristic:
     """Nearest-integer rounding of the LP point, greedy repair of uncovered rows by cost per newly covered
     row (gains kept up to date incrementally: O(nnz) per call), then removal of redundant columns (most
@@ -118,6 +165,7 @@ class BnbStats:
     integral: int = 0
     rounds: int = 0
     incumbent: float = math.inf
+    greedy_incumbent: float = math.inf
     lp_device_ms: float = 0.0
     kernels_launched: int = 0
     delta_rows: int = 0
@@ -127,6 +175,8 @@ class BnbStats:
     nodes_sent: int = 0
     nodes_received: int = 0
     maxiter_nodes: int = 0          # node LPs that stopped at the iteration cap
+    gap_stalled_nodes: int = 0      # node LPs that left through the gap-stagnation exit (kept, parent's bound)
+    exchange_wait_ms: float = 0.0   # host time blocked in inter-rank collectives (this rank's idle time)
     round_max_iterations: int = 0   # sum over rounds of the longest LP of the window (what a round waits for)
     round_ms: list = dataclasses.field(default_factory=list)
 
@@ -137,7 +187,8 @@ class BatchedBnb:
     def __init__(self, base: ScpModel, slots: int = 8, device: int = 0, max_iter: int = 100,
                  exchange=None, integer_costs: bool = True, device_nodes: bool = True, max_depth: int = 64,
                  heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1,
-                 share_gpu: bool = True, poll_every: int = 1):
+                 share_gpu: bool = True, poll_every: int = 1, node_lp: str = "reference", async_exchange=None,
+                 rebalance_min_imbalance: Optional[int] = None):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
@@ -147,10 +198,17 @@ class BatchedBnb:
         # poll_every > 1: the host enqueues that many iterations per LP before it reads the scalar block back
         # (kernels of an LP that has finished return at once), halving the host work per iteration of a window
         self.env = SyphaEnvironment(cudaDeviceId=device, pollEvery=max(1, poll_every))
-        # The reference runs node LPs with a gap-stagnation early exit (bnb_driver.cpp:835-837) and prunes with
-        # whatever dual objective the LP stopped at - not a bound before convergence (53.08 vs the
-        # LP optimum 48.12 on scpnrh1).  Here node LPs run to mu <= mu_tol and only converged LPs bound.
-        self.cfg = SolverExecutionConfig(maxIterations=max_iter, gapStagnation=SolverGapStagnationConfig(False, 0, 0.0))
+        # node LP configuration.  "reference": what the reference's driver passes for every node
+        # (bnb_driver.cpp:833-837): gap-stagnation early exit on, window kBnbGapStallBranchIters = 5, minimum
+        # improvement kBnbGapStallMinImprovPct = 1 % (sypha_environment_defaults.h:34-35).  "converged": every node
+        # LP runs to mu <= mu_tol.  Either way only a CONVERGED LP with dual <= primal bounds its node
+        # (boundIsReliableForPruning, bnb_driver.cpp:866-873); any other successful LP keeps its parent's bound
+        # and is still branched on.
+        if node_lp not in ("reference", "converged"):
+            raise ValueError("node_lp must be 'reference' or 'converged'")
+        self.node_lp = node_lp
+        gs = SolverGapStagnationConfig(True, 5, 1.0) if node_lp == "reference" else SolverGapStagnationConfig(False, 0, 0.0)
+        self.cfg = SolverExecutionConfig(maxIterations=max_iter, gapStagnation=gs)
         self.slots = slots
         self.ws: List[IpmWorkspace] = []
         self.base_node = SyphaNodeSparse.from_csr(base.m, base.n, base.n_orig, base.offs, base.inds, base.vals,
@@ -177,6 +235,11 @@ class BatchedBnb:
         self.rebalance = rebalance
         self.rebalance_every = max(1, rebalance_every)
         self.global_open: Optional[int] = None
+        # bnb_exchange.AsyncBoundExchange: objective-only exchange without a per-round barrier; replaces
+        # `exchange` (blocking, carries the vector every round) when given
+        self.async_exchange = async_exchange
+        self.rebalance_min_imbalance = slots // 2 if rebalance_min_imbalance is None else rebalance_min_imbalance
+        self.global_processed: Optional[int] = None
         self.stats = BnbStats()
         # optional: incumbent heuristics of round r on host threads WHILE the GPU solves round r+1 (the ctypes
         # call releases the GIL); results are folded in at a fixed point (after that solve), so the search stays
@@ -185,6 +248,30 @@ class BatchedBnb:
         import concurrent.futures
         self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=heuristic_threads) if heuristic_threads > 0 else None
         self._pending = []
+
+    @classmethod
+    def with_reference_presolve(cls, model: ScpModel, **kw) -> "BatchedBnb":
+        """The prelude of the reference's driver that shapes its node LPs (bnb_driver.cpp:262-306): greedy cover
+        as the first incumbent, then every column whose cost reaches it is dropped.  The search runs on the
+        reduced model; ``incumbent_in_input_space()`` maps the answer back."""
+        obj, x = greedy_cover(model)
+        red, keep = reduce_by_incumbent(model, obj)
+        drv = cls(red, **kw)
+        drv.input_model, drv.kept_cols = model, keep
+        if x is not None:
+            drv.incumbent, drv.incumbent_x = obj, x[keep]        # the greedy cover only uses columns cheaper than itself
+            drv.stats.greedy_incumbent = obj
+        return drv
+
+    def incumbent_in_input_space(self) -> Optional[np.ndarray]:
+        if self.incumbent_x is None:
+            return None
+        keep = getattr(self, "kept_cols", None)
+        if keep is None:
+            return self.incumbent_x
+        x = np.zeros(self.input_model.n_orig)
+        x[keep] = self.incumbent_x
+        return x
 
     def _fold_pending(self):
         for fut in self._pending:
@@ -200,8 +287,8 @@ class BatchedBnb:
 
     # a node whose bound cannot beat the incumbent is dropped (integer costs: bound rounds up)
     def _prunable(self, bound: float) -> bool:
-        if not math.isfinite(self.incumbent):
-            return False
+        if not math.isfinite(self.incumbent) or not math.isfinite(bound):
+            return bound == math.inf
         # the LP objective at mu <= 1e-4 is good to ~1e-5 relative: keep a 1e-4 safety margin
         bound = bound - 1e-4 * max(1.0, abs(bound))
         b = math.ceil(bound) if self.integer_costs else bound
@@ -210,6 +297,22 @@ class BatchedBnb:
     def _offer(self, obj: float, x: Optional[np.ndarray]):
         if x is not None and obj < self.incumbent:
             self.incumbent, self.incumbent_x = obj, x
+
+    def _node_bound(self, nd: BnbNode, ok: bool, reason: int, primal: float, dual: float) -> Optional[float]:
+        """The reference's node rule (bnb_driver.cpp:843-877).  None: the LP failed (status != SUCCESSFUL) and the
+        non-root node is skipped.  Otherwise the node's dual bound: the LP's dual objective when the bound is
+        reliable (CONVERGED, finite, dual <= primal), else the parent's bound - a MAX_ITER or GAP_STALLED node is
+        kept and branched on."""
+        if not ok:
+            self.stats.infeasible += 1
+            return None
+        reliable = (reason == TERM_CONVERGED and np.isfinite(dual) and np.isfinite(primal)
+                    and dual <= primal + 1e-9 * max(1.0, abs(primal)))
+        if reason == TERM_MAX_ITER:
+            self.stats.maxiter_nodes += 1
+        elif reason == TERM_GAP_STALLED:
+            self.stats.gap_stalled_nodes += 1
+        return max(nd.parent_bound, dual) if reliable else nd.parent_bound
 
     def _branch_from_device(self, nd: BnbNode, slot: int, bound: float, feasible: bool, cover_obj: float,
                             branch_var: int, branch_frac: float, rounded_obj: float):
@@ -255,17 +358,15 @@ class BatchedBnb:
                 self.device_nodes = self.device_heuristics = False      # the slots no longer hold the base model
             self._fold_pending()               # heuristics of the previous round (ran beside this solve)
             self.stats.round_max_iterations += max(r.iterations for r in results)
-            self.stats.maxiter_nodes += sum(1 for r in results if r.terminationReason == TERM_MAX_ITER)
             for slot, (nd, res) in enumerate(zip(batch, results)):
                 self.stats.processed += 1
                 self.stats.lp_iterations += res.iterations
                 self.stats.lp_device_ms += res.msStart + res.msSetup + res.msLoop
                 self.stats.kernels_launched += int(res.kernelsLaunched)
-                ok = res.status == CODE_SUCCESSFUL and res.terminationReason == TERM_CONVERGED
-                if not ok or not np.isfinite(res.dualObj):
-                    self.stats.infeasible += 1                 # failed non-root node is skipped (bnb_driver.cpp:844-859)
+                bound = self._node_bound(nd, res.status == CODE_SUCCESSFUL, res.terminationReason, res.primalObj,
+                                         res.dualObj)
+                if bound is None:                              # failed non-root node is skipped (bnb_driver.cpp:844-859)
                     continue
-                bound = max(nd.parent_bound, min(res.dualObj, res.primalObj))
                 if not nd.decisions:
                     self.stats.root_bound = bound
                 if self._prunable(bound):
@@ -299,6 +400,17 @@ class BatchedBnb:
         return len(batch)
 
     def _collectives(self):
+        ax = self.async_exchange
+        if ax is not None:
+            # post this round's (incumbent, open, processed); act on the gather posted `lag` rounds ago, which
+            # every rank reads identically - so every rank adopts the same bound and takes the same decision to
+            # rebalance, without waiting for anybody's current round
+            t0 = time.perf_counter()
+            ax.post(self.incumbent, len(self.frontier), self.stats.processed)
+            for rows in ax.collect():
+                self._apply_gather(rows)
+            self.stats.exchange_wait_ms += 1e3 * (time.perf_counter() - t0)
+            return
         if self.exchange is not None:                          # every rank calls it once per round
             self.incumbent, self.incumbent_x = self.exchange(self.incumbent, self.incumbent_x)
         if self.rebalance is not None and self.stats.rounds % self.rebalance_every == 0:
@@ -307,6 +419,36 @@ class BatchedBnb:
                 self.frontier = collections.deque(BnbNode(d, b) for d, b in nodes)
             self.stats.nodes_sent += sent
             self.stats.nodes_received += recv
+
+    def _apply_gather(self, rows):
+        """rows: [world, 3] = (incumbent objective, open nodes, processed nodes) of every rank at one round."""
+        best = float(rows[:, 0].min())
+        if best < self.incumbent:                              # somebody else's incumbent: only its value prunes
+            self.incumbent, self.incumbent_x = best, None
+        sizes = [int(v) for v in rows[:, 1].tolist()]
+        self.global_open = sum(sizes)
+        self.global_processed = int(rows[:, 2].sum())
+        if self.rebalance is not None and max(sizes) - min(sizes) > self.rebalance_min_imbalance:
+            # every rank saw the same sizes, so every rank enters the (blocking) donation here
+            nodes, _total, sent, recv = self.rebalance([(nd.decisions, nd.parent_bound) for nd in self.frontier])
+            if sent or recv:
+                self.frontier = collections.deque(BnbNode(d, b) for d, b in nodes)
+            self.stats.nodes_sent += sent
+            self.stats.nodes_received += recv
+
+    def finish_exchange(self):
+        """End of a multi-rank search: drain the posted gathers and fetch the best incumbent with its vector."""
+        ax = self.async_exchange
+        if ax is None:
+            return
+        for rows in ax.collect(drain=True):
+            best = float(rows[:, 0].min())
+            if best < self.incumbent:
+                self.incumbent, self.incumbent_x = best, None
+        own = self.incumbent if self.incumbent_x is not None else math.inf
+        best, bx, _owner = ax.final_incumbent(own, self.incumbent_x, self.base.n_orig)
+        if bx is not None and best <= self.incumbent:
+            self.incumbent, self.incumbent_x = best, bx
 
     def stream_round(self, node_limit: int) -> int:
         """Continuous batching (``sb200_solve_stream``): up to ``node_limit`` nodes are started, each slot taking
@@ -369,12 +511,9 @@ class BatchedBnb:
                 st.lp_iterations += r.iterations
                 st.lp_device_ms += r.ms_start + r.ms_setup + r.ms_loop
                 st.kernels_launched += int(r.kernels_launched) + 1
-                st.maxiter_nodes += 1 if r.reason == TERM_MAX_ITER else 0
-                ok = r.status == L.SB200_OK and r.reason == TERM_CONVERGED
-                if not ok or not np.isfinite(r.dual_obj):
-                    st.infeasible += 1
+                bound = self._node_bound(nd, r.status == L.SB200_OK, r.reason, r.primal_obj, r.dual_obj)
+                if bound is None:
                     return
-                bound = max(nd.parent_bound, min(r.dual_obj, r.primal_obj))
                 if not nd.decisions:
                     st.root_bound = bound
                 if self._prunable(bound):
@@ -406,9 +545,20 @@ class BatchedBnb:
         r = 0
         # with several ranks the stop test must be the same on every rank (the collectives of a round are
         # matched): open nodes over ALL ranks, as of the last rebalance
+        multi = self.exchange is not None or self.rebalance is not None or self.async_exchange is not None
+        if multi and rounds is None and self.async_exchange is None and not (self.rebalance is not None and self.rebalance_every == 1):
+            # the collectives of a round are matched calls: a rank-local stop test would leave ranks in different
+            # rounds and deadlock them
+            raise ValueError("multi-rank run to completion needs async_exchange, or rebalance with rebalance_every=1, "
+                             "or a fixed number of rounds")
+
         def more():
             if rounds is not None:
                 return r < rounds
+            if self.async_exchange is not None:                # the same lagged gather on every rank
+                if self.global_open is None:
+                    return True
+                return self.global_open > 0 and (self.global_processed or 0) < max_nodes
             if self.rebalance is not None and self.rebalance_every == 1 and self.global_open is not None:
                 return self.global_open > 0
             return bool(self.frontier) and self.stats.processed < max_nodes
@@ -422,6 +572,8 @@ class BatchedBnb:
             if not self.frontier and self._pending:            # last word of the heuristics before stopping
                 self._fold_pending()
         self._fold_pending()
+        if rounds is None:
+            self.finish_exchange()
         self.stats.wall_s += time.perf_counter() - t0
         self.stats.incumbent = self.incumbent
         self.stats.open_nodes = len(self.frontier)

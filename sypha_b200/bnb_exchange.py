@@ -9,6 +9,7 @@ all replicas - plus max/sum reductions of the timing counters for the bench.  Wo
 """
 from __future__ import annotations
 
+import collections
 import math
 from typing import Optional, Sequence
 
@@ -146,3 +147,60 @@ def rebalance_frontier(nodes: list, max_depth: int, min_imbalance: int = 1, grou
             keep.append((dec, bound))
             received += 1
     return keep, total, sent, received
+
+
+class AsyncBoundExchange:
+    """Incumbent bounds between ranks WITHOUT a per-round barrier (BASELINE.json north_star item 4: NCCL only
+    carries incumbent bounds and pruning information).
+
+    Every round a rank posts one non-blocking ``all_gather`` of three doubles - its incumbent objective, its
+    number of open nodes and its processed-node count - and collects the gather it posted ``lag`` rounds earlier,
+    which by then has normally completed: the host never waits on the slowest rank's current round, ranks may
+    drift up to ``lag`` rounds apart, and because every rank reads the SAME gathered rows for round r they all
+    take the same decisions from them (adopt the best bound, rebalance the frontiers, stop).  The incumbent
+    VECTOR does not travel during the search - only its 8-byte objective prunes - and is fetched once at the end
+    from the rank that owns it (``final_incumbent``).
+
+    Over NCCL the gather runs on NCCL's own stream and its result reaches the host through a pinned buffer; over
+    gloo (CPU tests) the tensors are host tensors."""
+
+    WORDS = 3
+
+    def __init__(self, lag: int = 2, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = _dev(group)
+        self.lag = max(0, int(lag))
+        self.pending = collections.deque()
+        self.posted = 0
+        self.bytes_posted = 0
+        self.wait_s = 0.0          # host time spent blocked in collect(): the rank's idle time due to the exchange
+
+    def post(self, incumbent: float, open_nodes: int, processed: int):
+        src = torch.tensor([incumbent, float(open_nodes), float(processed)], dtype=torch.float64).to(self.dev)
+        out = torch.empty(self.world * self.WORDS, dtype=torch.float64, device=self.dev)
+        work = dist.all_gather_into_tensor(out, src, group=self.group, async_op=True)
+        self.pending.append((work, out, src))
+        self.posted += 1
+        self.bytes_posted += 8 * self.WORDS
+
+    def collect(self, drain: bool = False):
+        """-> list of gathered [world, 3] tensors (host) that are due: everything older than ``lag`` rounds,
+        or everything posted when ``drain``."""
+        import time as _t
+        due = []
+        while self.pending and (drain or len(self.pending) > self.lag):
+            work, out, _src = self.pending.popleft()
+            t0 = _t.perf_counter()
+            work.wait()
+            rows = out.cpu().view(self.world, self.WORDS)
+            self.wait_s += _t.perf_counter() - t0
+            due.append(rows)
+        return due
+
+    def final_incumbent(self, obj: float, x, n: int):
+        """End of the search: the best objective over all ranks and its vector, from the owning rank."""
+        xt = None if x is None else torch.as_tensor(x, dtype=torch.float64)
+        best, bx, owner = exchange_incumbent(obj, xt, n, group=self.group)
+        return best, (None if bx is None else bx.cpu().numpy()), owner

@@ -97,3 +97,32 @@ def gen_scp(m, n, density, seed) -> ScpModel:
     cnt = np.bincount(rows, minlength=m)
     costs = r.integers(1, 101, n).astype(np.float64)
     return _standard_form(m, n, cols, cnt, costs, f"gen_scp({m},{n},{density},{seed})")
+
+
+def load_npz(path) -> ScpModel:
+    """An OR-Library instance from the compact archive the repository ships its instances in (``m``, ``n_orig``,
+    ``costs``, ``row_offs``, ``col_inds`` of A0 - tests/golden/*.npz, written by tests/golden/make_golden.py from
+    the reference's data/ files); the same standard form as ``read_scp``."""
+    z = np.load(path, allow_pickle=False)
+    m, n0 = int(z["m"]), int(z["n_orig"])
+    offs = z["row_offs"].astype(np.int64)
+    return _standard_form(m, n0, z["col_inds"].astype(np.int64), np.diff(offs), z["costs"].astype(np.float64),
+                          str(path))
+
+
+def write_scp(mdl: ScpModel, path) -> None:
+    """OR-Library text form of a standard-form model whose last entry per row is the surplus column (the inverse
+    of ``read_scp``): what the reference's own CLI reads (model_reader.cpp:90-174)."""
+    n0 = mdl.n_orig
+    costs = mdl.c[:n0]
+    as_int = bool(np.all(costs == np.round(costs)))
+    out = [f" {mdl.m} {n0}"]
+    for a in range(0, n0, 12):
+        out.append(" " + " ".join(str(int(v)) if as_int else repr(float(v)) for v in costs[a:a + 12]))
+    for i in range(mdl.m):
+        cols = mdl.inds[mdl.offs[i]:mdl.offs[i + 1] - 1] + 1
+        out.append(f" {len(cols)}")
+        for a in range(0, len(cols), 12):
+            out.append(" " + " ".join(map(str, cols[a:a + 12])))
+    with open(path, "w") as fh:
+        fh.write("\n".join(out) + "\n")

@@ -58,6 +58,17 @@ def known_lp_optima():
     return out
 
 
+def known_ip_optima():
+    """name -> integer optimum (SCIP, status OPTIMAL) held by the reference:
+    benchmark/results/benchmark_results_with_ip.csv, columns ip_status / ip_objective."""
+    out = {}
+    with open(REF / "benchmark/results/benchmark_results_with_ip.csv") as fh:
+        for row in csv.DictReader(fh):
+            if row.get("ip_status") == "OPTIMAL":
+                out[row["instance"].replace(".txt", "")] = float(row["ip_objective"])
+    return out
+
+
 def run_one(name, large):
     import interior_point as ip
     import model_importer as mi
@@ -125,6 +136,8 @@ def main():
         run_one(nm, nm in LARGE)
     with open(REPO / "tests/golden/lp_optima.json", "w") as fh:
         json.dump(known_lp_optima(), fh, indent=0, sort_keys=True)
+    with open(REPO / "tests/golden/ip_optima.json", "w") as fh:
+        json.dump(known_ip_optima(), fh, indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -91,3 +91,52 @@ def test_transfer_plan_is_balanced_and_minimal():
     assert targets == [2, 1, 1, 1, 1, 1, 1, 1] and sum(k for _, _, k in moves) == 8
     assert all(s == 3 for s, _, _ in moves)
     assert plan_transfers([5, 5])[1] == [] and plan_transfers([6, 5])[1] == []
+
+
+def _async_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sypha_b200 import bnb_exchange as ex
+    ax = ex.AsyncBoundExchange(lag=2)
+    seen = []
+    for r in range(5):
+        # rank 1 finds 30 in round 1, rank 0 finds 28 in round 3
+        inc = math.inf
+        if rank == 1 and r >= 1:
+            inc = 30.0
+        if rank == 0 and r >= 3:
+            inc = 28.0
+        ax.post(inc, open_nodes=10 * rank + r, processed=r + 1)
+        for rows in ax.collect():
+            seen.append(rows.tolist())
+    tail = [rows.tolist() for rows in ax.collect(drain=True)]
+    x = torch.full((3,), 7.0 + rank, dtype=torch.float64) if rank == 0 else None
+    final = ax.final_incumbent(28.0 if rank == 0 else math.inf, x, 3)
+    q.put((rank, {"seen": seen, "tail": tail, "final": (final[0], final[1].tolist(), final[2]),
+                  "posted": ax.posted, "bytes": ax.bytes_posted}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_async_bound_exchange_world2():
+    """Every rank reads the same lagged rows: round r's gather is collected in round r + lag on both ranks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_async_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    inf = math.inf
+    expect = [[[inf, r, r + 1], [30.0 if r >= 1 else inf, 10 + r, r + 1]] for r in range(5)]
+    expect[3][0][0] = expect[4][0][0] = 28.0
+    for r in range(world):
+        assert res[r]["seen"] == expect[:3]            # rounds 0..2 are due by round 4 with lag 2
+        assert res[r]["tail"] == expect[3:]
+        assert res[r]["final"] == (28.0, [7.0] * 3, 0)
+        assert res[r]["posted"] == 5 and res[r]["bytes"] == 5 * 24

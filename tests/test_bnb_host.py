@@ -52,3 +52,19 @@ def test_pruning_rule_uses_integer_costs():
     d.incumbent = float("inf")
     assert not d._prunable(1e9)
     assert mdl.m == 10
+
+
+def test_node_bound_rule():
+    """bnb_driver.cpp:843-877 as restated in BatchedBnb._node_bound: a failed LP is skipped, a converged one with
+    dual <= primal bounds the node, a MAX_ITER / GAP_STALLED one keeps its parent's bound and is still branched."""
+    class Dummy(bnb.BatchedBnb):
+        def __init__(self):
+            self.stats = bnb.BnbStats()
+    d = Dummy()
+    nd = bnb.BnbNode(((1, 0),), 40.0)
+    assert d._node_bound(nd, False, bnb.TERM_NUMERICAL, 1.0, 1.0) is None and d.stats.infeasible == 1
+    assert d._node_bound(nd, True, bnb.TERM_CONVERGED, 43.2, 42.9) == 42.9
+    assert d._node_bound(nd, True, bnb.TERM_CONVERGED, 39.0, 38.0) == 40.0
+    assert d._node_bound(nd, True, bnb.TERM_CONVERGED, 42.0, 43.0) == 40.0
+    assert d._node_bound(nd, True, bnb.TERM_MAX_ITER, 50.0, 45.0) == 40.0 and d.stats.maxiter_nodes == 1
+    assert d._node_bound(nd, True, bnb.TERM_GAP_STALLED, 50.0, 45.0) == 40.0 and d.stats.gap_stalled_nodes == 1

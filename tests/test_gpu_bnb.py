@@ -202,3 +202,48 @@ def test_concurrency_hint_changes_the_launch_geometry_not_the_result():
             assert np.array_equal(o[3], out[0][3])
     finally:
         sb.releaseIpmWorkspace(ws)
+
+
+# ---- the real instances, against the integer optima the reference holds ------------------------------------
+@pytest.mark.parametrize("name,node_lp", [("scp41", "reference"), ("scp48", "reference"), ("scp410", "reference"),
+                                          ("scp48", "converged"), ("scp42", "reference"), ("scp46", "converged")])
+def test_batched_bnb_reaches_the_reference_held_ip_optimum(name, node_lp):
+    """scp41 429, scp48 492, scp410 514 ... (benchmark/results/benchmark_results_with_ip.csv:4,5,12 via
+    tests/golden/ip_optima.json), with the reference's node LP configuration (gap-stagnation exit, window 5, 1 %)
+    and with node LPs run to convergence."""
+    import json
+    from conftest import GOLDEN
+    from sypha_b200.instances import load_npz
+    gold = json.load(open(GOLDEN / "ip_optima.json"))[name]
+    mdl = load_npz(GOLDEN / f"{name}.npz")
+    drv = bnb.BatchedBnb(mdl, slots=8, node_lp=node_lp)
+    try:
+        st = drv.run(max_nodes=20000)
+        assert st.open_nodes == 0, f"search did not finish: {st}"
+        assert st.incumbent == gold, (st.incumbent, gold)
+        x = drv.incumbent_x
+        assert np.all(drv.heur.A @ x >= 1.0) and float(mdl.c[:mdl.n_orig] @ x) == gold
+        assert st.root_bound <= gold * (1 + 1e-4)          # the LP dual objective at mu <= 1e-4 (SURVEY F4)
+    finally:
+        drv.close()
+
+
+def test_node_at_the_iteration_cap_is_kept_and_branched_on():
+    """a node LP that stops at max_iter is not a failed LP - the reference bounds it with its parent's
+    bound and branches (bnb_driver.cpp:866-877).  With a cap that some node LPs hit, the search must still end at
+    the MILP optimum (no subtree may be dropped)."""
+    mdl = gen_scp(20, 60, 0.15, 1)
+    opt = _milp_optimum(mdl)
+    hit = 0
+    for cap in (4, 5, 6, 7, 8, 9, 10, 12):
+        drv = bnb.BatchedBnb(mdl, slots=4, max_iter=cap, node_lp="converged")
+        try:
+            st = drv.run(max_nodes=3000)
+            if st.open_nodes:                      # too few converged LPs to bound the tree within the node budget
+                continue
+            assert st.infeasible == 0 or st.incumbent == opt
+            assert st.incumbent == opt, (cap, st.incumbent, opt, st)
+            hit += st.maxiter_nodes
+        finally:
+            drv.close()
+    assert hit > 0, "no cap in the range made a node LP stop at the iteration limit"

@@ -34,6 +34,8 @@ def check_against(res, iters, primal, dual):
 SMALL = ["demo00", "scp_demo06", "scp_demo_tiny03", "scp41", "scp42", "scp46", "scp48", "scp49", "scp410",
          "scp51", "scpclr10", "scpcyc06", "scpa1", "scpb1"]
 LARGE = ["scpnre1", "scpnrf1", "scpnrg1", "scpnrh1", "scpclr13"]
+# the rest of the families the bench runs on (configs[1]: scpnrh1-5; configs[4]: scpnre / scpnrg)
+LARGE += [f"scpnr{f}{i}" for f in "ehg" for i in range(2, 6)]
 
 
 @pytest.mark.parametrize("name", SMALL + LARGE)

@@ -191,11 +191,27 @@ typedef struct sb200_heur_result {
     double cover_obj;           /* cost of the cover (DBL_MAX when infeasible) */
     double branch_frac;         /* |x - rint(x)| at branch_var */
     double rounded_obj;         /* c . rint(x) over the original columns */
+    int nif_feasible;           /* SB200_HEUR_REFERENCE: NearestIntegerFixingHeuristic (rounding + decisions, no repair) covers */
+    int reserved;
+    double nif_obj;             /* its cost (DBL_MAX when it does not cover) */
 } sb200_heur_result;
+/* Which rules sb200_node_heuristics runs.
+ *   SB200_HEUR_REFERENCE (default): the reference's own - fractional candidates by `tol` and the selector
+ *     `branch_rule` (collect_fractional_candidates src/sypha_solver_bnb.cpp:368-382; MostFractionalSelector /
+ *     HighestCostFractionalSelector src/sypha_solver_heuristics.cpp:10-51), NearestIntegerFixingHeuristic (:53-110)
+ *     -> nif_feasible / nif_obj / sb200_get_rounded, DualGuidedCoverRepairHeuristic (:112-292, dual guidance from the
+ *     resident y) -> feasible / cover_obj / n_chosen / repair_steps / sb200_get_cover.  Set-covering models only (unit
+ *     coefficients in the base rows, rhs 1): anything else comes back as repair_steps = -1 with no cover.
+ *   SB200_HEUR_PLAIN: round at 0.5, greedy repair by cost per newly covered row, redundant columns dropped. */
+enum { SB200_HEUR_PLAIN = 0, SB200_HEUR_REFERENCE = 1 };
+enum { SB200_BRANCH_MOST_FRACTIONAL = 0, SB200_BRANCH_HIGHEST_COST_FRACTIONAL = 1 };
+int sb200_set_heuristic_rules(sb200_ws *ws, int rules, int branch_rule, double integrality_tol);
 /* runs the kernel for each of the k workspaces (their last solve must have finished) concurrently, then waits */
 int sb200_node_heuristics(sb200_ws **ws, int k, sb200_heur_result *out);
 /* the cover of the last sb200_node_heuristics on this workspace: n_orig bytes of 0/1 */
 int sb200_get_cover(sb200_ws *ws, unsigned char *x_host);
+/* the NearestIntegerFixing rounding of the last sb200_node_heuristics (SB200_HEUR_REFERENCE): n_orig bytes of 0/1 */
+int sb200_get_rounded(sb200_ws *ws, unsigned char *x_host);
 
 /* Throughput hint for workspaces that solve LPs CONCURRENTLY (B&B slots): the data-flow factorisation then
  * launches about (2 x SMs) / concurrent_lps CTAs instead of one per task - a CTA that waits for a dependency

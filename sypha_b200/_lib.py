@@ -52,7 +52,8 @@ class sb200_node_delta(C.Structure):
 
 class sb200_heur_result(C.Structure):
     _fields_ = [("feasible", C.c_int), ("n_chosen", C.c_int), ("branch_var", C.c_int), ("repair_steps", C.c_int),
-                ("cover_obj", C.c_double), ("branch_frac", C.c_double), ("rounded_obj", C.c_double)]
+                ("cover_obj", C.c_double), ("branch_frac", C.c_double), ("rounded_obj", C.c_double),
+                ("nif_feasible", C.c_int), ("reserved", C.c_int), ("nif_obj", C.c_double)]
 
 
 class sb200_scp_model(C.Structure):
@@ -82,6 +83,8 @@ SYMBOLS = {
     "sb200_solve_batch": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_node_delta), C.POINTER(sb200_params),
                                C.POINTER(sb200_result)]),
     "sb200_node_heuristics": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_heur_result)]),
+    "sb200_set_heuristic_rules": (_i, [_vp, _i, _i, C.c_double]),
+    "sb200_get_rounded": (_i, [_vp, _vp]),
     "sb200_get_cover": (_i, [_vp, _vp]),
     "sb200_set_concurrency_hint": (_i, [_vp, _i]),
     "sb200_solve_stream": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_params), NEXT_NODE_FN, NODE_DONE_FN, _vp]),

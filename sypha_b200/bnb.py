@@ -23,8 +23,9 @@ import numpy as np
 
 from .instances import ScpModel
 from .solver import (CODE_SUCCESSFUL, IpmWorkspace, SolverExecutionConfig, SolverGapStagnationConfig,
-                     SyphaEnvironment, SyphaNodeSparse, get_cover, get_primal, initializeIpmWorkspace, node_heuristics,
-                     releaseIpmWorkspace, solve_batch, solve_batch_nodes, workspace_for_nodes)
+                     SyphaEnvironment, SyphaNodeSparse, get_cover, get_primal, get_rounded, initializeIpmWorkspace,
+                     node_heuristics, releaseIpmWorkspace, set_heuristic_rules, solve_batch, solve_batch_nodes,
+                     workspace_for_nodes)
 
 TERM_CONVERGED, TERM_MAX_ITER, TERM_GAP_STALLED, TERM_NUMERICAL = 0, 1, 2, 3
 
@@ -188,7 +189,8 @@ class BatchedBnb:
                  exchange=None, integer_costs: bool = True, device_nodes: bool = True, max_depth: int = 64,
                  heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1,
                  share_gpu: bool = True, poll_every: int = 1, node_lp: str = "reference", async_exchange=None,
-                 rebalance_min_imbalance: Optional[int] = None):
+                 rebalance_min_imbalance: Optional[int] = None, heuristic_rules: str = "reference",
+                 branch_rule: str = "most_fractional"):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
@@ -220,6 +222,13 @@ class BatchedBnb:
                 w = IpmWorkspace()
                 initializeIpmWorkspace(w, device=device)
                 self.ws.append(w)
+        # per-node rules on the device: the reference's own (NearestIntegerFixing, then DualGuidedCoverRepair with the
+        # node's duals; bnb_driver.cpp:879-905 tries them in that order and takes the first that improves) or the
+        # plain rounding / greedy repair of round 1 ("plain", also what device_heuristics=False runs on the host)
+        self.heuristic_rules = heuristic_rules if self.device_heuristics else "plain"
+        if self.device_heuristics:
+            for w in self.ws:
+                set_heuristic_rules(w, self.heuristic_rules, branch_rule, 1e-6)
         if share_gpu and slots > 1:              # K LPs in flight: fewer CTAs per factorisation (throughput over latency)
             from . import _lib as L
             for w in self.ws:
@@ -315,11 +324,15 @@ class BatchedBnb:
         return max(nd.parent_bound, dual) if reliable else nd.parent_bound
 
     def _branch_from_device(self, nd: BnbNode, slot: int, bound: float, feasible: bool, cover_obj: float,
-                            branch_var: int, branch_frac: float, rounded_obj: float):
+                            branch_var: int, branch_frac: float, rounded_obj: float, nif_feasible: bool = False,
+                            nif_obj: float = math.inf):
         """What follows a converged, unpruned node LP when the heuristics ran on the device: incumbent offers
         (the cover, and c.rint(x) for an integral LP point) and the two children.  Shared by the window and the
         continuous drivers."""
-        if feasible and cover_obj < self.incumbent:
+        # heuristics in the reference's order; the first one that improves the incumbent is taken (bnb_driver.cpp:885-903)
+        if nif_feasible and nif_obj < self.incumbent:
+            self._offer(nif_obj, get_rounded(self.ws[slot], self.base.n_orig))
+        elif feasible and cover_obj < self.incumbent:
             self._offer(cover_obj, get_cover(self.ws[slot], self.base.n_orig))
         if branch_var < 0 or branch_frac < 1e-6:           # integral LP point
             self.stats.integral += 1
@@ -376,7 +389,7 @@ class BatchedBnb:
                     h = heur[slot]
                     self.stats.kernels_launched += 1
                     self._branch_from_device(nd, slot, bound, h.feasible, h.coverObj, h.branchVar, h.branchFrac,
-                                             h.roundedObj)
+                                             h.roundedObj, h.nifFeasible, h.nifObj)
                     continue
                 x = res.primalSolution[:self.base.n_orig]
                 zero_fixed = [v for v, f in nd.decisions if f == 0]
@@ -520,7 +533,7 @@ class BatchedBnb:
                     st.pruned_by_bound += 1
                     return
                 self._branch_from_device(nd, slot, bound, bool(h.feasible), h.cover_obj, h.branch_var, h.branch_frac,
-                                         h.rounded_obj)
+                                         h.rounded_obj, bool(h.nif_feasible), h.nif_obj)
             except BaseException as e:
                 failure.append(e)
 

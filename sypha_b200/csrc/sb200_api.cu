@@ -80,7 +80,9 @@ struct sb200_ws
     std::map<int, std::pair<cudaGraphExec_t, long long>> node_graphs;   // iteration graph per depth
     // per-node branching / incumbent kernel (sb200_heur.cu)
     int *heur_list = nullptr, *heur_sorted = nullptr;
-    unsigned char *heur_cover = nullptr;
+    unsigned char *heur_cover = nullptr, *heur_nif = nullptr;
+    int heur_rules = SB200_HEUR_REFERENCE, heur_branch_rule = SB200_BRANCH_MOST_FRACTIONAL;
+    double heur_tol = 1e-6;                 // kBnbIntegralityTol
     sb200_heur_result *heur_out = nullptr, *heur_out_host = nullptr;   // device, pinned
     int heur_cap = 0;
 
@@ -801,7 +803,7 @@ int sb200_ws_destroy(sb200_ws *ws)
     chol_work_free(ws->chol);
     void *ptrs[] = {ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
                     ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams, ws->base_colptr, ws->base_rows,
-                    ws->base_cvals, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out};
+                    ws->base_cvals, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_nif, ws->heur_out};
     if (ws->h_delta) cudaFreeHost(ws->h_delta);
     if (ws->heur_out_host) cudaFreeHost(ws->heur_out_host);
     for (void *p : ptrs)
@@ -1018,6 +1020,7 @@ static int enqueue_node_heuristics(sb200_ws *ws)
         if ((rc = grow(ws, &ws->heur_list, (size_t)n0))) return rc;
         if ((rc = grow(ws, &ws->heur_sorted, (size_t)n0))) return rc;
         if ((rc = grow(ws, &ws->heur_cover, (size_t)n0))) return rc;
+        if ((rc = grow(ws, &ws->heur_nif, (size_t)n0))) return rc;
         if (!ws->heur_out)
         {
             if ((rc = grow(ws, &ws->heur_out, 1))) return rc;
@@ -1026,7 +1029,8 @@ static int enqueue_node_heuristics(sb200_ws *ws)
         ws->heur_cap = n0;
     }
     HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
-               ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out};
+               ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out,
+               ws->heur_rules, ws->heur_branch_rule, ws->heur_tol, ws->V.y, ws->b, ws->csr_vals, ws->csc_vals, ws->heur_nif};
     const int rc = launch_node_heuristics(a, ws->stream);
     if (rc == SB200_ERR_UNSUPPORTED)
         return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
@@ -1152,6 +1156,27 @@ int sb200_get_cover(sb200_ws *ws, unsigned char *x_host)
     WS_TRY(cudaSetDevice(ws->device));
     WS_TRY(cudaMemcpyAsync(x_host, ws->heur_cover, (size_t)ws->n_orig, cudaMemcpyDeviceToHost, ws->stream));
     WS_TRY(cudaStreamSynchronize(ws->stream));
+    return SB200_OK;
+}
+
+int sb200_get_rounded(sb200_ws *ws, unsigned char *x_host)
+{
+    if (!ws || !ws->loaded || !x_host || !ws->heur_nif) return SB200_ERR_INVALID;
+    WS_TRY(cudaSetDevice(ws->device));
+    WS_TRY(cudaMemcpyAsync(x_host, ws->heur_nif, (size_t)ws->n_orig, cudaMemcpyDeviceToHost, ws->stream));
+    WS_TRY(cudaStreamSynchronize(ws->stream));
+    return SB200_OK;
+}
+
+int sb200_set_heuristic_rules(sb200_ws *ws, int rules, int branch_rule, double integrality_tol)
+{
+    if (!ws || (rules != SB200_HEUR_PLAIN && rules != SB200_HEUR_REFERENCE) ||
+        (branch_rule != SB200_BRANCH_MOST_FRACTIONAL && branch_rule != SB200_BRANCH_HIGHEST_COST_FRACTIONAL) ||
+        !(integrality_tol >= 0.0))
+        return SB200_ERR_INVALID;
+    ws->heur_rules = rules;
+    ws->heur_branch_rule = branch_rule;
+    ws->heur_tol = integrality_tol;
     return SB200_OK;
 }
 

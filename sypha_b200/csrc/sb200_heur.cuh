@@ -17,9 +17,16 @@ struct HeurArgs
     int *list, *sorted;               // scratch, n0 ints each
     unsigned char *cover_x;           // out: the cover, n0 bytes
     sb200_heur_result *out;           // out (device)
+    // the reference's rules (SB200_HEUR_REFERENCE) also read:
+    int rules, branch_rule;           // SB200_HEUR_*, SB200_BRANCH_*
+    double tol;                       // integrality tolerance (kBnbIntegralityTol = 1e-6)
+    const double *y_lp;               // dual point (dual guidance)
+    const double *b;                  // right-hand sides (base rows must be 1)
+    const double *row_vals, *col_vals; // CSR / CSC values (base entries of original columns must be 1)
+    unsigned char *nif_x;             // out: the NearestIntegerFixing rounding, n0 bytes
 };
 
-size_t heur_smem_bytes(int m0, int n0);
+size_t heur_smem_bytes(int m0, int n0, int rules);
 int launch_node_heuristics(const HeurArgs &a, cudaStream_t st);
 
 } // namespace sb200

@@ -304,6 +304,23 @@ class NodeHeuristicResult:
     branchFrac: float
     roundedObj: float
     repairSteps: int
+    nifFeasible: bool = False          # NearestIntegerFixingHeuristic (reference rules): rounding + decisions covers
+    nifObj: float = float("inf")
+
+
+HEUR_PLAIN, HEUR_REFERENCE = 0, 1
+BRANCH_RULES = {"most_fractional": 0, "highest_cost_fractional": 1}
+
+
+def set_heuristic_rules(workspace, rules: str = "reference", branch_rule: str = "most_fractional", tol: float = 1e-6):
+    """Which per-node rules ``node_heuristics`` runs on this workspace: the reference's own ("reference":
+    NearestIntegerFixing + DualGuidedCoverRepair, sypha_solver_heuristics.cpp:53-292, selector by
+    ``bnb_var_selection``) or the plain rounding / greedy repair ("plain")."""
+    lib = L.load()
+    rc = lib.sb200_set_heuristic_rules(workspace.handle, HEUR_REFERENCE if rules == "reference" else HEUR_PLAIN,
+                                       BRANCH_RULES[branch_rule], tol)
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_set_heuristic_rules failed (code {rc})")
 
 
 def node_heuristics(workspaces) -> List[NodeHeuristicResult]:
@@ -318,7 +335,7 @@ def node_heuristics(workspaces) -> List[NodeHeuristicResult]:
         msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in workspaces)
         raise Sb200Error(f"sb200_node_heuristics failed (code {rc}): {msgs}")
     return [NodeHeuristicResult(bool(o.feasible), o.cover_obj, o.n_chosen, o.branch_var, o.branch_frac,
-                                o.rounded_obj, o.repair_steps) for o in out]
+                                o.rounded_obj, o.repair_steps, bool(o.nif_feasible), o.nif_obj) for o in out]
 
 
 def get_primal(workspace: IpmWorkspace, n: int) -> np.ndarray:
@@ -338,6 +355,16 @@ def get_cover(workspace: IpmWorkspace, n_orig: int) -> np.ndarray:
     rc = lib.sb200_get_cover(workspace.handle, buf.ctypes.data)
     if rc != L.SB200_OK:
         raise Sb200Error(f"sb200_get_cover failed (code {rc}): {lib.sb200_last_error(workspace.handle).decode()}")
+    return buf.astype(np.float64)
+
+
+def get_rounded(workspace: IpmWorkspace, n_orig: int) -> np.ndarray:
+    """The NearestIntegerFixing rounding of the last ``node_heuristics`` (reference rules), float64, length n_orig."""
+    lib = L.load()
+    buf = np.empty(n_orig, dtype=np.uint8)
+    rc = lib.sb200_get_rounded(workspace.handle, buf.ctypes.data)
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_get_rounded failed (code {rc}): {lib.sb200_last_error(workspace.handle).decode()}")
     return buf.astype(np.float64)
 
 

@@ -108,6 +108,8 @@ def _check_node_heuristics(mdl, decs, max_iter):
     n0 = mdl.n_orig
     steps = []
     try:
+        for w in wss:
+            S.set_heuristic_rules(w, "plain")
         S.solve_batch_nodes(base, decs, cfg, wss, fetch_solutions=False)
         got = S.node_heuristics(wss)
         for dec, ws, h in zip(decs, wss, got):
@@ -161,6 +163,82 @@ def test_node_heuristics_kernel_reports_infeasible_fixings():
     ban = tuple((int(j), 0) for j in row0 if j < mdl.n_orig)       # every column of row 0 fixed to 0
     assert len(ban) <= 64
     _check_node_heuristics(mdl, [ban, ()], 100)
+
+
+def _check_reference_rules(mdl, decs, max_iter, branch_rule="most_fractional"):
+    """sb200_node_heuristics with the reference's rules (the default) against the CPU restatement of
+    sypha_solver_heuristics.cpp (oracle/heur_oracle.c, itself pinned to the reference's own translation unit by
+    tests/test_heuristics_oracle.py) on the same LP points: every decision and both covers identical."""
+    import sypha_b200 as sb
+    from oracle import heuristics as H
+    from oracle import scp_io
+    from sypha_b200 import _lib as L, solver as S
+    env = sb.SyphaEnvironment()
+    cfg = sb.SolverExecutionConfig(maxIterations=max_iter)
+    base = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+    inst = scp_io.ScpInstance(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b)
+    wss = [S.workspace_for_nodes(base, 70) for _ in decs]
+    n0 = mdl.n_orig
+    steps = []
+    try:
+        for w in wss:
+            S.set_heuristic_rules(w, "reference", branch_rule, 1e-6)
+        S.solve_batch_nodes(base, decs, cfg, wss, fetch_solutions=False)
+        got = S.node_heuristics(wss)
+        for dec, ws, h in zip(decs, wss, got):
+            k = len(dec)
+            x, y = np.empty(mdl.n + k), np.empty(mdl.m + k)
+            assert L.load().sb200_get_iterates(ws.handle, x.ctypes.data, y.ctypes.data, None) == L.SB200_OK
+            if not np.all(np.isfinite(x)):
+                continue
+            j, frac = H.select_branch(x, mdl.c, n0, 1e-6, branch_rule)
+            assert h.branchVar == j and h.branchFrac == frac
+            f, obj, sol = H.nearest_integer_fixing(inst, x, dec)
+            assert h.nifFeasible == f
+            assert np.array_equal(S.get_rounded(ws, n0), sol)
+            if f:
+                assert h.nifObj == obj
+            f, obj, sol, st = H.dual_guided_cover_repair(inst, x, y[:mdl.m], dec)
+            assert h.feasible == f, (h, f, obj)
+            if f:
+                assert h.coverObj == obj and h.repairSteps == st and h.nChosen == int(sol.sum())
+                assert np.array_equal(S.get_cover(ws, n0), sol)
+            steps.append(st)
+    finally:
+        for w in wss:
+            sb.releaseIpmWorkspace(w)
+    return steps
+
+
+def test_reference_rules_kernel_at_the_lp_optimum():
+    mdl = gen_scp(120, 900, 0.04, 11)
+    decs = [(), ((5, 1), (17, 0), (400, 1)), tuple((3 * i + 1, i % 2) for i in range(40)), ((7, 0),)]
+    _check_reference_rules(mdl, decs, 100)
+    _check_reference_rules(mdl, decs[:2], 100, "highest_cost_fractional")
+
+
+@pytest.mark.parametrize("max_iter", [2, 5, 12])
+def test_reference_rules_kernel_long_repairs_and_dual_guidance(max_iter):
+    """LP points 2, 5 and 12 iterations old: few columns at 1, so the dual-guided repair builds most of the cover
+    (scores (rows + sum of duals) / cost with real duals), plus tied unit-ish costs and real instances."""
+    from conftest import GOLDEN
+    from sypha_b200.instances import load_npz
+    mdl = gen_scp(200, 3000, 0.02, 4)
+    steps = _check_reference_rules(mdl, [(), tuple((11 * i, i % 2) for i in range(30)), ((1, 1), (2, 0))], max_iter)
+    ties = gen_scp(150, 1200, 0.03, 8)
+    ties.c[:ties.n_orig] = 1.0 + (np.arange(ties.n_orig) % 3)
+    steps += _check_reference_rules(ties, [(), ((0, 0), (1, 0), (2, 0))], max_iter)
+    steps += _check_reference_rules(load_npz(GOLDEN / "scp41.npz"), [(), ((10, 0), (200, 1))], max_iter)
+    red, _ = bnb.reduce_by_incumbent(load_npz(GOLDEN / "scpnre1.npz"), 38.0)
+    steps += _check_reference_rules(red, [(), ((3, 0), (900, 1), (1700, 0))], max_iter)
+    assert max(steps) >= 8, steps
+
+
+def test_reference_rules_kernel_reports_infeasible_fixings():
+    mdl = gen_scp(40, 200, 0.08, 5)
+    row0 = mdl.inds[mdl.offs[0]:mdl.offs[1]]
+    ban = tuple((int(j), 0) for j in row0 if j < mdl.n_orig)       # every column of row 0 fixed to 0
+    _check_reference_rules(mdl, [ban, ()], 100)
 
 
 @pytest.mark.parametrize("shape", [(30, 120, 0.1, 2), (40, 200, 0.08, 5)])
@@ -230,20 +308,25 @@ def test_batched_bnb_reaches_the_reference_held_ip_optimum(name, node_lp):
 
 def test_node_at_the_iteration_cap_is_kept_and_branched_on():
     """a node LP that stops at max_iter is not a failed LP - the reference bounds it with its parent's
-    bound and branches (bnb_driver.cpp:866-877).  With a cap that some node LPs hit, the search must still end at
-    the MILP optimum (no subtree may be dropped)."""
-    mdl = gen_scp(20, 60, 0.15, 1)
-    opt = _milp_optimum(mdl)
-    hit = 0
-    for cap in (4, 5, 6, 7, 8, 9, 10, 12):
-        drv = bnb.BatchedBnb(mdl, slots=4, max_iter=cap, node_lp="converged")
+    bound and branches (bnb_driver.cpp:866-877).  On scp48 (root LP 14 iterations, node LPs 8-15) a cap in between
+    makes SOME node LPs stop at the limit; the search must still end at the optimum the reference holds (492): no
+    subtree may be dropped."""
+    import json
+    from conftest import GOLDEN
+    from sypha_b200.instances import load_npz
+    gold = json.load(open(GOLDEN / "ip_optima.json"))["scp48"]
+    mdl = load_npz(GOLDEN / "scp48.npz")
+    hit = finished = 0
+    for cap in range(8, 16):
+        drv = bnb.BatchedBnb(mdl, slots=8, max_iter=cap, node_lp="converged")
         try:
-            st = drv.run(max_nodes=3000)
+            st = drv.run(max_nodes=4000)
             if st.open_nodes:                      # too few converged LPs to bound the tree within the node budget
                 continue
-            assert st.infeasible == 0 or st.incumbent == opt
-            assert st.incumbent == opt, (cap, st.incumbent, opt, st)
+            finished += 1
+            assert st.infeasible == 0
+            assert st.incumbent == gold, (cap, st.incumbent, gold, st)
             hit += st.maxiter_nodes
         finally:
             drv.close()
-    assert hit > 0, "no cap in the range made a node LP stop at the iteration limit"
+    assert finished > 0 and hit > 0, (finished, hit)

@@ -501,22 +501,57 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_evt.set()
     sampler.join(timeout=2)
 
-    # ---- secondary: the same resident LPs solved CONCURRENTLY (one stream each, sb200_solve_batch) -----
+    # ---- secondary: THROUGHPUT form - K LPs of the same workload in flight, each solved whole by one thread block
+    #      in one launch (csrc/sb200_cta.cu; sb200_solve_batch over K workspaces, results read back, host clock) ----
     batch_block = None
-    if rank == 0 and not args.no_batch_block and N_INSTANCES > 1:
-        from sypha_b200.solver import solve_batch
-        solve_batch(nodes, cfg, wss)                                   # warm-up
+    if rank == 0 and not args.no_batch_block and models[0].m <= 2048:
+        from sypha_b200.solver import set_solver_form, solve_batch
+        K = args.tp_slots
+        tp_ws, tp_nodes = [], []
+        for i in range(K):
+            w = sb.IpmWorkspace()
+            sb.initializeIpmWorkspace(w, device=local_rank)
+            mdl = models[i % N_INSTANCES]
+            nd = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+            nd.copyModelOnDevice(w)
+            set_solver_form(w, "throughput")
+            tp_ws.append(w)
+            tp_nodes.append(nd)
+        solve_batch(tp_nodes, cfg, tp_ws)                              # warm-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        reps, b_iters = 3, 0
+        reps, b_iters, b_launch = 3, 0, 0
         for _ in range(reps):
-            b_iters += sum(r.iterations for r in solve_batch(nodes, cfg, wss))
+            rs = solve_batch(tp_nodes, cfg, tp_ws)
+            b_iters += sum(r.iterations for r in rs)
+            b_launch += sum(r.kernelsLaunched for r in rs)
         torch.cuda.synchronize()
         b_el = time.perf_counter() - t0
-        batch_block = {"concurrent_lps": N_INSTANCES, "value": b_iters / b_el, "unit": "iter/s",
-                       "ms_per_batch": 1e3 * b_el / reps,
-                       "note": "throughput with the instances' LPs in flight together (host clock, results read back); "
-                               "the headline value is one LP at a time"}
+        ms = C.c_double()
+        ph = []
+        for q in range(8):
+            lib.sb200_time_phase(tp_ws[K // 2].handle, 100 + q, 1, C.byref(ms))
+            ph.append(ms.value)
+        it_mid = rs[K // 2].iterations
+        mm = models[0].m
+        fl = mm ** 3 / 3.0
+        per_it = {nm: 1e3 * v / max(it_mid, 1) for nm, v in zip(("assembly", "factorisation", "solves", "A_v", "At_v", "vector"), ph[:6])}
+        batch_block = {
+            "form": "one thread block per LP, one launch per LP (sb200_set_solver_form THROUGHPUT)",
+            "concurrent_lps": K, "value": b_iters / b_el, "unit": "iter/s", "ms_per_batch": 1e3 * b_el / reps,
+            "lp_per_sec": K * reps / b_el, "gpu_launches": int(b_launch),
+            "us_per_iteration_inside_one_block": per_it, "whole_lp_ms_inside_one_block": ph[7],
+            "roofline": {"kernel": "factorisation phase of k_ipm_cta (left-looking 128x64 DMMA accumulators)", "bound": "tensor",
+                         "flops_per_iteration": fl,
+                         "per_sm": {"achieved_gflops": fl / per_it["factorisation"] / 1e3 if per_it["factorisation"] else None,
+                                    "peak_gflops": 1e3 * fp64_peak / 148.0,
+                                    "frac": (fl / per_it["factorisation"] / 1e3) / (1e3 * fp64_peak / 148.0) if per_it["factorisation"] else None},
+                         "whole_gpu": {"achieved_tflops": b_iters * fl / b_el / 1e12, "peak": fp64_peak,
+                                       "frac": b_iters * fl / b_el / 1e12 / fp64_peak,
+                                       "note": "factorisation flops of ALL phases' wall time: the other phases run on the same blocks"}},
+            "note": "throughput with K LPs in flight (host clock, results read back); the headline value is one LP at a time"}
+        for w in tp_ws:
+            sb.releaseIpmWorkspace(w)
 
     # ---- secondary: B&B nodes/s on scpnre1 and scpnrg1 at THIS N (configs[4]; every rank takes part) ----
     bnb_block = None
@@ -757,7 +792,8 @@ def main():
     ap.add_argument("--workload", default="scpnrh", choices=sorted(ORLIB) + sorted(WORKLOADS) + ["bnb"])
     ap.add_argument("--ref-iters", type=int, default=6,
                     help="--impl reference: iterations of each LP the reference's CUDA solver is sampled over")
-    ap.add_argument("--slots", type=int, default=32, help="bnb: concurrent node LPs per GPU")
+    ap.add_argument("--slots", type=int, default=128, help="bnb: concurrent node LPs per GPU (one thread block each)")
+    ap.add_argument("--tp-slots", type=int, default=128, help="LPs in flight in the throughput block of the default line")
     ap.add_argument("--bnb-instance", default="scpnre1", help="bnb: OR-Library instance (tests/golden/<name>.npz)")
     ap.add_argument("--node-lp", default="reference", choices=["reference", "converged"],
                     help="bnb: node LP configuration - the reference's (gap-stagnation exit, window 5, 1 %%) or to mu <= 1e-4")

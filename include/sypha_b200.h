@@ -219,6 +219,17 @@ int sb200_get_rounded(sb200_ws *ws, unsigned char *x_host);
  * the single-LP geometry.  Cached iteration graphs are dropped. */
 int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps);
 
+/* Shape of the solve.  SB200_FORM_LATENCY (default): one LP spread over the whole GPU, ~12 kernels per iteration
+ * replayed from a CUDA graph - the fastest way to ONE optimum.  SB200_FORM_THROUGHPUT: the whole LP (starting point,
+ * every iteration, termination test) is ONE launch of ONE thread block (sb200_cta.cu) - several times slower for one
+ * LP, but 148 of them run side by side with no launch, host round trip or inter-block wait per phase: the form for
+ * B&B node LPs and batched relaxations (sb200_set_concurrency_hint with more than one LP selects it).  Needs the
+ * sparse-assembly + Cholesky strategy on a unit-coefficient model with at most 2048 rows (otherwise the latency form
+ * runs); the starting point is not copied out (x0_host / y0_host / s0_host must be NULL) and the stop flag is not
+ * polled inside an LP. */
+enum { SB200_FORM_LATENCY = 0, SB200_FORM_THROUGHPUT = 1 };
+int sb200_set_solver_form(sb200_ws *ws, int form);
+
 /* Continuous batching of B&B node LPs over k workspaces that hold the same base model: whenever a slot is
  * free `next(user, slot, &delta)` is asked for a node (return 1 with the decision list filled in - the arrays
  * are copied before `next` returns control a second time - or 0 if there is none right now); the node's LP is

@@ -13,6 +13,7 @@
 #include "sb200_chol.cuh"
 #include "sb200_pcg.cuh"
 #include "sb200_heur.cuh"
+#include "sb200_cta.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -81,6 +82,7 @@ struct sb200_ws
     // per-node branching / incumbent kernel (sb200_heur.cu)
     int *heur_list = nullptr, *heur_sorted = nullptr;
     unsigned char *heur_cover = nullptr, *heur_nif = nullptr;
+    double *heur_score = nullptr;
     int heur_rules = SB200_HEUR_REFERENCE, heur_branch_rule = SB200_BRANCH_MOST_FRACTIONAL;
     double heur_tol = 1e-6;                 // kBnbIntegralityTol
     sb200_heur_result *heur_out = nullptr, *heur_out_host = nullptr;   // device, pinned
@@ -93,6 +95,11 @@ struct sb200_ws
     long long cg_graph_kernels = 0;
     int cg_graph_chunk = 0;
     const double *cg_graph_dscale = nullptr;
+
+    // throughput form: the whole LP by one CTA in one launch (sb200_cta.cu)
+    int solver_form = SB200_FORM_LATENCY;
+    CtaLp *cta_dev = nullptr, *cta_host = nullptr;     // device, pinned
+    bool cta_launched = false;
 
     // async solve state
     sb200_params params{};
@@ -543,6 +550,14 @@ int ensure_iter_graph(sb200_ws *ws)
     return SB200_OK;
 }
 
+// the one-CTA solver needs the compact symbolic structure (unit products, 2-byte ids), the sparse-assembly +
+// Cholesky strategy and a matrix whose solve vectors fit shared memory
+bool cta_eligible(const sb200_ws *ws)
+{
+    return ws->strategy == SB200_STRATEGY_CHOLESKY && ws->pat.term16 && ws->pat.chunk_ptr && ws->pat.pad_id >= 0 &&
+           ws->mpad <= CTA_MAX_MPAD && ws->chol.linv && ws->csr_offs && ws->csc_colptr;
+}
+
 // ---- solve state machine ------------------------------------------------------------------------
 int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
 {
@@ -573,6 +588,46 @@ int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
 
     WS_TRY(cudaEventRecord(ws->ev[0], st));
     launch_reset_scalars(ws->sc, st);
+
+    ws->cta_launched = false;
+    if (ws->solver_form == SB200_FORM_THROUGHPUT && cta_eligible(ws) &&
+        !(res && (res->x0_host || res->y0_host || res->s0_host)))
+    {   // one launch, one CTA: starting point, loop and termination test on the device (sb200_cta.cu)
+        if (!ws->cta_dev)
+        {
+            WS_TRY(cudaMalloc(&ws->cta_dev, sizeof(CtaLp)));
+            WS_TRY(cudaMallocHost(&ws->cta_host, sizeof(CtaLp)));
+        }
+        CtaLp &c = *ws->cta_host;
+        c.V = V;
+        c.P = ws->dparams;
+        c.csr_offs = ws->csr_offs; c.csr_inds = ws->csr_inds; c.csr_vals = ws->csr_vals;
+        c.csc_colptr = ws->csc_colptr; c.csc_rows = ws->csc_rows; c.csc_vals = ws->csc_vals;
+        c.n_pairs = ws->pat.n_pairs;
+        c.chunk_ptr = ws->pat.chunk_ptr;
+        c.term8 = reinterpret_cast<const uint4 *>(ws->pat.term16);
+        c.nd = ws->pat.pad_id + 1;
+        c.ones = ws->ones_n;
+        c.base_m = ws->node_k ? ws->base_m : ws->m;
+        c.base_n = ws->node_k ? ws->base_n : ws->n;
+        c.node_k = ws->node_k;
+        c.d_var = ws->d_var; c.d_coef = ws->d_coef;
+        c.base_colptr = ws->base_colptr; c.base_rows = ws->base_rows; c.base_cvals = ws->base_cvals;
+        c.M = ws->M;
+        c.ld = ws->mpad;
+        c.linv = ws->chol.linv;
+        WS_TRY(cudaMemcpyAsync(ws->cta_dev, ws->cta_host, sizeof(CtaLp), cudaMemcpyHostToDevice, st));
+        WS_TRY(cudaEventRecord(ws->ev[1], st));
+        WS_TRY(cudaEventRecord(ws->ev[2], st));
+        const int rc = launch_ipm_cta(ws->cta_dev, 1, st);
+        if (rc) return fail(ws, rc, "sb200_solve: launch of the one-CTA solver failed");
+        WS_TRY(cudaGetLastError());
+        ws->cta_launched = true;
+        ws->enqueued = ws->params.max_iter;        // nothing left to enqueue: solve_step only requests the scalar block
+        ws->active = true;
+        ws->sc_host->done = 0;
+        return SB200_OK;
+    }
 
     // ---- starting point (sypha_solver_init.cpp:543-652), D = I ---------------------------------
     int rc;
@@ -803,9 +858,11 @@ int sb200_ws_destroy(sb200_ws *ws)
     chol_work_free(ws->chol);
     void *ptrs[] = {ws->csr_offs, ws->csr_inds, ws->csr_vals, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
                     ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams, ws->base_colptr, ws->base_rows,
-                    ws->base_cvals, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_nif, ws->heur_out};
+                    ws->base_cvals, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_nif, ws->heur_score, ws->heur_out};
     if (ws->h_delta) cudaFreeHost(ws->h_delta);
     if (ws->heur_out_host) cudaFreeHost(ws->heur_out_host);
+    if (ws->cta_dev) cudaFree(ws->cta_dev);
+    if (ws->cta_host) cudaFreeHost(ws->cta_host);
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ws->sc_host) cudaFreeHost(ws->sc_host);
@@ -1021,6 +1078,7 @@ static int enqueue_node_heuristics(sb200_ws *ws)
         if ((rc = grow(ws, &ws->heur_sorted, (size_t)n0))) return rc;
         if ((rc = grow(ws, &ws->heur_cover, (size_t)n0))) return rc;
         if ((rc = grow(ws, &ws->heur_nif, (size_t)n0))) return rc;
+        if ((rc = grow(ws, &ws->heur_score, (size_t)n0))) return rc;
         if (!ws->heur_out)
         {
             if ((rc = grow(ws, &ws->heur_out, 1))) return rc;
@@ -1030,7 +1088,7 @@ static int enqueue_node_heuristics(sb200_ws *ws)
     }
     HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
                ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out,
-               ws->heur_rules, ws->heur_branch_rule, ws->heur_tol, ws->V.y, ws->b, ws->csr_vals, ws->csc_vals, ws->heur_nif};
+               ws->heur_rules, ws->heur_branch_rule, ws->heur_tol, ws->V.y, ws->b, ws->csr_vals, ws->csc_vals, ws->heur_nif, ws->heur_score};
     const int rc = launch_node_heuristics(a, ws->stream);
     if (rc == SB200_ERR_UNSUPPORTED)
         return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
@@ -1138,7 +1196,8 @@ int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps)
         const char *fs = getenv("SB200_SHARE_FACTOR");
         const int factor = fs ? std::max(1, atoi(fs)) : 2;
         const int slots = factor * (ws->chol.sms > 0 ? ws->chol.sms : 148);
-        limit = std::max(4, slots / concurrent_lps);
+        const char *ms = getenv("SB200_MIN_CTAS");
+        limit = std::max(ms ? std::max(1, atoi(ms)) : 4, slots / concurrent_lps);
     }
     if (limit != ws->chol.grid_limit)
     {
@@ -1147,6 +1206,16 @@ int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps)
         drop_graphs(ws);                       // the launch geometry is part of the captured iteration
         ws->chol.grid_limit = limit;
     }
+    // many LPs in flight: one CTA per LP (sb200_cta.cu) unless SB200_CTA_SOLVER=0 asks for the shared multi-kernel form
+    const char *cs = getenv("SB200_CTA_SOLVER");
+    ws->solver_form = (concurrent_lps > 1 && !(cs && atoi(cs) == 0)) ? SB200_FORM_THROUGHPUT : SB200_FORM_LATENCY;
+    return SB200_OK;
+}
+
+int sb200_set_solver_form(sb200_ws *ws, int form)
+{
+    if (!ws || (form != SB200_FORM_LATENCY && form != SB200_FORM_THROUGHPUT)) return SB200_ERR_INVALID;
+    ws->solver_form = form;
     return SB200_OK;
 }
 
@@ -1224,6 +1293,19 @@ int sb200_model_info(sb200_ws *ws, long long *info, int n_info)
 int sb200_time_phase(sb200_ws *ws, int phase, int reps, double *ms_out)
 {
     if (!ws || !ws->loaded || !ms_out || reps <= 0) return SB200_ERR_INVALID;
+    if (phase >= 100 && phase < 100 + 2 * SB200_TRACE_COLS)
+    {   // 108, 109, 110: the factorisation split into accumulation steps, diagonal tiles, chunk epilogues   // phases of the LAST one-CTA solve on this workspace (sb200_cta.cu leaves them in the last trace row, ns):
+        // 100 assembly, 101 factorisation, 102 solves, 103 A v, 104 A' v + epilogues, 105 vector steps,
+        // 106 starting point, 107 whole LP
+        double ns = 0.0;
+        WS_TRY(cudaSetDevice(ws->device));
+        WS_TRY(cudaStreamSynchronize(ws->stream));
+        WS_TRY(cudaMemcpy(&ns, ws->V.trace + (size_t)(SB200_TRACE_ROWS - 1) * SB200_TRACE_COLS +
+                                   (phase < 108 ? phase - 100 : phase - 108 - SB200_TRACE_COLS), sizeof(double),
+                          cudaMemcpyDeviceToHost));
+        *ms_out = ns * 1e-6;
+        return SB200_OK;
+    }
     if (ws->strategy == SB200_STRATEGY_PCG && (phase == 0 || phase == 1 || phase == 2))
         return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_time_phase: direct-path phase on a PCG model");
     WS_TRY(cudaSetDevice(ws->device));

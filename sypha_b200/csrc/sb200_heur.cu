@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
     int *cover = reinterpret_cast<int *>(ypos + a.m0);                   // [m0]
     int *ug = cover + a.m0;                                              // [n0] uncovered rows a column would cover
     unsigned char *state = reinterpret_cast<unsigned char *>(ug + a.n0); // [n0]
+    unsigned char *dirty = state + a.n0;                                 // [n0] score must be recomputed
     __shared__ MinKey sred[HW];
     __shared__ double sredd[HW];
     __shared__ int s_unc, s_chosen, s_steps, s_bad;
@@ -405,6 +406,7 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
     {
         state[j] = a.x_lp[j] >= 1.0 - tol ? ST_X : 0;
         ug[j] = 0;
+        dirty[j] = 1;
     }
     __syncthreads();
     for (int r = tid; r < a.k; r += HT)
@@ -451,6 +453,10 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
     __syncthreads();
 
     // ---- repair -----------------------------------------------------------------------------------------
+    // A column's score only changes when one of ITS rows gets covered: scores are cached (a.score) and recomputed
+    // for the columns of the rows the last pick covered ("dirty"), from scratch and in row order, so every score is
+    // the number the reference's full rescan would produce.  (The first version rescanned every column every round:
+    // 8 ms per node at scpnrg size, more than the node's LP.)
     int feasible = 1;
     while (true)
     {
@@ -460,14 +466,22 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
         for (int j = tid; j < n0; j += HT)
             if (state[j] == 0 && ug[j] > 0)
             {
-                double dg = 0.0;
-                for (int p = a.col_ptr[j]; p < a.col_ptr[j + 1]; ++p)          // rows ascending: the reference's order
+                double score;
+                if (dirty[j])
                 {
-                    const int i = a.col_rows[p];
-                    if (i < m0 && cover[i] == 0) dg = __dadd_rn(dg, ypos[i]);
+                    double dg = 0.0;
+                    for (int p = a.col_ptr[j]; p < a.col_ptr[j + 1]; ++p)      // rows ascending: the reference's order
+                    {
+                        const int i = a.col_rows[p];
+                        if (i < m0 && cover[i] == 0) dg = __dadd_rn(dg, ypos[i]);
+                    }
+                    const double cost = a.c[j] > 1e-9 ? a.c[j] : 1e-9;
+                    score = __ddiv_rn(__dadd_rn((double)ug[j], dg), cost);
+                    a.score[j] = score;
+                    dirty[j] = 0;
                 }
-                const double cost = a.c[j] > 1e-9 ? a.c[j] : 1e-9;
-                const double score = __ddiv_rn(__dadd_rn((double)ug[j], dg), cost);
+                else
+                    score = a.score[j];
                 if (score > best) { best = score; bj = j; }
             }
         const MinKey k = block_min(-best, bj, sred);
@@ -488,7 +502,11 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
                 for (int p = a.row_ptr[i] + lane; p < a.row_ptr[i + 1]; p += 32)
                 {
                     const int j = a.row_cols[p];
-                    if (j < n0) atomicSub(&ug[j], 1);
+                    if (j < n0)
+                    {
+                        atomicSub(&ug[j], 1);
+                        dirty[j] = 1;
+                    }
                 }
             }
         }
@@ -569,8 +587,8 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
 
 size_t heur_smem_bytes(int m0, int n0, int rules)
 {
-    return (rules == SB200_HEUR_REFERENCE ? sizeof(double) * (size_t)m0 : 0) + sizeof(int) * ((size_t)m0 + (size_t)n0) +
-           (size_t)n0 + 16;
+    return (rules == SB200_HEUR_REFERENCE ? sizeof(double) * (size_t)m0 + (size_t)n0 : 0) +
+           sizeof(int) * ((size_t)m0 + (size_t)n0) + (size_t)n0 + 16;
 }
 
 int launch_node_heuristics(const HeurArgs &a, cudaStream_t st)

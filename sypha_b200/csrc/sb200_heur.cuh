@@ -24,6 +24,7 @@ struct HeurArgs
     const double *b;                  // right-hand sides (base rows must be 1)
     const double *row_vals, *col_vals; // CSR / CSC values (base entries of original columns must be 1)
     unsigned char *nif_x;             // out: the NearestIntegerFixing rounding, n0 bytes
+    double *score;                    // scratch, n0 doubles: cached repair scores
 };
 
 size_t heur_smem_bytes(int m0, int n0, int rules);

@@ -308,6 +308,18 @@ class NodeHeuristicResult:
     nifObj: float = float("inf")
 
 
+FORM_LATENCY, FORM_THROUGHPUT = 0, 1
+
+
+def set_solver_form(workspace, form: str = "latency"):
+    """"latency": one LP over the whole GPU, ~12 kernels per iteration (default).  "throughput": the whole LP by one
+    thread block in one launch (csrc/sb200_cta.cu) - the form for many LPs in flight (B&B nodes)."""
+    lib = L.load()
+    rc = lib.sb200_set_solver_form(workspace.handle, FORM_THROUGHPUT if form == "throughput" else FORM_LATENCY)
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_set_solver_form failed (code {rc})")
+
+
 HEUR_PLAIN, HEUR_REFERENCE = 0, 1
 BRANCH_RULES = {"most_fractional": 0, "highest_cost_fractional": 1}
 

@@ -273,6 +273,7 @@ def test_concurrency_hint_changes_the_launch_geometry_not_the_result():
         out = []
         for hint in (0, 32, 0):
             assert L.load().sb200_set_concurrency_hint(ws.handle, hint) == L.SB200_OK
+            S.set_solver_form(ws, "latency")            # the hint alone would also switch to one thread block per LP
             r = S.solve_batch_nodes(base, [((3, 1), (40, 0))], cfg, [ws])[0]
             out.append((r.iterations, r.primalObj, r.dualObj, r.primalSolution.copy()))
         for o in out[1:]:

@@ -746,11 +746,14 @@ def run_reference(args, rank, world):
         files.append(tmp / f"inst{i}.txt")
         write_scp(mdl, files[-1])
 
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)      # torchrun pins it to 1: the host-side start point (the GSL
+                                                           # stand-in, outside the metric) would take 18 s per step
     def one(i):
         t0 = time.perf_counter()
         r = subprocess.run([str(binary), "--model", "scp", "--input-file", str(files[i % len(files)]),
                             "--mehrotra-max-iter", str(args.ref_iters), "--disable-bnb", "--verbosity", "5"],
-                           capture_output=True, text=True, timeout=900)
+                           capture_output=True, text=True, timeout=900, env=env)
         out = r.stdout + r.stderr
         if r.returncode != 0:
             raise RuntimeError(f"reference binary failed ({r.returncode}): {out[-800:]}")

@@ -258,7 +258,7 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
 
     drv = bnb.BatchedBnb.with_reference_presolve(
         mdl, slots=slots, device=local_rank, device_heuristics=not args.host_heuristics, share_gpu=not args.no_share,
-        poll_every=1, node_lp=args.node_lp, async_exchange=ax,
+        poll_every=1, node_lp=args.node_lp, async_exchange=ax, warm_start=args.warm_start,
         rebalance=rebalance if (dist is not None and not args.no_donation) else None)
     red = drv.base
     # every rank expands the same first levels (deterministic, no exchange yet), then keeps its round-robin share
@@ -309,7 +309,7 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
             "model": {"m": int(red.m), "n_orig": int(red.n_orig), "n_orig_input": int(mdl.n_orig), "nnz": int(red.nnz),
                       "greedy_incumbent": drv.stats.greedy_incumbent},
             "incumbent": drv.incumbent, "root_bound": drv.stats.root_bound,
-            "slots_per_gpu": slots, "node_lp": args.node_lp,
+            "slots_per_gpu": slots, "node_lp": args.node_lp, "warm_start": bool(args.warm_start),
             "batching": (f"continuous (sb200_solve_stream), {stream_factor} x slots nodes per round"
                          if stream_factor > 0 else "windows of K nodes (sb200_solve_batch)"),
             "exchange": ({"kind": "asynchronous all_gather of (incumbent objective, open nodes, processed nodes) per "
@@ -800,6 +800,7 @@ def main():
     ap.add_argument("--bnb-instance", default="scpnre1", help="bnb: OR-Library instance (tests/golden/<name>.npz)")
     ap.add_argument("--node-lp", default="reference", choices=["reference", "converged"],
                     help="bnb: node LP configuration - the reference's (gap-stagnation exit, window 5, 1 %%) or to mu <= 1e-4")
+    ap.add_argument("--warm-start", action="store_true", help="bnb: children start from their parent's iterate (sb200_node_delta.warm_start)")
     ap.add_argument("--no-bnb-block", action="store_true", help="skip the B&B block of the default line")
     ap.add_argument("--bnb-rounds", type=int, default=8, help="rounds per instance in the B&B block of the default line")
     ap.add_argument("--host-heuristics", action="store_true",

@@ -119,6 +119,8 @@ typedef struct sb200_result {
     double *x0_host;            /* out: starting point (node.hX/hY/hS), may be NULL */
     double *y0_host;
     double *s0_host;
+    double *xys_device;         /* out, DEVICE memory, may be NULL: the final x[n] | y[m] | s[n] packed - what a child node
+                                   of the B&B takes as its warm start (sb200_node_delta.warm_start) */
 } sb200_result;
 
 /* one B&B node = base model + appended rows (build_branch_model, src/sypha_solver_bnb.cpp:453-468):
@@ -128,6 +130,18 @@ typedef struct sb200_node_delta {
     const int *var;
     const double *coef;
     const double *rhs;
+    /* Warm start of a child LP from its parent's iterate (the reference starts every node cold,
+     * src/sypha_solver.cpp:77).  warm_start: DEVICE pointer to the parent's final x[warm_n] | y[warm_m] | s[warm_n]
+     * (sb200_result.xys_device of the parent's solve; the parent's rows and columns are the first warm_m / warm_n of the
+     * child) or NULL for the Mehrotra starting point.  The child starts from x = max(x_parent, warm_floor),
+     * s = max(s_parent, warm_floor), y = y_parent, new rows and columns at warm_floor / 0 - the parent's optimal
+     * face pulled back into the interior - and skips the starting-point factorisation.  Honoured by the throughput form
+     * (SB200_FORM_THROUGHPUT); the latency form starts cold. */
+    const double *warm_start;
+    int warm_n, warm_m;
+    double warm_floor;          /* <= 0: 0.1 */
+    double *export_xys;         /* DEVICE, may be NULL: receives this node's final x | y | s (sb200_solve_batch /
+                                   sb200_solve_stream set sb200_result.xys_device from it) - the warm start of its children */
 } sb200_node_delta;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+tag=${1:-warm}
+mkdir -p gpurun_out
+{
+  echo "== pytest cta + refbuild(scpnre1)"; timeout 900 python -m pytest tests/test_gpu_cta.py "tests/test_refbuild.py::test_batched_cpp_node_loop_on_scpnre1" -x -q 2>&1 | tail -12
+  for inst in scpnre1 scpnrg1; do for extra in "" "--warm-start" "--stream-factor 4" "--warm-start --stream-factor 4" "--slots 148 --warm-start --stream-factor 4"; do
+    echo "== bnb $inst $extra"; timeout 600 python bench.py --workload bnb --bnb-instance $inst --steps 8 --warmup 3 $extra 2>>gpurun_out/${tag}.err | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); b=d['bnb']
+print({a:(round(b[a],2) if isinstance(b[a],float) else b[a]) for a in ('value','nodes','lp_iterations_per_node','lp_device_ms_per_node','ms_per_round','incumbent')}); print('  ', b['rank0'])"
+  done; done
+  echo "== C++ batched driver"; python - <<'PY'
+import sys, subprocess
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from conftest import load_golden
+from oracle import scp_io
+for nm in ("scpnre1", "scpnrg1"):
+    inst, _ = load_golden(nm)
+    scp_io.write_scp_text(inst, f"/tmp/{nm}.txt")
+    for extra in (["--no-preprocessing"], []):
+        r = subprocess.run(["oracle/_ref/bnb_batched_b200", f"/tmp/{nm}.txt", "--max-iter", "100", "--max-nodes", "3000", "--slots", "128", "--time-limit", "60"] + extra, capture_output=True, text=True, timeout=300)
+        print(nm, extra, r.stdout.strip()[-600:], r.stderr[-300:])
+PY
+  tail -5 gpurun_out/${tag}.err
+} > gpurun_out/${tag}.log 2>&1
+cat gpurun_out/${tag}.log

@@ -42,12 +42,15 @@ class sb200_result(C.Structure):
         ("strategy_used", C.c_int), ("cg_iterations", C.c_longlong), ("kernels_launched", C.c_longlong),
         ("x_host", C.c_void_p), ("y_host", C.c_void_p), ("s_host", C.c_void_p),
         ("x0_host", C.c_void_p), ("y0_host", C.c_void_p), ("s0_host", C.c_void_p),
+        ("xys_device", C.c_void_p),
     ]
 
 
 class sb200_node_delta(C.Structure):
     _fields_ = [("n_extra_rows", C.c_int), ("var", C.POINTER(C.c_int)), ("coef", C.POINTER(C.c_double)),
-                ("rhs", C.POINTER(C.c_double))]
+                ("rhs", C.POINTER(C.c_double)),
+                ("warm_start", C.c_void_p), ("warm_n", C.c_int), ("warm_m", C.c_int), ("warm_floor", C.c_double),
+                ("export_xys", C.c_void_p)]
 
 
 class sb200_heur_result(C.Structure):

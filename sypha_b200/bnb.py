@@ -155,6 +155,7 @@ class CoverHeuristic:
 class BnbNode:
     decisions: Tuple[Tuple[int, int], ...]
     parent_bound: float
+    warm: Optional[tuple] = None        # (device tensor x | y | s of the parent's LP, n, m): the child's warm start
 
 
 @dataclasses.dataclass
@@ -190,7 +191,7 @@ class BatchedBnb:
                  heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1,
                  share_gpu: bool = True, poll_every: int = 1, node_lp: str = "reference", async_exchange=None,
                  rebalance_min_imbalance: Optional[int] = None, heuristic_rules: str = "reference",
-                 branch_rule: str = "most_fractional"):
+                 branch_rule: str = "most_fractional", warm_start: bool = False, warm_floor: float = 0.1):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
@@ -225,6 +226,12 @@ class BatchedBnb:
         # per-node rules on the device: the reference's own (NearestIntegerFixing, then DualGuidedCoverRepair with the
         # node's duals; bnb_driver.cpp:879-905 tries them in that order and takes the first that improves) or the
         # plain rounding / greedy repair of round 1 ("plain", also what device_heuristics=False runs on the host)
+        # children start from their parent's final iterate floored at `warm_floor` instead of the Mehrotra starting
+        # point (sb200_node_delta.warm_start): fewer iterations per node LP and no starting-point
+        # factorisation.  Needs the device-resident node path and the throughput form (several slots).
+        self.warm_start = warm_start and self.device_nodes
+        self.warm_floor = warm_floor
+        self._export: List = [None] * slots
         self.heuristic_rules = heuristic_rules if self.device_heuristics else "plain"
         if self.device_heuristics:
             for w in self.ws:
@@ -340,8 +347,26 @@ class BatchedBnb:
                 x = get_primal(self.ws[slot], self.base.n + len(nd.decisions))[:self.base.n_orig]
                 self._offer(rounded_obj, np.round(x))
             return
-        self.frontier.append(BnbNode(nd.decisions + ((branch_var, 0),), bound))
-        self.frontier.append(BnbNode(nd.decisions + ((branch_var, 1),), bound))
+        warm = None
+        if self.warm_start and self._export[slot] is not None:
+            k = len(nd.decisions)
+            warm = (self._export[slot], self.base.n + k, self.base.m + k)
+        self.frontier.append(BnbNode(nd.decisions + ((branch_var, 0),), bound, warm))
+        self.frontier.append(BnbNode(nd.decisions + ((branch_var, 1),), bound, warm))
+
+    def _new_export(self, slot: int, depth: int):
+        """device buffer that receives the node's final x | y | s (kept alive by the children that start from it)"""
+        if not self.warm_start:
+            return None
+        import torch
+        t = torch.empty(2 * (self.base.n + depth) + self.base.m + depth, dtype=torch.float64,
+                        device=torch.device("cuda", self.env.cudaDeviceId))
+        self._export[slot] = t
+        return t.data_ptr()
+
+    @staticmethod
+    def _warm_arg(nd: "BnbNode"):
+        return None if nd.warm is None else (nd.warm[0].data_ptr(), nd.warm[1], nd.warm[2])
 
     def round(self) -> int:
         """Pop up to K nodes, solve their LPs as one batch, branch.  Returns the number processed."""
@@ -356,8 +381,11 @@ class BatchedBnb:
         if batch:
             if self.device_nodes and all(len(nd.decisions) <= self.max_depth for nd in batch):
                 on_dev = self.device_heuristics
+                export = [self._new_export(i, len(nd.decisions)) for i, nd in enumerate(batch)] if self.warm_start else None
+                warm = [self._warm_arg(nd) for nd in batch] if self.warm_start else None
                 results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self.ws,
-                                            fetch_solutions=not on_dev)
+                                            fetch_solutions=not on_dev, warm=warm, export=export,
+                                            warm_floor=self.warm_floor)
                 heur = node_heuristics(self.ws[:len(batch)]) if on_dev else None
                 self.stats.delta_rows += sum(len(nd.decisions) for nd in batch)
             else:
@@ -507,6 +535,13 @@ class BatchedBnb:
                     delta[0].var = var.ctypes.data_as(C.POINTER(C.c_int))
                     delta[0].coef = coef.ctypes.data_as(C.POINTER(C.c_double))
                     delta[0].rhs = fix.ctypes.data_as(C.POINTER(C.c_double))
+                    if self.warm_start:
+                        w = self._warm_arg(nd)
+                        if w is not None:
+                            delta[0].warm_start, delta[0].warm_n, delta[0].warm_m = w
+                            delta[0].warm_floor = self.warm_floor
+                        keep[slot] = keep[slot] + (nd.warm,)            # the parent's buffer lives until this LP is done
+                        delta[0].export_xys = self._new_export(slot, d)
                     in_slot[slot] = nd
                     started[0] += 1
                     st.delta_rows += d

@@ -100,6 +100,9 @@ struct sb200_ws
     int solver_form = SB200_FORM_LATENCY;
     CtaLp *cta_dev = nullptr, *cta_host = nullptr;     // device, pinned
     bool cta_launched = false;
+    const double *warm_ptr = nullptr;                  // parent's x | y | s for the next solve (one use)
+    int warm_n = 0, warm_m = 0;
+    double warm_floor = 0.1;
 
     // async solve state
     sb200_params params{};
@@ -110,6 +113,8 @@ struct sb200_ws
     long long graph_kernel_launches = 0;
     std::vector<double> trace_host;
     int trace_rows = 0;
+    int base_n_or_n() const { return node_k ? base_n : n; }
+    int base_m_or_m() const { return node_k ? base_m : m; }
 };
 
 namespace {
@@ -425,6 +430,15 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
     if (!ws->loaded) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: no model loaded");
     const int k = delta ? delta->n_extra_rows : 0;
     if (k < 0) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: negative row count");
+    ws->warm_ptr = nullptr;
+    if (delta && delta->warm_start && delta->warm_n > 0 && delta->warm_m > 0 && delta->warm_n <= ws->base_n_or_n() + k &&
+        delta->warm_m <= ws->base_m_or_m() + k)
+    {
+        ws->warm_ptr = delta->warm_start;
+        ws->warm_n = delta->warm_n;
+        ws->warm_m = delta->warm_m;
+        ws->warm_floor = delta->warm_floor > 0.0 ? delta->warm_floor : 0.1;
+    }
     if (k == 0 && ws->node_k == 0) return SB200_OK;
     if (ws->strategy != SB200_STRATEGY_CHOLESKY)
         return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_set_node_delta: only the sparse-assembly + Cholesky strategy folds node rows");
@@ -616,6 +630,11 @@ int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
         c.M = ws->M;
         c.ld = ws->mpad;
         c.linv = ws->chol.linv;
+        c.warm = ws->warm_ptr;
+        c.warm_n = ws->warm_n;
+        c.warm_m = ws->warm_m;
+        c.warm_floor = ws->warm_floor;
+        ws->warm_ptr = nullptr;                    // one use
         WS_TRY(cudaMemcpyAsync(ws->cta_dev, ws->cta_host, sizeof(CtaLp), cudaMemcpyHostToDevice, st));
         WS_TRY(cudaEventRecord(ws->ev[1], st));
         WS_TRY(cudaEventRecord(ws->ev[2], st));
@@ -628,6 +647,7 @@ int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
         ws->sc_host->done = 0;
         return SB200_OK;
     }
+    ws->warm_ptr = nullptr;                        // the latency form starts cold
 
     // ---- starting point (sypha_solver_init.cpp:543-652), D = I ---------------------------------
     int rc;
@@ -717,6 +737,12 @@ int solve_finish(sb200_ws *ws, sb200_result *r)
     if (r->x_host) WS_TRY(cudaMemcpyAsync(r->x_host, V.x, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
     if (r->y_host) WS_TRY(cudaMemcpyAsync(r->y_host, V.y, sizeof(double) * ws->m, cudaMemcpyDeviceToHost, st));
     if (r->s_host) WS_TRY(cudaMemcpyAsync(r->s_host, V.s, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
+    if (r->xys_device)
+    {   // the iterate a child node may start from: x | y | s packed, device to device, before the final sync
+        WS_TRY(cudaMemcpyAsync(r->xys_device, V.x, sizeof(double) * ws->n, cudaMemcpyDeviceToDevice, st));
+        WS_TRY(cudaMemcpyAsync(r->xys_device + ws->n, V.y, sizeof(double) * ws->m, cudaMemcpyDeviceToDevice, st));
+        WS_TRY(cudaMemcpyAsync(r->xys_device + ws->n + ws->m, V.s, sizeof(double) * ws->n, cudaMemcpyDeviceToDevice, st));
+    }
     WS_TRY(cudaStreamSynchronize(st));
     const Scalars &sc = *ws->sc_host;
     ws->active = false;
@@ -1037,6 +1063,7 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
             if ((rc = apply_node_delta(wss[i], &deltas[i]))) return abort_batch(wss, k, rc);
     for (int i = 0; i < k; ++i)
     {
+        if (deltas && deltas[i].export_xys && !results[i].xys_device) results[i].xys_device = deltas[i].export_xys;
         if ((rc = solve_begin(wss[i], params, &results[i]))) return abort_batch(wss, k, rc);
         live[i] = 1;
         ++remaining;
@@ -1134,7 +1161,7 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
             if (state[i] == IDLE)
             {
                 if (dry && busy) continue;             // ask again only after some node has been handed back
-                sb200_node_delta d{0, nullptr, nullptr, nullptr};
+                sb200_node_delta d{};
                 if (!next(user, i, &d))
                 {
                     dry = true;
@@ -1142,6 +1169,7 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
                 }
                 if ((rc = apply_node_delta(ws, &d))) return abort_batch(wss, k, rc);
                 res[i] = sb200_result{};
+                res[i].xys_device = d.export_xys;
                 if ((rc = solve_begin(ws, params, &res[i]))) return abort_batch(wss, k, rc);
                 if ((rc = solve_step(ws))) return abort_batch(wss, k, rc);
                 state[i] = SOLVING;

@@ -665,42 +665,62 @@ __global__ void __launch_bounds__(NT, 1) k_ipm_cta(const CtaLp *lps)
     unsigned long long t_last = now_ns();
     const unsigned long long t_begin = t_last;
 
-    // ---- starting point (sypha_solver_init.cpp:543-652): D = I ------------------------------------------------------
     if (tid == 0) s_info = 0;
-    cta_assemble(L, L.ones, smem);
-    cta_potrf(L, smem, &s_fail, &s_info, sub);
-    for (int i = tid; i < mpad; i += NT) V.rhs[i] = i < m ? V.b[i] : 0.0;
-    cta_solve(L, V.rhs, smem);                                             // (A A')^-1 b
-    cta_spmv_csc<CSC_START_X>(L, V.rhs, red, &mn0, &mn1, smem);                  // x~ = A' (.)
-    const double min_x = mn0;
-    cta_spmv_csr(L, V.c, nullptr, V.rhs, 1.0, 0.0, smem);                        // A c
-    cta_solve(L, V.rhs, smem);                                             // y~
-    for (int i = tid; i < m; i += NT) V.y[i] = V.rhs[i];
     __syncthreads();
-    cta_spmv_csc<CSC_START_S>(L, V.y, red, &mn0, &mn1, smem);                    // s~ = c - A' y~
-    const double min_s = mn1;
-    {
-        const double dx = fmax(-1.5 * min_x, 0.0), ds = fmax(-1.5 * min_s, 0.0);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (L.warm)
+    {   // ---- warm start from the parent node's iterate: its optimal face pulled back into the interior ------------------
+        const double *wx = L.warm, *wy = L.warm + L.warm_n, *ws_ = L.warm + L.warm_n + L.warm_m;
+        const double fl = L.warm_floor;
         for (int j = tid; j < n; j += NT)
         {
-            const double xj = V.x[j] + dx, sj = V.s[j] + ds;
-            V.x[j] = xj;
-            V.s[j] = sj;
-            a0 += xj * sj;
-            a1 += xj;
-            a2 += sj;
+            V.x[j] = j < L.warm_n ? fmax(wx[j], fl) : fl;
+            V.s[j] = j < L.warm_n ? fmax(ws_[j], fl) : fl;
         }
-        a0 = cta_sum(a0, red);
-        a1 = cta_sum(a1, red);
-        a2 = cta_sum(a2, red);
-        const double prod = 0.5 * a0, dx2 = prod / a2, ds2 = prod / a1;
-        for (int j = tid; j < n; j += NT)
+        for (int i = tid; i < mpad; i += NT)
         {
-            V.x[j] += dx2;
-            V.s[j] += ds2;
+            if (i < m) V.y[i] = i < L.warm_m ? wy[i] : 0.0;
+            V.rhs[i] = 0.0;
         }
         __syncthreads();
+    }
+    else
+    {
+    // ---- starting point (sypha_solver_init.cpp:543-652): D = I ------------------------------------------------------
+        cta_assemble(L, L.ones, smem);
+        cta_potrf(L, smem, &s_fail, &s_info, sub);
+        for (int i = tid; i < mpad; i += NT) V.rhs[i] = i < m ? V.b[i] : 0.0;
+        cta_solve(L, V.rhs, smem);                                             // (A A')^-1 b
+        cta_spmv_csc<CSC_START_X>(L, V.rhs, red, &mn0, &mn1, smem);                  // x~ = A' (.)
+        const double min_x = mn0;
+        cta_spmv_csr(L, V.c, nullptr, V.rhs, 1.0, 0.0, smem);                        // A c
+        cta_solve(L, V.rhs, smem);                                             // y~
+        for (int i = tid; i < m; i += NT) V.y[i] = V.rhs[i];
+        __syncthreads();
+        cta_spmv_csc<CSC_START_S>(L, V.y, red, &mn0, &mn1, smem);                    // s~ = c - A' y~
+        const double min_s = mn1;
+        {
+            const double dx = fmax(-1.5 * min_x, 0.0), ds = fmax(-1.5 * min_s, 0.0);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int j = tid; j < n; j += NT)
+            {
+                const double xj = V.x[j] + dx, sj = V.s[j] + ds;
+                V.x[j] = xj;
+                V.s[j] = sj;
+                a0 += xj * sj;
+                a1 += xj;
+                a2 += sj;
+            }
+            a0 = cta_sum(a0, red);
+            a1 = cta_sum(a1, red);
+            a2 = cta_sum(a2, red);
+            const double prod = 0.5 * a0, dx2 = prod / a2, ds2 = prod / a1;
+            for (int j = tid; j < n; j += NT)
+            {
+                V.x[j] += dx2;
+                V.s[j] += ds2;
+            }
+            __syncthreads();
+        }
     }
     // ---- initial residuals and mu (sypha_solver.cpp:375-459) ----------------------------------------------------------
     cta_spmv_csc<CSC_RESC>(L, V.y, red, &mn0, &mn1, smem);                       // resC = c - s - A'y

@@ -32,6 +32,10 @@ struct CtaLp
     double *M;                      // mpad x mpad row-major, identity pad; L in place (lower)
     int ld;
     double *linv;                   // [T][64][64] inverses of the diagonal tiles
+    // warm start (sb200_node_delta.warm_start): the parent's x[warm_n] | y[warm_m] | s[warm_n], or nullptr
+    const double *warm;
+    int warm_n, warm_m;
+    double warm_floor;
 };
 
 static constexpr int CTA_MAX_MPAD = 2048;      // vectors of the solves live in shared memory

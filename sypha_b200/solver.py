@@ -381,10 +381,14 @@ def get_rounded(workspace: IpmWorkspace, n_orig: int) -> np.ndarray:
 
 
 def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecutionConfig, workspaces,
-                      fetch_solutions: bool = True):
+                      fetch_solutions: bool = True, warm=None, export=None, warm_floor: float = 0.1):
     """B&B node body, batched and device-resident: workspace i holds the base model; node i = base + one row
     per (var, fix) decision (bnb.cpp:453-468) is formed on the device (``sb200_node_delta``) and the LPs are
-    solved concurrently.  Returns one SolverExecutionResult per node (solutions have the node's dimensions)."""
+    solved concurrently.  Returns one SolverExecutionResult per node (solutions have the node's dimensions).
+
+    ``export[i]``: device address (or None) that receives node i's final x | y | s packed; ``warm[i]``: (device
+    address, n, m) of the PARENT's packed iterate (or None): the child then starts from it instead of the Mehrotra
+    starting point (throughput form only; see sb200_node_delta in the header)."""
     lib = L.load()
     k = len(decisions_list)
     p = _params_from(base, config)
@@ -402,6 +406,11 @@ def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecu
         deltas[i].var = var.ctypes.data_as(C.POINTER(C.c_int))
         deltas[i].coef = coef.ctypes.data_as(C.POINTER(C.c_double))
         deltas[i].rhs = fix.ctypes.data_as(C.POINTER(C.c_double))
+        if warm is not None and warm[i] is not None:
+            deltas[i].warm_start, deltas[i].warm_n, deltas[i].warm_m = warm[i]
+            deltas[i].warm_floor = warm_floor
+        if export is not None and export[i] is not None:
+            res[i].xys_device = export[i]
         if fetch_solutions:
             x, y, s = np.empty(base.ncols + d), np.empty(base.nrows + d), np.empty(base.ncols + d)
             res[i].x_host, res[i].y_host, res[i].s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data

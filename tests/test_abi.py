@@ -32,7 +32,7 @@ def test_struct_layouts_match_c():
     """sizes the C compiler produces for the ABI structs (x86-64 SysV)."""
     assert ctypes.sizeof(_lib.sb200_caps) == 16
     assert ctypes.sizeof(_lib.sb200_params) == 104
-    assert ctypes.sizeof(_lib.sb200_result) == 144
+    assert ctypes.sizeof(_lib.sb200_result) == 152
 
 
 def test_struct_layouts_against_the_c_compiler(tmp_path):

@@ -113,3 +113,66 @@ def test_forms_search_the_same_tree():
         finally:
             os.environ.pop("SB200_CTA_SOLVER", None)
     assert out[0] == out[1] and out[0][1] == 0
+
+
+def test_warm_started_children_need_fewer_iterations():
+    """a child LP started from its parent's final iterate, floored at 0.1 (sb200_node_delta.warm_start),
+    against the same LP from the Mehrotra starting point - on the model the reference's B&B really solves for scpnre1
+    (500 x 1775 after its reductions).  Both runs converge (mu <= 1e-4, dual <= primal); exit objectives of two different
+    trajectories agree to the duality gap the mu-only stop test leaves (n mu / |obj|), not to 1e-6."""
+    from conftest import GOLDEN
+    from sypha_b200.instances import load_npz
+    red, _ = bnb.reduce_by_incumbent(load_npz(GOLDEN / "scpnre1.npz"), 38.0)
+    env = sb.SyphaEnvironment()
+    cfg = sb.SolverExecutionConfig(maxIterations=100)
+    base = sb.SyphaNodeSparse.from_csr(red.m, red.n, red.n_orig, red.offs, red.inds, red.vals, red.c, red.b, env)
+    wss = [S.workspace_for_nodes(base, 16) for _ in range(4)]
+    try:
+        for w in wss:
+            S.set_solver_form(w, "throughput")
+        n, m = red.n, red.m
+        exp0 = torch.empty(2 * n + m, dtype=torch.float64, device="cuda")
+        root = S.solve_batch_nodes(base, [()], cfg, wss[:1], export=[exp0.data_ptr()])[0]
+        assert root.terminationReason == sb.SOLVER_TERM_CONVERGED
+        assert np.array_equal(exp0[:n].cpu().numpy(), root.primalSolution)
+        x0 = root.primalSolution[:red.n_orig]
+        j = int(np.argmax(np.abs(x0 - np.round(x0))))
+        decs = [((j, 0),), ((j, 1),)]
+        cold = S.solve_batch_nodes(base, decs, cfg, wss[:2])
+        exps = [torch.empty(2 * (n + 1) + m + 1, dtype=torch.float64, device="cuda") for _ in decs]
+        warm = S.solve_batch_nodes(base, decs, cfg, wss[2:4], warm=[(exp0.data_ptr(), n, m)] * 2,
+                                   export=[e.data_ptr() for e in exps])
+        total_c = total_w = 0
+        for c, w_ in zip(cold, warm):
+            assert c.terminationReason == w_.terminationReason == sb.SOLVER_TERM_CONVERGED
+            assert w_.mu <= 1e-4 and w_.dualObj <= w_.primalObj + 1e-9
+            gap = 2.0 * (n + 1) * 1e-4
+            assert abs(w_.primalObj - c.primalObj) <= gap and abs(w_.dualObj - c.dualObj) <= gap
+            total_c += c.iterations
+            total_w += w_.iterations
+        assert total_w <= 0.8 * total_c, (total_w, total_c)
+        # second level: children of the x_j = 1 child, from ITS exported iterate
+        x1 = warm[1].primalSolution[:red.n_orig]
+        j2 = int(np.argmax(np.abs(x1 - np.round(x1))))
+        decs2 = [((j, 1), (j2, 0)), ((j, 1), (j2, 1))]
+        cold2 = S.solve_batch_nodes(base, decs2, cfg, wss[:2])
+        warm2 = S.solve_batch_nodes(base, decs2, cfg, wss[2:4], warm=[(exps[1].data_ptr(), n + 1, m + 1)] * 2)
+        assert sum(r.iterations for r in warm2) <= 0.85 * sum(r.iterations for r in cold2)
+        assert all(r.terminationReason == sb.SOLVER_TERM_CONVERGED for r in warm2)
+    finally:
+        for w in wss:
+            sb.releaseIpmWorkspace(w)
+
+
+@pytest.mark.parametrize("name", ["scp41", "scp48", "scp410"])
+def test_warm_started_bnb_reaches_the_ip_optimum(name):
+    import json
+    from conftest import GOLDEN
+    from sypha_b200.instances import load_npz
+    gold = json.load(open(GOLDEN / "ip_optima.json"))[name]
+    drv = bnb.BatchedBnb(load_npz(GOLDEN / f"{name}.npz"), slots=8, warm_start=True)
+    try:
+        st = drv.run(max_nodes=20000)
+        assert st.open_nodes == 0 and st.incumbent == gold, st
+    finally:
+        drv.close()

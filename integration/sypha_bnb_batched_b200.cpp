@@ -289,7 +289,33 @@ SyphaStatus solver_sparse_branch_and_bound_batched(SyphaNodeSparse &node, const 
     S.deadlineMs = limit > 0.0 ? node.timeSolverStart + 1000.0 * limit : 0.0;
     if (S.log) S.log->log(LOG_INFO, "Branch-and-bound started (%d node LPs in flight)", K);
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = sb200_solve_stream(S.ws.data(), K, &p, nextNode, nodeDone, &S);
+    int rc = SB200_OK;
+    if (cfg.continuousBatching)
+        rc = sb200_solve_stream(S.ws.data(), K, &p, nextNode, nodeDone, &S);
+    else
+    {   // windows of up to K nodes (the reference's DeviceNodeWindow, sypha_solver_bnb.cpp:32-69, pops one at a time):
+        // K one-block LPs launched together, the K node kernels behind them, then the host-side node rule
+        std::vector<sb200_node_delta> deltas(static_cast<size_t>(K));
+        std::vector<sb200_result> results(static_cast<size_t>(K));
+        std::vector<sb200_heur_result> heur(static_cast<size_t>(K));
+        while (rc == SB200_OK)
+        {
+            int cnt = 0;
+            while (cnt < K)
+            {
+                deltas[static_cast<size_t>(cnt)] = sb200_node_delta{};
+                if (!nextNode(&S, cnt, &deltas[static_cast<size_t>(cnt)])) break;
+                results[static_cast<size_t>(cnt)] = sb200_result{};
+                ++cnt;
+            }
+            if (cnt == 0) break;
+            rc = sb200_solve_batch(S.ws.data(), cnt, deltas.data(), &p, results.data());
+            if (rc != SB200_OK) break;
+            rc = sb200_node_heuristics(S.ws.data(), cnt, heur.data());
+            if (rc != SB200_OK) break;
+            for (int i = 0; i < cnt; ++i) nodeDone(&S, i, &results[static_cast<size_t>(i)], &heur[static_cast<size_t>(i)]);
+        }
+    }
     const double wallMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc != SB200_OK) fatal("sb200_solve_stream", rc, S.ws[0]);
     node.timeSolverEnd = node.env->timer();

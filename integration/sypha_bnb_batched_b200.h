@@ -14,6 +14,7 @@ struct SyphaBatchedBnbConfig
     int maxNodes = 0;                    // 0: env->getBnbMaxNodes()
     int maxDepth = 64;                   // branch decisions a workspace is sized for
     bool nodeLpToConvergence = false;    // false: the reference's gap-stagnation exit (bnb_driver.cpp:833-837)
+    bool continuousBatching = false;     // true: sb200_solve_stream (a slot takes its next node at once) instead of windows of K
     bool referencePreprocessing = true;  // cost-driven and dominance reductions (bnb_driver.cpp:308-334)
 };
 

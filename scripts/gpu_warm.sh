@@ -2,8 +2,8 @@
 tag=${1:-warm}
 mkdir -p gpurun_out
 {
-  echo "== pytest cta + refbuild(scpnre1)"; timeout 900 python -m pytest tests/test_gpu_cta.py "tests/test_refbuild.py::test_batched_cpp_node_loop_on_scpnre1" -x -q 2>&1 | tail -12
-  for inst in scpnre1 scpnrg1; do for extra in "" "--warm-start" "--stream-factor 4" "--warm-start --stream-factor 4" "--slots 148 --warm-start --stream-factor 4"; do
+  echo "== pytest cta + refbuild(scpnre1)"; timeout 900 python -m pytest tests/test_gpu_cta.py tests/test_gpu_bnb.py "tests/test_refbuild.py::test_batched_cpp_node_loop_on_scpnre1" "tests/test_refbuild.py::test_batched_cpp_node_loop_reaches_the_ip_optimum" -x -q 2>&1 | tail -12
+  for inst in scpnre1 scpnrg1; do for extra in "" "--slots 128" "--stream-factor 4" "--warm-start --stream-factor 4"; do
     echo "== bnb $inst $extra"; timeout 600 python bench.py --workload bnb --bnb-instance $inst --steps 8 --warmup 3 $extra 2>>gpurun_out/${tag}.err | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); b=d['bnb']
@@ -18,7 +18,7 @@ for nm in ("scpnre1", "scpnrg1"):
     inst, _ = load_golden(nm)
     scp_io.write_scp_text(inst, f"/tmp/{nm}.txt")
     for extra in (["--no-preprocessing"], []):
-        r = subprocess.run(["oracle/_ref/bnb_batched_b200", f"/tmp/{nm}.txt", "--max-iter", "100", "--max-nodes", "3000", "--slots", "128", "--time-limit", "60"] + extra, capture_output=True, text=True, timeout=300)
+        r = subprocess.run(["oracle/_ref/bnb_batched_b200", f"/tmp/{nm}.txt", "--max-iter", "100", "--max-nodes", "3000", "--slots", "148", "--time-limit", "60"] + extra, capture_output=True, text=True, timeout=300)
         print(nm, extra, r.stdout.strip()[-600:], r.stderr[-300:])
 PY
   tail -5 gpurun_out/${tag}.err

@@ -85,7 +85,9 @@ struct sb200_ws
     double *heur_score = nullptr;
     int heur_rules = SB200_HEUR_REFERENCE, heur_branch_rule = SB200_BRANCH_MOST_FRACTIONAL;
     double heur_tol = 1e-6;                 // kBnbIntegralityTol
-    sb200_heur_result *heur_out = nullptr, *heur_out_host = nullptr;   // device, pinned
+    sb200_heur_result *heur_out = nullptr, *heur_out_host = nullptr;   // device (unused since the kernel writes the pinned record), pinned
+    int *heur_flag_host = nullptr;          // pinned: the node kernel sets it to heur_seq when its record is complete
+    int heur_seq = 0;
     int heur_cap = 0;
 
     // graph of one IPM iteration (direct strategies)
@@ -113,6 +115,7 @@ struct sb200_ws
     long long graph_kernel_launches = 0;
     std::vector<double> trace_host;
     int trace_rows = 0;
+    bool trace_stale = false;
     int base_n_or_n() const { return node_k ? base_n : n; }
     int base_m_or_m() const { return node_k ? base_m : m; }
 };
@@ -635,6 +638,8 @@ int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
         c.warm_m = ws->warm_m;
         c.warm_floor = ws->warm_floor;
         ws->warm_ptr = nullptr;                    // one use
+        c.export_xys = res ? res->xys_device : nullptr;
+        c.sc_pinned = ws->sc_host;
         WS_TRY(cudaMemcpyAsync(ws->cta_dev, ws->cta_host, sizeof(CtaLp), cudaMemcpyHostToDevice, st));
         WS_TRY(cudaEventRecord(ws->ev[1], st));
         WS_TRY(cudaEventRecord(ws->ev[2], st));
@@ -689,6 +694,11 @@ int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
 int solve_step(sb200_ws *ws)
 {
     cudaStream_t st = ws->stream;
+    if (ws->cta_launched)
+    {   // the kernel mirrors the scalar block into pinned memory itself; the event is for callers that block
+        WS_TRY(cudaEventRecord(ws->ev[3], st));
+        return SB200_OK;
+    }
     const int room = ws->params.max_iter - ws->enqueued;
     const int k = std::min(ws->params.poll_every, std::max(room, 0));
     for (int i = 0; i < k; ++i)
@@ -733,6 +743,40 @@ int solve_finish(sb200_ws *ws, sb200_result *r)
 {
     cudaStream_t st = ws->stream;
     const IpmVecs &V = ws->V;
+    if (ws->cta_launched && !r->x_host && !r->y_host && !r->s_host)
+    {   // one-block solve, nothing to copy out: the kernel left the scalars in the pinned mirror (and the packed
+        // iterate in xys_device) and the caller has seen it finish (event or the mirror's `done`): no copy, no sync
+        const Scalars &sc = *ws->sc_host;
+        ws->active = false;
+        const bool numerical = sc.numerical != 0 || sc.chol_info != 0;
+        int reason = sc.reason;
+        if (numerical) reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
+        const double viol = sc.dual - sc.primal;
+        bool num2 = numerical;
+        if (!numerical && reason != SB200_TERM_CONVERGED && std::isfinite(viol) && viol > 1e6 * std::max(1.0, std::fabs(sc.primal)))
+        {
+            num2 = true;
+            reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
+        }
+        r->status = num2 ? SB200_ERR_NUMERICAL : SB200_OK;
+        r->reason = reason;
+        r->iterations = sc.iter;
+        r->primal_obj = sc.primal;
+        r->dual_obj = sc.dual;
+        r->rel_gap = std::fabs(sc.primal - sc.dual) / std::max(1.0, std::fabs(sc.primal));
+        r->mu = sc.mu;
+        r->strategy_used = ws->strategy;
+        r->cg_iterations = 0;
+        // device time of the LP: the kernel's own clock (%globaltimer around the whole solve, mirrored in sum0)
+        r->ms_start = 0.0;
+        r->ms_setup = 0.0;
+        r->ms_loop = sc.sum0 * 1e-6;
+        r->kernels_launched = (g_launch_count - ws->launches_at_begin) + ws->graph_kernel_launches;
+        ws->trace_rows = std::min(sc.iter, SB200_TRACE_ROWS);
+        ws->trace_stale = true;                 // copied on demand (sb200_get_trace)
+        return SB200_OK;
+    }
+    if (ws->cta_launched && r->xys_device) r->xys_device = nullptr;      // already written by the kernel
     WS_TRY(cudaMemcpyAsync(ws->sc_host, ws->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
     if (r->x_host) WS_TRY(cudaMemcpyAsync(r->x_host, V.x, sizeof(double) * ws->n, cudaMemcpyDeviceToHost, st));
     if (r->y_host) WS_TRY(cudaMemcpyAsync(r->y_host, V.y, sizeof(double) * ws->m, cudaMemcpyDeviceToHost, st));
@@ -783,6 +827,7 @@ int solve_finish(sb200_ws *ws, sb200_result *r)
     cudaEventElapsedTime(&ms, ws->ev[2], ws->ev[3]); r->ms_loop = ms;
     r->kernels_launched = (g_launch_count - ws->launches_at_begin) + ws->graph_kernel_launches;
     ws->trace_rows = std::min(sc.iter, SB200_TRACE_ROWS);
+    ws->trace_stale = false;
     ws->trace_host.resize((size_t)ws->trace_rows * SB200_TRACE_COLS);
     if (ws->trace_rows)
         WS_TRY(cudaMemcpy(ws->trace_host.data(), V.trace, sizeof(double) * ws->trace_host.size(),
@@ -887,6 +932,7 @@ int sb200_ws_destroy(sb200_ws *ws)
                     ws->base_cvals, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_nif, ws->heur_score, ws->heur_out};
     if (ws->h_delta) cudaFreeHost(ws->h_delta);
     if (ws->heur_out_host) cudaFreeHost(ws->heur_out_host);
+    if (ws->heur_flag_host) cudaFreeHost(ws->heur_flag_host);
     if (ws->cta_dev) cudaFree(ws->cta_dev);
     if (ws->cta_host) cudaFreeHost(ws->cta_host);
     for (void *p : ptrs)
@@ -1110,19 +1156,19 @@ static int enqueue_node_heuristics(sb200_ws *ws)
         {
             if ((rc = grow(ws, &ws->heur_out, 1))) return rc;
             WS_TRY(cudaMallocHost(&ws->heur_out_host, sizeof(sb200_heur_result)));
+            WS_TRY(cudaMallocHost(&ws->heur_flag_host, sizeof(int)));
+            *ws->heur_flag_host = 0;
         }
         ws->heur_cap = n0;
     }
     HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
-               ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out,
-               ws->heur_rules, ws->heur_branch_rule, ws->heur_tol, ws->V.y, ws->b, ws->csr_vals, ws->csc_vals, ws->heur_nif, ws->heur_score};
+               ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out_host,
+               ws->heur_rules, ws->heur_branch_rule, ws->heur_tol, ws->V.y, ws->b, ws->csr_vals, ws->csc_vals, ws->heur_nif, ws->heur_score, ws->heur_flag_host, ++ws->heur_seq};
     const int rc = launch_node_heuristics(a, ws->stream);
     if (rc == SB200_ERR_UNSUPPORTED)
         return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
     if (rc) return fail(ws, rc, "sb200_node_heuristics: launch configuration failed");
-    WS_TRY(cudaGetLastError());
-    WS_TRY(cudaMemcpyAsync(ws->heur_out_host, ws->heur_out, sizeof(sb200_heur_result), cudaMemcpyDeviceToHost,
-                           ws->stream));
+    WS_TRY(cudaGetLastError());      // the kernel writes its record straight into the pinned heur_out_host, then heur_flag_host
     return SB200_OK;
 }
 
@@ -1178,9 +1224,16 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
             }
             else if (state[i] == SOLVING)
             {
-                const cudaError_t q = cudaEventQuery(ws->ev[3]);
-                if (q == cudaErrorNotReady) continue;
-                WS_TRY(q);
+                if (ws->cta_launched)
+                {   // one-block LP: the kernel sets the pinned mirror's `done` last - a host memory read, no driver call
+                    if (!*reinterpret_cast<volatile int *>(&ws->sc_host->done)) continue;
+                }
+                else
+                {
+                    const cudaError_t q = cudaEventQuery(ws->ev[3]);
+                    if (q == cudaErrorNotReady) continue;
+                    WS_TRY(q);
+                }
                 int fin = 0;
                 if ((rc = solve_poll(ws, &fin))) return abort_batch(wss, k, rc);
                 if (!fin)
@@ -1191,16 +1244,13 @@ int sb200_solve_stream(sb200_ws **wss, int k, const sb200_params *params, sb200_
                 {
                     if ((rc = solve_finish(ws, &res[i]))) return abort_batch(wss, k, rc);
                     if ((rc = enqueue_node_heuristics(ws))) return abort_batch(wss, k, rc);
-                    WS_TRY(cudaEventRecord(ws->ev[3], ws->stream));
                     state[i] = HEUR;
                 }
                 progressed = true;
             }
             else
             {
-                const cudaError_t q = cudaEventQuery(ws->ev[3]);
-                if (q == cudaErrorNotReady) continue;
-                WS_TRY(q);
+                if (*reinterpret_cast<volatile int *>(ws->heur_flag_host) != ws->heur_seq) continue;    // the node kernel's flag
                 done(user, i, &res[i], ws->heur_out_host);     // may add nodes to the caller's frontier
                 state[i] = IDLE;
                 --busy;
@@ -1281,6 +1331,17 @@ int sb200_get_trace(sb200_ws *ws, double *out, int max_rows)
 {
     if (!ws || !out) return 0;
     const int rows = std::min(max_rows, ws->trace_rows);
+    if (ws->trace_stale)
+    {   // one-block solves leave the trace on the device until somebody asks for it
+        ws->trace_host.resize((size_t)ws->trace_rows * SB200_TRACE_COLS);
+        if (ws->trace_rows)
+        {
+            cudaSetDevice(ws->device);
+            cudaStreamSynchronize(ws->stream);
+            cudaMemcpy(ws->trace_host.data(), ws->V.trace, sizeof(double) * ws->trace_host.size(), cudaMemcpyDeviceToHost);
+        }
+        ws->trace_stale = false;
+    }
     if (rows > 0) memcpy(out, ws->trace_host.data(), sizeof(double) * (size_t)rows * SB200_TRACE_COLS);
     return rows;
 }

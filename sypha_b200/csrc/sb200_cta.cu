@@ -866,6 +866,19 @@ __global__ void __launch_bounds__(NT, 1) k_ipm_cta(const CtaLp *lps)
         }
         PH(5);
     }
+    // the node's final x | y | s for its children (sb200_node_delta.export_xys), written by the kernel itself
+    if (L.export_xys)
+    {
+        double *ex = L.export_xys, *ey = ex + n, *es = ey + m;
+        for (int j = tid; j < n; j += NT)
+        {
+            ex[j] = V.x[j];
+            es[j] = V.s[j];
+        }
+        for (int i = tid; i < m; i += NT) ey[i] = V.y[i];
+    }
+    __threadfence();
+    __syncthreads();
     if (tid == 0)
     {
         ph[7] = (double)(now_ns() - t_begin);
@@ -875,21 +888,37 @@ __global__ void __launch_bounds__(NT, 1) k_ipm_cta(const CtaLp *lps)
         tr[-8] = sub[0];
         tr[-7] = sub[1];
         tr[-6] = sub[2];
-        sc->mu = mu;
-        sc->mu_aff = mu_aff;
-        sc->sigma = sigma;
-        sc->alpha_p = alpha_p;
-        sc->alpha_d = alpha_d;
-        sc->primal = primal;
-        sc->dual = dual;
-        sc->gap = fabs(primal - dual) / fmax(1.0, fabs(primal));
-        sc->best_gap = best_gap;
-        sc->iter = iter;
-        sc->stall = stall;
-        sc->reason = reason;
-        sc->numerical = numerical;
-        sc->chol_info = s_info;
+        // the scalar block twice: in device memory (the other kernels of the library read it there) and in the pinned
+        // host mirror, whose `done` flag - written last, behind a system-scope fence - is what the host polls: no event,
+        // no copy, no stream synchronisation per node LP
+        Scalars *dst[2] = {sc, L.sc_pinned};
+        for (int q = 0; q < 2; ++q)
+        {
+            Scalars *o = dst[q];
+            if (!o) continue;
+            o->mu = mu;
+            o->mu_aff = mu_aff;
+            o->sigma = sigma;
+            o->alpha_p = alpha_p;
+            o->alpha_d = alpha_d;
+            o->primal = primal;
+            o->dual = dual;
+            o->gap = fabs(primal - dual) / fmax(1.0, fabs(primal));
+            o->best_gap = best_gap;
+            o->iter = iter;
+            o->stall = stall;
+            o->reason = reason;
+            o->numerical = numerical;
+            o->chol_info = s_info;
+            o->cg_total = 0;
+            o->sum0 = ph[7];                     // the LP's own wall time in ns (%globaltimer)
+        }
         sc->done = 1;
+        if (L.sc_pinned)
+        {
+            __threadfence_system();
+            *reinterpret_cast<volatile int *>(&L.sc_pinned->done) = 1;
+        }
         (void)s_done;
     }
 }

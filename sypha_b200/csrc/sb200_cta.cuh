@@ -36,6 +36,8 @@ struct CtaLp
     const double *warm;
     int warm_n, warm_m;
     double warm_floor;
+    double *export_xys;             // device: receives the final x | y | s, or nullptr
+    Scalars *sc_pinned;             // pinned host mirror of the scalar block; its `done` is set last
 };
 
 static constexpr int CTA_MAX_MPAD = 2048;      // vectors of the solves live in shared memory

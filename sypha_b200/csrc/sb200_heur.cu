@@ -279,6 +279,11 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics(HeurArgs a)
         a.out->repair_steps = s_steps;
         a.out->nif_feasible = 0;                 // the plain rules have no separate no-repair rounding
         a.out->nif_obj = DBL_MAX;
+        if (a.host_flag)
+        {
+            __threadfence_system();
+            *a.host_flag = a.flag_value;
+        }
     }
 }
 
@@ -596,6 +601,11 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
         a.out->n_chosen = (int)nsel;
         a.out->repair_steps = s_bad ? -1 : s_steps;
         if (s_bad) { a.out->nif_feasible = 0; a.out->nif_obj = DBL_MAX; }
+        if (a.host_flag)
+        {
+            __threadfence_system();
+            *a.host_flag = a.flag_value;
+        }
     }
 }
 

@@ -25,6 +25,8 @@ struct HeurArgs
     const double *row_vals, *col_vals; // CSR / CSC values (base entries of original columns must be 1)
     unsigned char *nif_x;             // out: the NearestIntegerFixing rounding, n0 bytes
     double *score;                    // scratch, n0 doubles: cached repair scores
+    volatile int *host_flag;          // pinned host word set to flag_value (behind a system fence) when `out` is complete
+    int flag_value;
 };
 
 size_t heur_smem_bytes(int m0, int n0, int rules);

@@ -21,6 +21,17 @@ REL = 1e-6
 PCG = dict(krylovMaxCgIter=200000, krylovCgTolInitial=1e-8, krylovCgTolFinal=1e-8, krylovCgTolDecayRate=1.0)
 
 
+@pytest.fixture(scope="module")
+def cuda_ws():
+    """A workspace of this module's own: the ladder models grow it to 10k x 200k, and a grown workspace selects other
+    kernel variants for small models (e.g. the assembly without shared-memory staging once the pad id no longer fits) -
+    same results to rounding, but the session-wide workspace is also used by bit-equality tests."""
+    w = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(w)
+    yield w
+    sb.releaseIpmWorkspace(w)
+
+
 def solve(inst, ws, strategy, **kw):
     node = node_from_instance(inst, linearSolverStrategy=strategy, **kw)
     res = sb.SolverExecutionResult()
@@ -36,7 +47,7 @@ def close(a, b):
 def test_appendix_c_check_values_1000x20000(cuda_ws):
     """gen_scp(1000, 20000, 0.005, 0): nnz 101147, 24 iterations, 554.166452726 / 552.956531973."""
     inst = scp_io.gen_scp(1000, 20000, 0.005, 0)
-    assert inst.nnz == 101147 + 1000
+    assert inst.nnz == 101147            # nnz(A) of SURVEY App. C counts the surplus column of each row
     d = solve(inst, cuda_ws, "cholesky")
     assert d.iterations == 24 and close(d.primalObj, 554.166452726) and close(d.dualObj, 552.956531973)
     p = solve(inst, cuda_ws, "pcg", **PCG)
@@ -57,7 +68,7 @@ def test_appendix_c_check_values_5kx100k_direct_and_pcg(cuda_ws):
     """gen_scp(5000, 100000, 0.001, 0): nnz 505691, 27 iterations, 2719.944694956 / 2710.607473538
     from the direct path, and the PCG path within the contract of it."""
     inst = scp_io.gen_scp(5000, 100000, 0.001, 0)
-    assert inst.nnz == 505691 + 5000
+    assert inst.nnz == 505691
     d = solve(inst, cuda_ws, "cholesky")
     assert d.iterations == 27 and close(d.primalObj, 2719.944694956) and close(d.dualObj, 2710.607473538)
     p = solve(inst, cuda_ws, "pcg", **PCG)

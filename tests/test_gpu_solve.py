@@ -166,3 +166,55 @@ def test_batch_of_independent_lps():
         check_against(r, int(z["ref_iters"]), float(z["ref_primal"]), float(z["ref_dual"]))
     for w in wss:
         sb.releaseIpmWorkspace(w)
+
+
+def test_reload_of_the_resident_model_is_recognised():
+    """sb200_load_model fingerprints the CSR it is given: the SAME matrix as the resident one keeps the CSC copy, the
+    symbolic structure and the captured iteration graph (only c and b are refreshed); a changed coefficient, a changed
+    cost or a node delta in between must all be honoured."""
+    import time
+    inst, z = load_golden("scpnre1")
+    ws = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(ws)
+    fresh = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(fresh)
+    try:
+        node = node_from_instance(inst, linearSolverStrategy="cholesky")
+        cfg = sb.SolverExecutionConfig(maxIterations=100)
+
+        def solve(nd, w, reload=True):
+            if reload:
+                nd.copyModelOnDevice(w)
+            r = sb.SolverExecutionResult()
+            assert sb.solver_sparse_mehrotra_run(nd, cfg, r, w) == sb.CODE_SUCCESSFUL
+            return r
+
+        r0 = solve(node, ws)
+        t0 = time.perf_counter()
+        node.copyModelOnDevice(ws)
+        t_hit = time.perf_counter() - t0
+        r1 = solve(node, ws, reload=False)
+        assert (r1.iterations, r1.primalObj, r1.dualObj) == (r0.iterations, r0.primalObj, r0.dualObj)
+        assert np.array_equal(r1.primalSolution, r0.primalSolution)
+        # a changed cost vector on the same matrix: fast path, new c
+        node2 = node_from_instance(inst, linearSolverStrategy="cholesky")
+        node2.hObjDns = node2.hObjDns.copy()
+        node2.hObjDns[:inst.n_orig] *= 1.5
+        a, b = solve(node2, ws), solve(node2, fresh)
+        assert a.iterations == b.iterations and a.primalObj == b.primalObj and abs(a.primalObj - 1.5 * r0.primalObj) < 1e-3 * r0.primalObj
+        # a changed coefficient: new fingerprint, everything rebuilt
+        node3 = node_from_instance(inst, linearSolverStrategy="cholesky")
+        node3.hCsrMatVals = node3.hCsrMatVals.copy()
+        node3.hCsrMatVals[0] = 2.0
+        a, b = solve(node3, ws), solve(node3, fresh)
+        assert a.iterations == b.iterations and a.primalObj == b.primalObj and a.primalObj != r0.primalObj
+        # back to the original: rebuilt again, same answer as at the start
+        r4 = solve(node, ws)
+        assert (r4.iterations, r4.primalObj, r4.dualObj) == (r0.iterations, r0.primalObj, r0.dualObj)
+        t0 = time.perf_counter()
+        node3.copyModelOnDevice(ws)
+        t_miss = time.perf_counter() - t0
+        assert t_hit < t_miss, (t_hit, t_miss)
+    finally:
+        sb.releaseIpmWorkspace(ws)
+        sb.releaseIpmWorkspace(fresh)

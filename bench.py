@@ -801,8 +801,8 @@ def main():
     ap.add_argument("--workload", default="scpnrh", choices=sorted(ORLIB) + sorted(WORKLOADS) + ["bnb"])
     ap.add_argument("--ref-iters", type=int, default=6,
                     help="--impl reference: iterations of each LP the reference's CUDA solver is sampled over")
-    ap.add_argument("--slots", type=int, default=128, help="bnb: concurrent node LPs per GPU (one thread block each; a device runs at most 128 kernels at once)")
-    ap.add_argument("--tp-slots", type=int, default=128, help="LPs in flight in the throughput block of the default line")
+    ap.add_argument("--slots", type=int, default=148, help="bnb: node LPs per window and GPU (one thread block each, one launch per window; 148 = the SMs of a B200)")
+    ap.add_argument("--tp-slots", type=int, default=148, help="LPs in flight in the throughput block of the default line")
     ap.add_argument("--bnb-instance", default="scpnre1", help="bnb: OR-Library instance (tests/golden/<name>.npz)")
     ap.add_argument("--node-lp", default="reference", choices=["reference", "converged"],
                     help="bnb: node LP configuration - the reference's (gap-stagnation exit, window 5, 1 %%) or to mu <= 1e-4")

@@ -9,7 +9,7 @@ class SyphaNodeSparse;
 
 struct SyphaBatchedBnbConfig
 {
-    int slots = 128;                     // node LPs in flight (one thread block each)
+    int slots = 148;                     // node LPs per window (one thread block each, one launch per window; 148 = the SMs of a B200)
     int maxIterations = 0;               // per node LP; 0: env->getMehrotraMaxIter()
     int maxNodes = 0;                    // 0: env->getBnbMaxNodes()
     int maxDepth = 64;                   // branch decisions a workspace is sized for

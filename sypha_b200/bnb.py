@@ -232,6 +232,9 @@ class BatchedBnb:
         self.warm_start = warm_start and self.device_nodes
         self.warm_floor = warm_floor
         self._export: List = [None] * slots
+        self._pool_free: List = []
+        self._arena = None
+        self.warm_pool = 4096               # export buffers kept for open nodes (a node without one starts its children cold)
         self.heuristic_rules = heuristic_rules if self.device_heuristics else "plain"
         if self.device_heuristics:
             for w in self.ws:
@@ -355,14 +358,28 @@ class BatchedBnb:
         self.frontier.append(BnbNode(nd.decisions + ((branch_var, 1),), bound, warm))
 
     def _new_export(self, slot: int, depth: int):
-        """device buffer that receives the node's final x | y | s (kept alive by the children that start from it)"""
+        """device buffer that receives the node's final x | y | s (kept alive by the children that start from it).
+        The buffers are views of ONE arena allocated up front: an allocation inside the search synchronises the device
+        (measured: 66-450 ms spikes in 35-110 ms windows).  An empty pool means the node's children start cold."""
         if not self.warm_start:
             return None
         import torch
-        t = torch.empty(2 * (self.base.n + depth) + self.base.m + depth, dtype=torch.float64,
-                        device=torch.device("cuda", self.env.cudaDeviceId))
-        self._export[slot] = t
-        return t.data_ptr()
+        if self._arena is None:
+            size = 2 * (self.base.n + self.max_depth + 1) + self.base.m + self.max_depth + 1
+            count = max(4 * self.slots, self.warm_pool)
+            self._arena = torch.empty((count, size), dtype=torch.float64, device=torch.device("cuda", self.env.cudaDeviceId))
+            self._pool_free = [self._arena[i] for i in range(count)]
+        old = self._export[slot]
+        self._export[slot] = self._pool_free.pop() if self._pool_free else None
+        self._retire(old)
+        t = self._export[slot]
+        return None if t is None else t.data_ptr()
+
+    def _retire(self, t):
+        """a buffer goes back to the pool when neither a slot nor an open node refers to it any more"""
+        import sys
+        if t is not None and sys.getrefcount(t) <= 3:       # `t`, the getrefcount argument, the caller's local
+            self._pool_free.append(t)
 
     @staticmethod
     def _warm_arg(nd: "BnbNode"):
@@ -433,6 +450,12 @@ class BatchedBnb:
                     continue
                 self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
                 self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+            if self.warm_start:
+                for nd in batch:                               # children solved: their parent's buffer may be free now
+                    if nd.warm is not None:
+                        t, nd.warm = nd.warm[0], None
+                        self._retire(t)
+                        del t
         else:
             self._fold_pending()
         self._collectives()

@@ -110,6 +110,9 @@ struct sb200_ws
     int solver_form = SB200_FORM_LATENCY;
     CtaLp *cta_dev = nullptr, *cta_host = nullptr;     // device, pinned
     bool cta_launched = false;
+    CtaLp *batch_dev = nullptr, *batch_host = nullptr;      // a window of LPs in one launch (owned by the window's first slot)
+    HeurArgs *hbatch_dev = nullptr, *hbatch_host = nullptr;
+    int batch_cap = 0;
     const double *warm_ptr = nullptr;                  // parent's x | y | s for the next solve (one use)
     int warm_n = 0, warm_m = 0;
     double warm_floor = 0.1;
@@ -617,6 +620,35 @@ bool cta_eligible(const sb200_ws *ws)
            ws->mpad <= CTA_MAX_MPAD && ws->chol.linv && ws->csr_offs && ws->csc_colptr;
 }
 
+// everything k_ipm_cta needs for the model as it stands in the workspace (base model + applied node delta)
+void fill_cta_args(sb200_ws *ws, const sb200_result *res, CtaLp &c)
+{
+    c.V = ws->V;
+    c.P = ws->dparams;
+    c.csr_offs = ws->csr_offs; c.csr_inds = ws->csr_inds; c.csr_vals = ws->csr_vals;
+    c.csc_colptr = ws->csc_colptr; c.csc_rows = ws->csc_rows; c.csc_vals = ws->csc_vals;
+    c.n_pairs = ws->pat.n_pairs;
+    c.chunk_ptr = ws->pat.chunk_ptr;
+    c.term8 = reinterpret_cast<const uint4 *>(ws->pat.term16);
+    c.nd = ws->pat.pad_id + 1;
+    c.ones = ws->ones_n;
+    c.base_m = ws->node_k ? ws->base_m : ws->m;
+    c.base_n = ws->node_k ? ws->base_n : ws->n;
+    c.node_k = ws->node_k;
+    c.d_var = ws->d_var; c.d_coef = ws->d_coef;
+    c.base_colptr = ws->base_colptr; c.base_rows = ws->base_rows; c.base_cvals = ws->base_cvals;
+    c.M = ws->M;
+    c.ld = ws->mpad;
+    c.linv = ws->chol.linv;
+    c.warm = ws->warm_ptr;
+    c.warm_n = ws->warm_n;
+    c.warm_m = ws->warm_m;
+    c.warm_floor = ws->warm_floor;
+    ws->warm_ptr = nullptr;                    // one use
+    c.export_xys = res ? res->xys_device : nullptr;
+    c.sc_pinned = ws->sc_host;
+}
+
 // ---- solve state machine ------------------------------------------------------------------------
 int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
 {
@@ -657,31 +689,7 @@ int solve_begin(sb200_ws *ws, const sb200_params *p, sb200_result *res)
             WS_TRY(cudaMalloc(&ws->cta_dev, sizeof(CtaLp)));
             WS_TRY(cudaMallocHost(&ws->cta_host, sizeof(CtaLp)));
         }
-        CtaLp &c = *ws->cta_host;
-        c.V = V;
-        c.P = ws->dparams;
-        c.csr_offs = ws->csr_offs; c.csr_inds = ws->csr_inds; c.csr_vals = ws->csr_vals;
-        c.csc_colptr = ws->csc_colptr; c.csc_rows = ws->csc_rows; c.csc_vals = ws->csc_vals;
-        c.n_pairs = ws->pat.n_pairs;
-        c.chunk_ptr = ws->pat.chunk_ptr;
-        c.term8 = reinterpret_cast<const uint4 *>(ws->pat.term16);
-        c.nd = ws->pat.pad_id + 1;
-        c.ones = ws->ones_n;
-        c.base_m = ws->node_k ? ws->base_m : ws->m;
-        c.base_n = ws->node_k ? ws->base_n : ws->n;
-        c.node_k = ws->node_k;
-        c.d_var = ws->d_var; c.d_coef = ws->d_coef;
-        c.base_colptr = ws->base_colptr; c.base_rows = ws->base_rows; c.base_cvals = ws->base_cvals;
-        c.M = ws->M;
-        c.ld = ws->mpad;
-        c.linv = ws->chol.linv;
-        c.warm = ws->warm_ptr;
-        c.warm_n = ws->warm_n;
-        c.warm_m = ws->warm_m;
-        c.warm_floor = ws->warm_floor;
-        ws->warm_ptr = nullptr;                    // one use
-        c.export_xys = res ? res->xys_device : nullptr;
-        c.sc_pinned = ws->sc_host;
+        fill_cta_args(ws, res, *ws->cta_host);
         WS_TRY(cudaMemcpyAsync(ws->cta_dev, ws->cta_host, sizeof(CtaLp), cudaMemcpyHostToDevice, st));
         WS_TRY(cudaEventRecord(ws->ev[1], st));
         WS_TRY(cudaEventRecord(ws->ev[2], st));
@@ -781,41 +789,48 @@ int solve_poll(sb200_ws *ws, int *finished)
     return SB200_OK;
 }
 
+// result of a one-block solve from the pinned mirror the kernel filled (no copy, no synchronisation here: the caller has
+// seen the LP finish - an event, a stream synchronisation or the mirror's `done`)
+void finish_from_mirror(sb200_ws *ws, sb200_result *r)
+{
+    const Scalars &sc = *ws->sc_host;
+    ws->active = false;
+    const bool numerical = sc.numerical != 0 || sc.chol_info != 0;
+    int reason = sc.reason;
+    if (numerical) reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
+    const double viol = sc.dual - sc.primal;
+    bool num2 = numerical;
+    if (!numerical && reason != SB200_TERM_CONVERGED && std::isfinite(viol) && viol > 1e6 * std::max(1.0, std::fabs(sc.primal)))
+    {
+        num2 = true;
+        reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
+    }
+    r->status = num2 ? SB200_ERR_NUMERICAL : SB200_OK;
+    r->reason = reason;
+    r->iterations = sc.iter;
+    r->primal_obj = sc.primal;
+    r->dual_obj = sc.dual;
+    r->rel_gap = std::fabs(sc.primal - sc.dual) / std::max(1.0, std::fabs(sc.primal));
+    r->mu = sc.mu;
+    r->strategy_used = ws->strategy;
+    r->cg_iterations = 0;
+    // device time of the LP: the kernel's own clock (%globaltimer around the whole solve, mirrored in sum0)
+    r->ms_start = 0.0;
+    r->ms_setup = 0.0;
+    r->ms_loop = sc.sum0 * 1e-6;
+    r->kernels_launched = (g_launch_count - ws->launches_at_begin) + ws->graph_kernel_launches;
+    ws->trace_rows = std::min(sc.iter, SB200_TRACE_ROWS);
+    ws->trace_stale = true;                 // copied on demand (sb200_get_trace)
+}
+
 int solve_finish(sb200_ws *ws, sb200_result *r)
 {
     cudaStream_t st = ws->stream;
     const IpmVecs &V = ws->V;
     if (ws->cta_launched && !r->x_host && !r->y_host && !r->s_host)
-    {   // one-block solve, nothing to copy out: the kernel left the scalars in the pinned mirror (and the packed
-        // iterate in xys_device) and the caller has seen it finish (event or the mirror's `done`): no copy, no sync
-        const Scalars &sc = *ws->sc_host;
-        ws->active = false;
-        const bool numerical = sc.numerical != 0 || sc.chol_info != 0;
-        int reason = sc.reason;
-        if (numerical) reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
-        const double viol = sc.dual - sc.primal;
-        bool num2 = numerical;
-        if (!numerical && reason != SB200_TERM_CONVERGED && std::isfinite(viol) && viol > 1e6 * std::max(1.0, std::fabs(sc.primal)))
-        {
-            num2 = true;
-            reason = SB200_TERM_INFEASIBLE_OR_NUMERICAL;
-        }
-        r->status = num2 ? SB200_ERR_NUMERICAL : SB200_OK;
-        r->reason = reason;
-        r->iterations = sc.iter;
-        r->primal_obj = sc.primal;
-        r->dual_obj = sc.dual;
-        r->rel_gap = std::fabs(sc.primal - sc.dual) / std::max(1.0, std::fabs(sc.primal));
-        r->mu = sc.mu;
-        r->strategy_used = ws->strategy;
-        r->cg_iterations = 0;
-        // device time of the LP: the kernel's own clock (%globaltimer around the whole solve, mirrored in sum0)
-        r->ms_start = 0.0;
-        r->ms_setup = 0.0;
-        r->ms_loop = sc.sum0 * 1e-6;
-        r->kernels_launched = (g_launch_count - ws->launches_at_begin) + ws->graph_kernel_launches;
-        ws->trace_rows = std::min(sc.iter, SB200_TRACE_ROWS);
-        ws->trace_stale = true;                 // copied on demand (sb200_get_trace)
+    {   // one-block solve, nothing to copy out: the kernel left the scalars in the pinned mirror (and the packed iterate
+        // in xys_device) and the caller has seen it finish
+        finish_from_mirror(ws, r);
         return SB200_OK;
     }
     if (ws->cta_launched && r->xys_device) r->xys_device = nullptr;      // already written by the kernel
@@ -977,6 +992,10 @@ int sb200_ws_destroy(sb200_ws *ws)
     if (ws->heur_flag_host) cudaFreeHost(ws->heur_flag_host);
     if (ws->cta_dev) cudaFree(ws->cta_dev);
     if (ws->cta_host) cudaFreeHost(ws->cta_host);
+    if (ws->batch_dev) cudaFree(ws->batch_dev);
+    if (ws->batch_host) cudaFreeHost(ws->batch_host);
+    if (ws->hbatch_dev) cudaFree(ws->hbatch_dev);
+    if (ws->hbatch_host) cudaFreeHost(ws->hbatch_host);
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ws->sc_host) cudaFreeHost(ws->sc_host);
@@ -1171,6 +1190,89 @@ static int abort_batch(sb200_ws **wss, int k, int rc)
     return rc;
 }
 
+// A window of LPs in the throughput form as ONE launch: block i of k_ipm_cta solves the LP resident in wss[i].  The node
+// deltas run on the slots' own streams (a few small kernels each); the first slot's stream waits for them, carries the one
+// LP launch, and is the only thing the host waits on.  No limit of 128 concurrent kernels, no launch per LP.
+static bool batch_is_one_launch(sb200_ws **wss, int k, const sb200_result *results)
+{
+    if (k < 2) return false;
+    const char *off = getenv("SB200_WINDOW_LAUNCH");
+    if (off && off[0] == '0') return false;
+    for (int i = 0; i < k; ++i)
+    {
+        const sb200_ws *w = wss[i];
+        if (!w || !w->loaded || w->device != wss[0]->device || w->solver_form != SB200_FORM_THROUGHPUT || !cta_eligible(w))
+            return false;
+        const sb200_result &r = results[i];
+        if (r.x_host || r.y_host || r.s_host || r.x0_host || r.y0_host || r.s0_host) return false;
+    }
+    return true;
+}
+
+static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *params, sb200_result *results)
+{
+    sb200_ws *lead = wss[0];
+    sb200_ws *ws = lead;                    // for WS_TRY
+    WS_TRY(cudaSetDevice(lead->device));
+    cudaStream_t main = lead->stream;
+    if (k > lead->batch_cap)
+    {
+        if (lead->batch_dev) cudaFree(lead->batch_dev);
+        if (lead->batch_host) cudaFreeHost(lead->batch_host);
+        if (lead->hbatch_dev) cudaFree(lead->hbatch_dev);
+        if (lead->hbatch_host) cudaFreeHost(lead->hbatch_host);
+        lead->batch_dev = nullptr; lead->batch_host = nullptr; lead->hbatch_dev = nullptr; lead->hbatch_host = nullptr;
+        lead->batch_cap = 0;
+        WS_TRY(cudaMalloc(&lead->batch_dev, sizeof(CtaLp) * (size_t)k));
+        WS_TRY(cudaMallocHost(&lead->batch_host, sizeof(CtaLp) * (size_t)k));
+        WS_TRY(cudaMalloc(&lead->hbatch_dev, sizeof(HeurArgs) * (size_t)k));
+        WS_TRY(cudaMallocHost(&lead->hbatch_host, sizeof(HeurArgs) * (size_t)k));
+        lead->batch_cap = k;
+    }
+    // parameters: one device copy (the lead's) serves every block
+    DevParams &hp = lead->hparams;
+    hp.eta = params->eta;
+    hp.mu_tol = params->mu_tol;
+    hp.min_improv_ratio = params->gap_min_improv_pct / 100.0;
+    hp.max_iter = params->max_iter;
+    hp.gap_enabled = (params->gap_enabled && params->gap_window > 0 && params->gap_min_improv_pct >= 0.0) ? 1 : 0;
+    hp.gap_window = params->gap_window;
+    hp.n_orig = lead->n_orig;
+    hp.cg_max_iter = params->cg_max_iter;
+    hp.cg_tol_initial = params->cg_tol_initial;
+    hp.cg_tol_final = params->cg_tol_final;
+    hp.cg_tol_decay = params->cg_tol_decay;
+    WS_TRY(cudaMemcpyAsync(lead->dparams, &hp, sizeof hp, cudaMemcpyHostToDevice, main));
+    for (int i = 0; i < k; ++i)
+    {
+        sb200_ws *w = wss[i];
+        w->params = *params;
+        w->launches_at_begin = g_launch_count;
+        w->graph_kernel_launches = 0;
+        fill_cta_args(w, &results[i], lead->batch_host[i]);
+        lead->batch_host[i].P = lead->dparams;
+        w->sc_host->done = 0;
+        w->cta_launched = true;
+        w->active = true;
+        if (i)
+        {   // the slot's node-delta kernels (its own stream) before the window's launch
+            WS_TRY(cudaEventRecord(w->ev[0], w->stream));
+            WS_TRY(cudaStreamWaitEvent(main, w->ev[0], 0));
+        }
+    }
+    WS_TRY(cudaMemcpyAsync(lead->batch_dev, lead->batch_host, sizeof(CtaLp) * (size_t)k, cudaMemcpyHostToDevice, main));
+    const int rc = launch_ipm_cta(lead->batch_dev, k, main);
+    if (rc) return fail(lead, rc, "sb200_solve_batch: launch of the one-block solver failed");
+    WS_TRY(cudaGetLastError());
+    WS_TRY(cudaStreamSynchronize(main));
+    for (int i = 0; i < k; ++i)
+    {
+        finish_from_mirror(wss[i], &results[i]);
+        results[i].kernels_launched = i == 0 ? 1 : 0;        // one launch for the whole window
+    }
+    return SB200_OK;
+}
+
 int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, const sb200_params *params,
                       sb200_result *results)
 {
@@ -1183,8 +1285,14 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
         for (int i = 0; i < k; ++i)
             if ((rc = apply_node_delta(wss[i], &deltas[i]))) return abort_batch(wss, k, rc);
     for (int i = 0; i < k; ++i)
-    {
         if (deltas && deltas[i].export_xys && !results[i].xys_device) results[i].xys_device = deltas[i].export_xys;
+    if (batch_is_one_launch(wss, k, results))
+    {
+        if ((rc = solve_batch_one_launch(wss, k, params, results))) return abort_batch(wss, k, rc);
+        return SB200_OK;
+    }
+    for (int i = 0; i < k; ++i)
+    {
         if ((rc = solve_begin(wss[i], params, &results[i]))) return abort_batch(wss, k, rc);
         live[i] = 1;
         ++remaining;
@@ -1211,13 +1319,8 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
 
 // launch the per-node branching / incumbent kernel behind the workspace's last solve and request its 40-byte
 // record (pinned); the caller waits on the stream (or an event) before reading ws->heur_out_host
-static int enqueue_node_heuristics(sb200_ws *ws)
+static int ensure_heur_buffers(sb200_ws *ws)
 {
-    if (!ws || !ws->loaded) return SB200_ERR_INVALID;
-    if (ws->active) return fail(ws, SB200_ERR_INVALID, "sb200_node_heuristics: a solve is still in flight");
-    if (!ws->csr_offs || !ws->csc_colptr || ws->n_orig <= 0)
-        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_node_heuristics: the model keeps no CSR/CSC lists");
-    WS_TRY(cudaSetDevice(ws->device));
     const int n0 = ws->n_orig;
     if (n0 > ws->heur_cap)
     {
@@ -1236,9 +1339,27 @@ static int enqueue_node_heuristics(sb200_ws *ws)
         }
         ws->heur_cap = n0;
     }
-    HeurArgs a{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
+    return SB200_OK;
+}
+
+static HeurArgs heur_args_of(sb200_ws *ws)
+{
+    const int n0 = ws->n_orig;
+    return HeurArgs{ws->base_m, n0, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->c, ws->V.x,
                ws->node_k, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_out_host,
                ws->heur_rules, ws->heur_branch_rule, ws->heur_tol, ws->V.y, ws->b, ws->csr_vals, ws->csc_vals, ws->heur_nif, ws->heur_score, ws->heur_flag_host, ++ws->heur_seq};
+}
+
+static int enqueue_node_heuristics(sb200_ws *ws)
+{
+    if (!ws || !ws->loaded) return SB200_ERR_INVALID;
+    if (ws->active) return fail(ws, SB200_ERR_INVALID, "sb200_node_heuristics: a solve is still in flight");
+    if (!ws->csr_offs || !ws->csc_colptr || ws->n_orig <= 0)
+        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_node_heuristics: the model keeps no CSR/CSC lists");
+    WS_TRY(cudaSetDevice(ws->device));
+    int rc0 = ensure_heur_buffers(ws);
+    if (rc0) return rc0;
+    const HeurArgs a = heur_args_of(ws);
     const int rc = launch_node_heuristics(a, ws->stream);
     if (rc == SB200_ERR_UNSUPPORTED)
         return fail(ws, rc, "sb200_node_heuristics: m + n_orig too large for the single-CTA kernel's shared memory");
@@ -1251,6 +1372,31 @@ int sb200_node_heuristics(sb200_ws **wss, int k, sb200_heur_result *out)
 {
     if (!wss || k <= 0 || !out) return SB200_ERR_INVALID;
     int rc;
+    {   // a window of nodes of the same base model with the reference's rules: ONE launch, a block per node
+        bool one = k >= 2 && wss[0] && wss[0]->batch_cap >= k;
+        for (int i = 0; one && i < k; ++i)
+            one = wss[i] && wss[i]->loaded && !wss[i]->active && wss[i]->device == wss[0]->device &&
+                  wss[i]->heur_rules == SB200_HEUR_REFERENCE && wss[i]->base_m == wss[0]->base_m &&
+                  wss[i]->n_orig == wss[0]->n_orig && wss[i]->csr_offs && wss[i]->csc_colptr;
+        if (one)
+        {
+            sb200_ws *ws = wss[0];
+            WS_TRY(cudaSetDevice(ws->device));
+            for (int i = 0; i < k; ++i)
+            {
+                if ((rc = ensure_heur_buffers(wss[i]))) return rc;
+                ws->hbatch_host[i] = heur_args_of(wss[i]);
+                ws->hbatch_host[i].host_flag = nullptr;          // the host waits on the stream
+            }
+            WS_TRY(cudaMemcpyAsync(ws->hbatch_dev, ws->hbatch_host, sizeof(HeurArgs) * (size_t)k, cudaMemcpyHostToDevice, ws->stream));
+            rc = launch_node_heuristics_batch(ws->hbatch_dev, k, ws->base_m, ws->n_orig, ws->stream);
+            if (rc) return fail(ws, rc, "sb200_node_heuristics: window launch failed");
+            WS_TRY(cudaGetLastError());
+            WS_TRY(cudaStreamSynchronize(ws->stream));
+            for (int i = 0; i < k; ++i) out[i] = *wss[i]->heur_out_host;
+            return SB200_OK;
+        }
+    }
     for (int i = 0; i < k; ++i)
         if ((rc = enqueue_node_heuristics(wss[i]))) return rc;
     for (int i = 0; i < k; ++i)

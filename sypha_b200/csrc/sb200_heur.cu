@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics(HeurArgs a)
 // them every choice - are bit-identical.
 constexpr unsigned char ST_FIXED1 = 4, ST_NIF = 8;
 
-__global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
+__device__ __forceinline__ void node_heuristics_ref_body(const HeurArgs &a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ypos = reinterpret_cast<double *>(smem_raw);                 // [m0] max(0, y_i)
@@ -609,6 +609,17 @@ __global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a)
     }
 }
 
+__global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref(HeurArgs a) { node_heuristics_ref_body(a); }
+
+// a window of nodes in ONE launch: block b runs the node kernel on args[b] (same base model, own LP point and decisions)
+__global__ void __launch_bounds__(HT, 1) k_node_heuristics_ref_batch(const HeurArgs *args)
+{
+    __shared__ HeurArgs sa;
+    if (threadIdx.x == 0) sa = args[blockIdx.x];
+    __syncthreads();
+    node_heuristics_ref_body(sa);
+}
+
 } // namespace
 
 size_t heur_smem_bytes(int m0, int n0, int rules)
@@ -626,6 +637,18 @@ int launch_node_heuristics(const HeurArgs &a, cudaStream_t st)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return SB200_ERR_CUDA;
     kern<<<1, HT, smem, st>>>(a);
+    ++g_launch_count;
+    return SB200_OK;
+}
+
+int launch_node_heuristics_batch(const HeurArgs *d_args, int count, int m0, int n0, cudaStream_t st)
+{
+    const size_t smem = heur_smem_bytes(m0, n0, SB200_HEUR_REFERENCE);
+    if (smem > 200 * 1024) return SB200_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_node_heuristics_ref_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return SB200_ERR_CUDA;
+    k_node_heuristics_ref_batch<<<count, HT, smem, st>>>(d_args);
     ++g_launch_count;
     return SB200_OK;
 }

@@ -31,5 +31,7 @@ struct HeurArgs
 
 size_t heur_smem_bytes(int m0, int n0, int rules);
 int launch_node_heuristics(const HeurArgs &a, cudaStream_t st);
+// the reference-rules kernel for `count` nodes of the same base model in one launch (d_args: device array)
+int launch_node_heuristics_batch(const HeurArgs *d_args, int count, int m0, int n0, cudaStream_t st);
 
 } // namespace sb200

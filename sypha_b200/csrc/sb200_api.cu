@@ -238,6 +238,15 @@ __global__ void k_densify(int m, const int *__restrict__ offs, const int *__rest
             atomicAdd(&A[(size_t)row * lda + inds[k]], vals[k]);   // duplicates sum, like CSR semantics
 }
 
+// a (row, column) pair stored twice: the products sum duplicates, the symbolic structure of M counts a column's rows once
+// each, so the two would disagree - such a model is rejected at load.  CSC rows are ascending within a column.
+__global__ void k_find_duplicates(int n, const int *__restrict__ colptr, const int *__restrict__ rows, int *__restrict__ flag)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        for (int k = colptr[j] + 1; k < colptr[j + 1]; ++k)
+            if (rows[k] == rows[k - 1]) *flag = 1;
+}
+
 // ---- model fingerprint ---------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long mix64(unsigned long long v)
 {
@@ -492,6 +501,9 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
         return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_set_node_delta: only the sparse-assembly + Cholesky strategy folds node rows");
     if (k && (!delta->var || !delta->coef || !delta->rhs))
         return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: null delta arrays");
+    for (int r = 0; r < k; ++r)       // before any state changes: a rejected delta leaves the workspace as it was
+        if (delta->var[r] < 0 || delta->var[r] >= ws->base_n)
+            return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: branch variable out of range");
     const int m0 = ws->base_m, n0 = ws->base_n;
     const long long nnz0 = ws->base_nnz;
     if (m0 + k > ws->m_cap || n0 + k > ws->n_cap || nnz0 + 2ll * k > ws->nnz_cap ||
@@ -515,7 +527,7 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
     }
     if (k > ws->delta_cap)
     {
-        const int cap = std::max(64, k);
+        const int cap = (std::max(64, k) + 1) & ~1;     // even: the coefficient staging behind the ids stays 8-byte aligned
         int rc;
         if ((rc = grow(ws, &ws->d_var, (size_t)cap))) return rc;
         if ((rc = grow(ws, &ws->d_coef, (size_t)cap))) return rc;
@@ -1064,6 +1076,16 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
                    ws->csc_rows, ws->csc_vals, st);
     if (rc) return rc;
     ws->csc_lanes = pick_csc_lanes(nnz, n);
+    {
+        if (!ws->fp_dev) WS_TRY(cudaMalloc(&ws->fp_dev, 2 * sizeof(unsigned long long)));
+        int *flag = reinterpret_cast<int *>(ws->fp_dev), dup = 0;
+        WS_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        k_find_duplicates<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(n, ws->csc_colptr, ws->csc_rows, flag);
+        ++g_launch_count;
+        WS_TRY(cudaMemcpyAsync(&dup, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        WS_TRY(cudaStreamSynchronize(st));
+        if (dup) return fail(ws, SB200_ERR_INVALID, "sb200_load_model: a (row, column) pair is stored more than once");
+    }
 
     // ---- strategy --------------------------------------------------------------------------------
     int strat = strategy_hint;

@@ -69,7 +69,8 @@ extern "C" int sb200_read_scp(const char *path, sb200_scp_model *out)
     const long size = ftell(f);
     fseek(f, 0, SEEK_SET);
     if (size <= 0) { fclose(f); return SB200_ERR_INVALID; }
-    std::vector<char> buf((size_t)size);
+    std::vector<char> buf((size_t)size + 1);        // + a terminating NUL: strtod on a trailing non-integer token must stop there
+    buf[(size_t)size] = '\0';
     const size_t got = fread(buf.data(), 1, (size_t)size, f);
     fclose(f);
     if (got != (size_t)size) return SB200_ERR_INVALID;

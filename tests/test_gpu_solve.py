@@ -218,3 +218,19 @@ def test_reload_of_the_resident_model_is_recognised():
     finally:
         sb.releaseIpmWorkspace(ws)
         sb.releaseIpmWorkspace(fresh)
+
+
+def test_duplicate_entries_are_rejected_at_load():
+    """a (row, column) pair stored twice would make M = A D A' (symbolic structure) disagree with the products."""
+    inst, _ = load_golden("scp_demo06")
+    node = node_from_instance(inst, linearSolverStrategy="cholesky")
+    node.hCsrMatInds = node.hCsrMatInds.copy()
+    a = int(node.hCsrMatOffs[3])
+    node.hCsrMatInds[a + 1] = node.hCsrMatInds[a]            # row 3: its first column twice
+    ws = sb.IpmWorkspace()
+    sb.initializeIpmWorkspace(ws)
+    try:
+        with pytest.raises(sb.Sb200Error):
+            node.copyModelOnDevice(ws)
+    finally:
+        sb.releaseIpmWorkspace(ws)

@@ -436,16 +436,18 @@ def run_ours(args, rank, world, local_rank):
             raise RuntimeError(f"LP {i} failed: reason {res.terminationReason}")
         return res
 
+    # one LP at a time (latency form): the headline with --headline single, the `single_lp` block otherwise
+    s_steps, s_warm = (1, 0) if args.quick_single else (args.steps, args.warmup)
     for i in range(N_INSTANCES):                   # set-up: every instance's iteration graph is built once
         step(i)
-    for i in range(args.warmup):
+    for i in range(s_warm):
         step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.ready.wait(10)
     barrier()
     t0 = time.perf_counter()
-    results = [step(i) for i in range(args.steps)]
+    results = [step(i) for i in range(s_steps)]
     barrier()
     elapsed = time.perf_counter() - t0
     wall = elapsed
@@ -485,7 +487,7 @@ def run_ours(args, rank, world, local_rank):
         sb.solver_sparse_mehrotra_run(node, cfg, res, e2e_wss[i % N_INSTANCES])      # uploads the model, solves, D2H
         return res
 
-    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
+    e2e_steps = 0 if args.no_e2e else max(2, min(s_steps, 5))
     for i in range(max(3, N_INSTANCES) if e2e_steps else 0):   # warm-up: the pools, the driver's allocation paths and the
                                                                # grow-only buffers (every instance seen once: scpclr13's
                                                                # 400 MB structure otherwise grows inside timed steps 4-5)
@@ -507,13 +509,16 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_evt.set()
     sampler.join(timeout=2)
 
-    # ---- secondary: THROUGHPUT form - K LPs of the same workload in flight, each solved whole by one thread block
-    #      in one launch (csrc/sb200_cta.cu; sb200_solve_batch over K workspaces, results read back, host clock) ----
-    batch_block = None
-    if rank == 0 and not args.no_batch_block and models[0].m <= 2048:
-        from sypha_b200.solver import set_solver_form, solve_batch
+    # ---- THROUGHPUT form (the headline when the shape fits one thread block, m <= 2048): a step = ONE WINDOW of K LPs of
+    #      the workload (the instances in rotation), each solved whole by one thread block, the window ONE launch
+    #      (csrc/sb200_cta.cu; sb200_solve_batch over K workspaces).  `value`: CUDA events on the launching stream around
+    #      the window kernel (sb200_last_window), models resident.  `e2e`: every step uploads all K models from pinned
+    #      host memory (sb200_load_model), solves the window and reads every LP's x, y, s back into pinned memory ----
+    tp = None
+    if args.headline != "single" and not args.no_batch_block and models[0].m <= 2048 and strategy in ("auto", "cholesky"):
+        from sypha_b200.solver import set_solver_form, solve_batch, last_window
         K = args.tp_slots
-        tp_ws, tp_nodes = [], []
+        tp_ws, tp_nodes, tp_bufs = [], [], []
         for i in range(K):
             w = sb.IpmWorkspace()
             sb.initializeIpmWorkspace(w, device=local_rank)
@@ -523,39 +528,85 @@ def run_ours(args, rank, world, local_rank):
             set_solver_form(w, "throughput")
             tp_ws.append(w)
             tp_nodes.append(nd)
-        solve_batch(tp_nodes, cfg, tp_ws)                              # warm-up
-        torch.cuda.synchronize()
+            hb = torch.empty(2 * mdl.n + mdl.m, dtype=torch.float64).pin_memory().numpy()
+            tp_bufs.append((hb[:mdl.n], hb[mdl.n:mdl.n + mdl.m], hb[mdl.n + mdl.m:]))
+
+        def window():
+            rs = solve_batch(tp_nodes, cfg, tp_ws, host_bufs=tp_bufs)
+            ms, k = last_window(tp_ws[0])
+            if k != K:
+                raise RuntimeError(f"the window was not one launch of {K} thread blocks (got {k})")
+            bad = [r.terminationReason for r in rs if r.terminationReason != 0]
+            if bad:
+                raise RuntimeError(f"{len(bad)} LPs of the window did not converge: {bad[:4]}")
+            return rs, ms
+
+        try:
+            window()
+        except RuntimeError as e:
+            if args.headline == "throughput":
+                raise
+            print(f"[bench] throughput form not available for this workload ({e}); headline = one LP at a time", file=sys.stderr)
+            K = 0
+        for _ in range(max(args.warmup, 3) - 1 if K else 0):
+            window()
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        sampler2.ready.wait(10)
+        barrier()
         t0 = time.perf_counter()
-        reps, b_iters, b_launch = 3, 0, 0
-        for _ in range(reps):
-            rs = solve_batch(tp_nodes, cfg, tp_ws)
-            b_iters += sum(r.iterations for r in rs)
-            b_launch += sum(r.kernelsLaunched for r in rs)
-        torch.cuda.synchronize()
-        b_el = time.perf_counter() - t0
+        tp_ms, tp_iters, tp_launch, tp_flops, tp_each = 0.0, 0, 0, 0.0, []
+        for _ in range(args.steps if K else 0):
+            rs, ms = window()
+            tp_ms += ms
+            tp_each.append(round(ms, 2))
+            tp_iters += sum(r.iterations for r in rs)
+            tp_launch += sum(r.kernelsLaunched for r in rs)
+            # factorisations per LP: one per iteration + the starting point's (M = A A')
+            tp_flops += sum((r.iterations + 1) * (tp_nodes[j].nrows ** 3) / 3.0 for j, r in enumerate(rs))
+        barrier()
+        tp_wall = time.perf_counter() - t0
         ms = C.c_double()
         ph = []
         for q in range(8):
             lib.sb200_time_phase(tp_ws[K // 2].handle, 100 + q, 1, C.byref(ms))
             ph.append(ms.value)
-        it_mid = rs[K // 2].iterations
+        it_mid = rs[K // 2].iterations if K else 1
+
+        # e2e of the same step
+        def tp_e2e_step():
+            for j in range(K):
+                mdl, a = models[j % N_INSTANCES], pinned[j % N_INSTANCES]
+                node = sb.SyphaNodeSparse(env)
+                node.nrows, node.ncols, node.ncolsOriginal, node.nnz = mdl.m, mdl.n, mdl.n_orig, mdl.nnz
+                node.hCsrMatOffs, node.hCsrMatInds, node.hCsrMatVals = a["offs"].numpy(), a["inds"].numpy(), a["vals"].numpy()
+                node.hObjDns, node.hRhsDns = a["c"].numpy(), a["b"].numpy()
+                node.copyModelOnDevice(tp_ws[j])                   # H2D of the whole model, every LP, every step
+                tp_nodes[j] = node
+            return window()[0]
+
+        tp_e2e = None
+        if e2e_steps and K:
+            tp_e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e, it_e2e = max(2, min(args.steps, 3)), 0
+            for _ in range(n_e2e):
+                it_e2e += sum(r.iterations for r in tp_e2e_step())
+            barrier()
+            el = time.perf_counter() - t0
+            tp_e2e = {"iters": it_e2e, "elapsed": el, "steps": n_e2e,
+                      "h2d": int(sum(sum(pinned[j % N_INSTANCES][k].numel() * pinned[j % N_INSTANCES][k].element_size()
+                                         for k in ("offs", "inds", "vals", "c", "b")) for j in range(K))),
+                      "d2h": int(sum(8 * (2 * models[j % N_INSTANCES].n + models[j % N_INSTANCES].m) for j in range(K)))}
+        sampler2.stop_evt.set()
+        sampler2.join(timeout=2)
         mm = models[0].m
         fl = mm ** 3 / 3.0
         per_it = {nm: 1e3 * v / max(it_mid, 1) for nm, v in zip(("assembly", "factorisation", "solves", "A_v", "At_v", "vector"), ph[:6])}
-        batch_block = {
-            "form": "one thread block per LP, one launch per LP (sb200_set_solver_form THROUGHPUT)",
-            "concurrent_lps": K, "value": b_iters / b_el, "unit": "iter/s", "ms_per_batch": 1e3 * b_el / reps,
-            "lp_per_sec": K * reps / b_el, "gpu_launches": int(b_launch),
-            "us_per_iteration_inside_one_block": per_it, "whole_lp_ms_inside_one_block": ph[7],
-            "roofline": {"kernel": "factorisation phase of k_ipm_cta (left-looking 128x64 DMMA accumulators)", "bound": "tensor",
-                         "flops_per_iteration": fl,
-                         "per_sm": {"achieved_gflops": fl / per_it["factorisation"] / 1e3 if per_it["factorisation"] else None,
-                                    "peak_gflops": 1e3 * fp64_peak / 148.0,
-                                    "frac": (fl / per_it["factorisation"] / 1e3) / (1e3 * fp64_peak / 148.0) if per_it["factorisation"] else None},
-                         "whole_gpu": {"achieved_tflops": b_iters * fl / b_el / 1e12, "peak": fp64_peak,
-                                       "frac": b_iters * fl / b_el / 1e12 / fp64_peak,
-                                       "note": "factorisation flops of ALL phases' wall time: the other phases run on the same blocks"}},
-            "note": "throughput with K LPs in flight (host clock, results read back); the headline value is one LP at a time"}
+        if K:
+            tp = dict(K=K, ms=tp_ms, iters=tp_iters, launches=tp_launch, flops=tp_flops, each=tp_each, wall=tp_wall,
+                      per_it=per_it, whole_lp_ms=ph[7], e2e=tp_e2e, clocks=sampler2.summary(), fl=fl)
         for w in tp_ws:
             sb.releaseIpmWorkspace(w)
 
@@ -580,6 +631,22 @@ def run_ours(args, rank, world, local_rank):
         c = torch.tensor([iters, launches, e2e_iters], device="cuda", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         iters, launches, e2e_iters = int(c[0]), int(c[1]), int(c[2])
+        if tp:
+            t = torch.tensor([tp["ms"], tp["wall"], tp["e2e"]["elapsed"] if tp["e2e"] else 0.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tp["ms_max"], tp["wall_max"], e2e_max = float(t[0]), float(t[1]), float(t[2])
+            c = torch.tensor([tp["iters"], tp["launches"], tp["flops"], tp["e2e"]["iters"] if tp["e2e"] else 0,
+                              tp["e2e"]["h2d"] if tp["e2e"] else 0, tp["e2e"]["d2h"] if tp["e2e"] else 0],
+                             device="cuda", dtype=torch.float64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            tp["iters_all"], tp["launches_all"], tp["flops_all"] = int(c[0]), int(c[1]), float(c[2])
+            if tp["e2e"]:
+                tp["e2e"].update(elapsed_max=e2e_max, iters_all=int(c[3]), h2d_all=int(c[4]), d2h_all=int(c[5]))
+    elif tp:
+        tp.update(ms_max=tp["ms"], wall_max=tp["wall"], iters_all=tp["iters"], launches_all=tp["launches"], flops_all=tp["flops"])
+        if tp["e2e"]:
+            tp["e2e"].update(elapsed_max=tp["e2e"]["elapsed"], iters_all=tp["e2e"]["iters"], h2d_all=tp["e2e"]["h2d"],
+                             d2h_all=tp["e2e"]["d2h"])
 
     out = None
     if rank == 0:
@@ -638,7 +705,7 @@ def run_ours(args, rank, world, local_rank):
                                                "(CUDA events); launches and dependent latency, not bandwidth, bound this shape"}
         out = {
             "metric": "ipm_iterations_per_sec", "value": iters / elapsed, "unit": "iter/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+            "steps": s_steps, "warmup": s_warm, "ms_per_step": 1e3 * elapsed / s_steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": data_kind,
             "config": dict(base_config(args.workload, models, desc),
@@ -648,11 +715,11 @@ def run_ours(args, rank, world, local_rank):
                                "one instance; its resident structure exceeds the 126 MB L2" if models[0].nnz > 10 ** 7 else
                                "one instance, L2-resident between steps (stated, not flushed)"),
                            poll_every=args.poll_every, graph=not args.no_graph),
-            "time_to_lp_opt_ms": 1e3 * elapsed / args.steps,
+            "time_to_lp_opt_ms": 1e3 * elapsed / s_steps,
             "timing": "CUDA events on the workspace stream around every LP, summed over the K steps, max over ranks",
-            "wall_ms_per_step": 1e3 * wall / args.steps,
-            "iterations_per_lp": iters / (args.steps * world),
-            "device_ms_per_lp": dev_ms / args.steps, "loop_ms_per_lp": loop_ms / args.steps,
+            "wall_ms_per_step": 1e3 * wall / s_steps,
+            "iterations_per_lp": iters / (s_steps * world),
+            "device_ms_per_lp": dev_ms / s_steps, "loop_ms_per_lp": loop_ms / s_steps,
             "e2e": ({"value": e2e_iters / e2e_elapsed, "unit": "iter/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_elapsed / e2e_steps, "steps": e2e_steps}
                     if e2e_steps else None),
@@ -661,8 +728,58 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof,
             "phases": phases,
         }
-        if batch_block:
-            out["concurrent_lps"] = batch_block
+        if tp:
+            # the throughput form is the headline; the one-LP-at-a-time (latency form) line above moves into `single_lp`
+            single = {k: out[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "time_to_lp_opt_ms", "timing",
+                                          "wall_ms_per_step", "iterations_per_lp", "device_ms_per_lp", "loop_ms_per_lp",
+                                          "e2e", "gpu_launches", "clocks", "roofline", "phases")}
+            single["form"] = ("one LP at a time over the whole GPU, ~12 kernels per iteration as one CUDA graph (latency form, "
+                              "sb200_set_solver_form LATENCY): the time-to-optimal-LP-relaxation number")
+            K = tp["K"]
+            win_ms = tp["ms_max"] / args.steps
+            tfl = tp["flops_all"] / world / args.steps / win_ms / 1e9          # per launch (one GPU's window)
+            ktr = read_traffic().get("k_ipm_cta_per_lp_iteration")
+            f_us = tp["per_it"]["factorisation"]
+            roof_tp = {"kernel": "k_ipm_cta (one launch per window, one thread block per LP: assembly, left-looking DMMA Cholesky, "
+                                 "solves, products, vector steps of every iteration)",
+                       "bound": "tensor", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
+                       "flops": tp["flops_all"] / world / args.steps,
+                       "flops_note": "m^3/3 per factorisation, one per iteration + the starting point's, summed over the window's LPs; "
+                                     "ALL of the kernel's time is in the denominator (the factorisation is ~40% of it)",
+                       "ms_per_launch": win_ms,
+                       "traffic": (ktr * tp["iters_all"] / world / args.steps) if ktr else None,
+                       "traffic_note": "dram bytes per LP iteration of a K-block window (ncu --set full, profiles/traffic.json) x this "
+                                       "window's iterations" if ktr else "no ncu capture of a full window committed",
+                       "peak_source": fp64_src + "; MEASURED_PEAKS.json has no FP64 entry; scripts/fp64_peak.cu on this pool: DMMA issue "
+                                      "rate 37.2, DGEMM 8192^3 35.9 TFLOP/s (profiles/r2_a_fp64_peaks.json); nominal 40",
+                       "factorisation_phase_per_sm": {"achieved_gflops": tp["fl"] / f_us / 1e3 if f_us else None,
+                                                      "peak_gflops": 1e3 * fp64_peak / 148.0,
+                                                      "frac": (tp["fl"] / f_us / 1e3) / (1e3 * fp64_peak / 148.0) if f_us else None,
+                                                      "note": "in-kernel %globaltimer of one block of the window (sb200_time_phase 101)"},
+                       "us_per_iteration_inside_one_block": tp["per_it"], "whole_lp_ms_inside_one_block": tp["whole_lp_ms"]}
+            e2 = tp["e2e"]
+            out.update({
+                "value": tp["iters_all"] / (tp["ms_max"] / 1e3), "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": win_ms,
+                "timing": "CUDA events on the launching stream around each window's kernel (sb200_last_window), summed over the K "
+                          "steps, max over ranks",
+                "wall_ms_per_step": 1e3 * tp["wall_max"] / args.steps,
+                "iterations_per_lp": tp["iters_all"] / (args.steps * world * K),
+                "lps_per_sec": args.steps * world * K / (tp["ms_max"] / 1e3),
+                "window_ms": tp["each"],
+                "e2e": ({"value": e2["iters_all"] / e2["elapsed_max"], "unit": "iter/s",
+                         "h2d_bytes_per_step": e2["h2d_all"], "d2h_bytes_per_step": e2["d2h_all"],
+                         "ms_per_step": 1e3 * e2["elapsed_max"] / e2["steps"], "steps": e2["steps"],
+                         "note": "every step: all K models host->device from pinned memory (sb200_load_model), the window, every "
+                                 "LP's x, y, s device->host into pinned memory; host clock between barriers"} if e2 else None),
+                "gpu_launches": tp["launches_all"], "clocks": tp["clocks"], "roofline": roof_tp,
+            })
+            out["config"] = dict(out["config"], lps_per_step=K, form="throughput: one thread block per LP, one launch per step",
+                                 l2=f"{K} LPs x ~75 MB of resident structure per GPU: working set >> 126 MB L2 (no flush needed)")
+            out["time_to_lp_opt_ms"] = single["time_to_lp_opt_ms"]
+            for k in ("device_ms_per_lp", "loop_ms_per_lp", "phases"):
+                out.pop(k, None)
+            out["single_lp"] = single
         if bnb_block:
             out["bnb"] = bnb_block
         if world == 1 and not args.no_pcg_block and args.workload != "synth50k":
@@ -824,7 +941,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
     ap.add_argument("--no-pcg-block", action="store_true")
-    ap.add_argument("--no-batch-block", action="store_true")
+    ap.add_argument("--headline", default="auto", choices=["auto", "throughput", "single"],
+                    help="throughput (default where m <= 2048): a step = one window of --tp-slots LPs, one thread block each, one "
+                         "launch; single: a step = one LP over the whole GPU (latency form)")
+    ap.add_argument("--no-batch-block", action="store_true", help="same as --headline single")
+    ap.add_argument("--quick-single", action="store_true", help="profiling runs: the one-LP-at-a-time block does a single step")
     ap.add_argument("--no-pcg-solve", action="store_true", help="skip the whole 50k x 1M LP solve (about 15 s)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--cg-max-iter", type=int, default=50000)

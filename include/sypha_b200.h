@@ -243,6 +243,10 @@ int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps);
  * polled inside an LP. */
 enum { SB200_FORM_LATENCY = 0, SB200_FORM_THROUGHPUT = 1 };
 int sb200_set_solver_form(sb200_ws *ws, int form);
+/* sb200_solve_batch over workspaces in the throughput form is ONE launch (a thread block per LP) on the first workspace's
+ * stream.  Device time of the last such window on `ws` (= the first workspace of that batch), measured with CUDA events on
+ * the launching stream around the kernel, and the number of LPs it held. */
+int sb200_last_window(sb200_ws *ws, double *ms, int *lps);
 
 /* Continuous batching of B&B node LPs over k workspaces that hold the same base model: whenever a slot is
  * free `next(user, slot, &delta)` is asked for a node (return 1 with the decision list filled in - the arrays

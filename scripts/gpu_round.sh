@@ -10,11 +10,13 @@ mkdir -p gpurun_out
   echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 "$@" 2> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench.json | python -c "
 import sys,json
 d=json.loads(sys.stdin.read())
-print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'loop_ms',round(d['loop_ms_per_lp'],3), d['config']['workload'])
-print({k:round(v['ms']*1e3,1) for k,v in d['phases'].items()})
-print('roofline',{k:(round(v,4) if isinstance(v,float) else v) for k,v in d['roofline'].items() if k in ('kernel','achieved','peak','frac','peak_source')})
-print('whole_iteration',d['roofline'].get('whole_iteration'))
-print('concurrent',d.get('concurrent_lps',{}).get('value'))
+print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'ms_per_step',round(d['ms_per_step'],3), d['config']['workload'], d['config'].get('form'))
+print('window_ms',d.get('window_ms'),'e2e',d['e2e'])
+print('roofline',{k:(round(v,4) if isinstance(v,float) else v) for k,v in d['roofline'].items() if k in ('kernel','achieved','peak','frac','traffic','ms_per_launch','factorisation_phase_per_sm','us_per_iteration_inside_one_block')})
+sl=d.get('single_lp') or d
+print('single_lp value',round(sl['value'],1),'e2e',round(sl['e2e']['value'],1),'loop_ms',round(sl['loop_ms_per_lp'],3))
+print({k:round(v['ms']*1e3,1) for k,v in sl['phases'].items()})
+print('single roofline',{k:(round(v,4) if isinstance(v,float) else v) for k,v in sl['roofline'].items() if k in ('kernel','achieved','peak','frac')})
 for k,v in (d.get('bnb') or {}).items(): print('bnb',k,{a:v.get(a) for a in ('value','nodes','lp_iterations_per_node','lp_device_ms_per_node','incumbent','root_bound','model','error')}, v.get('rank0'))
 print('pcg',{k:d.get('pcg_50kx1M',{}).get(k) for k in ('cg_iteration_us','lp_solve','error')})
 print('cpu',d.get('cpu_baseline'))

@@ -91,6 +91,7 @@ SYMBOLS = {
     "sb200_get_cover": (_i, [_vp, _vp]),
     "sb200_set_concurrency_hint": (_i, [_vp, _i]),
     "sb200_set_solver_form": (_i, [_vp, _i]),
+    "sb200_last_window": (_i, [_vp, C.POINTER(_d), C.POINTER(_i)]),
     "sb200_solve_stream": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_params), NEXT_NODE_FN, NODE_DONE_FN, _vp]),
     "sb200_get_trace": (_i, [_vp, _vp, _i]),
     "sb200_get_device_iterates": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),

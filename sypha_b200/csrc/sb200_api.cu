@@ -113,6 +113,8 @@ struct sb200_ws
     CtaLp *batch_dev = nullptr, *batch_host = nullptr;      // a window of LPs in one launch (owned by the window's first slot)
     HeurArgs *hbatch_dev = nullptr, *hbatch_host = nullptr;
     int batch_cap = 0;
+    double window_ms = 0.0;                 // device time (CUDA events on the launching stream) of the last one-launch window
+    int window_lps = 0;
     const double *warm_ptr = nullptr;                  // parent's x | y | s for the next solve (one use)
     int warm_n = 0, warm_m = 0;
     double warm_floor = 0.1;
@@ -1226,7 +1228,7 @@ static bool batch_is_one_launch(sb200_ws **wss, int k, const sb200_result *resul
         if (!w || !w->loaded || w->device != wss[0]->device || w->solver_form != SB200_FORM_THROUGHPUT || !cta_eligible(w))
             return false;
         const sb200_result &r = results[i];
-        if (r.x_host || r.y_host || r.s_host || r.x0_host || r.y0_host || r.s0_host) return false;
+        if (r.x0_host || r.y0_host || r.s0_host) return false;
     }
     return true;
 }
@@ -1283,10 +1285,27 @@ static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *par
         }
     }
     WS_TRY(cudaMemcpyAsync(lead->batch_dev, lead->batch_host, sizeof(CtaLp) * (size_t)k, cudaMemcpyHostToDevice, main));
+    WS_TRY(cudaEventRecord(lead->ev[1], main));
     const int rc = launch_ipm_cta(lead->batch_dev, k, main);
     if (rc) return fail(lead, rc, "sb200_solve_batch: launch of the one-block solver failed");
     WS_TRY(cudaGetLastError());
+    WS_TRY(cudaEventRecord(lead->ev[2], main));
+    bool copies = false;
+    for (int i = 0; i < k; ++i)
+    {   // results the caller wants on the host: behind the window's launch, on the same stream
+        const sb200_ws *w = wss[i];
+        sb200_result &r = results[i];
+        if (r.x_host) WS_TRY(cudaMemcpyAsync(r.x_host, w->V.x, sizeof(double) * w->n, cudaMemcpyDeviceToHost, main));
+        if (r.y_host) WS_TRY(cudaMemcpyAsync(r.y_host, w->V.y, sizeof(double) * w->m, cudaMemcpyDeviceToHost, main));
+        if (r.s_host) WS_TRY(cudaMemcpyAsync(r.s_host, w->V.s, sizeof(double) * w->n, cudaMemcpyDeviceToHost, main));
+        copies = copies || r.x_host || r.y_host || r.s_host;
+    }
+    (void)copies;
     WS_TRY(cudaStreamSynchronize(main));
+    float wms = 0.f;
+    cudaEventElapsedTime(&wms, lead->ev[1], lead->ev[2]);
+    lead->window_ms = wms;
+    lead->window_lps = k;
     for (int i = 0; i < k; ++i)
     {
         finish_from_mirror(wss[i], &results[i]);
@@ -1530,6 +1549,14 @@ int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps)
     // many LPs in flight: one CTA per LP (sb200_cta.cu) unless SB200_CTA_SOLVER=0 asks for the shared multi-kernel form
     const char *cs = getenv("SB200_CTA_SOLVER");
     ws->solver_form = (concurrent_lps > 1 && !(cs && atoi(cs) == 0)) ? SB200_FORM_THROUGHPUT : SB200_FORM_LATENCY;
+    return SB200_OK;
+}
+
+int sb200_last_window(sb200_ws *ws, double *ms, int *lps)
+{
+    if (!ws) return SB200_ERR_INVALID;
+    if (ms) *ms = ws->window_ms;
+    if (lps) *lps = ws->window_lps;
     return SB200_OK;
 }
 

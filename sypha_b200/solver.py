@@ -256,9 +256,10 @@ def solver_sparse_mehrotra(node: SyphaNodeSparse) -> int:
     return status if status != CODE_SUCCESSFUL else result.status
 
 
-def solve_batch(nodes, config: SolverExecutionConfig, workspaces):
+def solve_batch(nodes, config: SolverExecutionConfig, workspaces, host_bufs=None):
     """Solve independent LPs concurrently (one workspace/stream each) - the B&B node body of
-    src/sypha_solver_bnb_driver.cpp:789-859 batched per GPU."""
+    src/sypha_solver_bnb_driver.cpp:789-859 batched per GPU.  ``host_bufs[i]`` = (x, y, s) float64 arrays that receive
+    LP i's solution (e.g. views of pinned memory); allocated here when absent."""
     lib = L.load()
     k = len(nodes)
     for node, ws in zip(nodes, workspaces):
@@ -269,7 +270,12 @@ def solve_batch(nodes, config: SolverExecutionConfig, workspaces):
     res = (L.sb200_result * k)()
     bufs = []
     for i, node in enumerate(nodes):
-        x, y, s = np.empty(node.ncols), np.empty(node.nrows), np.empty(node.ncols)
+        if host_bufs is not None:
+            x, y, s = host_bufs[i]
+            if x.size < node.ncols or y.size < node.nrows or s.size < node.ncols:
+                raise ValueError(f"host_bufs[{i}] is smaller than LP {i}")
+        else:
+            x, y, s = np.empty(node.ncols), np.empty(node.nrows), np.empty(node.ncols)
         res[i].x_host, res[i].y_host, res[i].s_host = x.ctypes.data, y.ctypes.data, s.ctypes.data
         bufs.append((x, y, s))
     rc = lib.sb200_solve_batch(handles, k, None, C.byref(p), res)
@@ -309,6 +315,15 @@ class NodeHeuristicResult:
 
 
 FORM_LATENCY, FORM_THROUGHPUT = 0, 1
+
+
+def last_window(workspace):
+    """(device milliseconds, LPs) of the last one-launch window whose FIRST workspace was ``workspace``: CUDA events on the
+    launching stream around the kernel (sb200_last_window)."""
+    lib = L.load()
+    ms, k = C.c_double(), C.c_int()
+    lib.sb200_last_window(workspace.handle, C.byref(ms), C.byref(k))
+    return ms.value, k.value
 
 
 def set_solver_form(workspace, form: str = "latency"):

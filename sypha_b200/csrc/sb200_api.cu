@@ -46,6 +46,7 @@ struct sb200_ws
     long long nnz_cap = 0;
 
     NormalPattern pat;
+    CompactLists lists;                     // pattern-only rows / columns for the one-block solver's products
     BlockedPattern blk_rows, blk_cols;    // PCG strategy on a +/-1 matrix: shared-memory-staged products
     double *denseA = nullptr;     // SYRK strategy: dense row-major copy of A, mpad x kpad
     int kpad = 0;
@@ -654,6 +655,15 @@ void fill_cta_args(sb200_ws *ws, const sb200_result *res, CtaLp &c)
     c.M = ws->M;
     c.ld = ws->mpad;
     c.linv = ws->chol.linv;
+    {   // pattern-only products when the lists exist and their staging fits the block's shared memory
+        const int bm = c.base_m, bn = c.base_n, k = c.node_k;
+        const bool fit = ws->lists.row16 && ws->lists.m == bm && ws->lists.n == bn && cta_lists_fit(bm, bn, k);
+        c.row_ptr = fit ? ws->lists.row_ptr : nullptr;
+        c.col_ptr = fit ? ws->lists.col_ptr : nullptr;
+        c.row16 = fit ? reinterpret_cast<const uint4 *>(ws->lists.row16) : nullptr;
+        c.col16 = fit ? reinterpret_cast<const uint4 *>(ws->lists.col16) : nullptr;
+        c.col_sign = fit ? ws->lists.col_sign : nullptr;
+    }
     c.warm = ws->warm_ptr;
     c.warm_n = ws->warm_n;
     c.warm_m = ws->warm_m;
@@ -995,6 +1005,7 @@ int sb200_ws_destroy(sb200_ws *ws)
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     drop_graphs(ws);
     free_normal_pattern(&ws->pat);
+    free_compact_lists(&ws->lists);
     free_blocked(&ws->blk_rows);
     free_blocked(&ws->blk_cols);
     chol_work_free(ws->chol);
@@ -1117,6 +1128,17 @@ int sb200_load_model(sb200_ws *ws, int m, int n, int n_orig, long long nnz, cons
         }
     }
     ws->strategy = strat;
+    free_compact_lists(&ws->lists, st);
+    if (strat == SB200_STRATEGY_CHOLESKY && ws->pat.term16 && ws->mpad <= CTA_MAX_MPAD)
+    {   // the one-block solver's products read 2-byte pattern lists instead of the 12-byte CSR / CSC entries
+        const char *off = getenv("SB200_COMPACT_PRODUCTS");
+        if (!(off && off[0] == '0'))
+        {
+            rc = build_compact_lists(ws->err, m, n, ws->csr_offs, ws->csr_inds, ws->csc_colptr, ws->csc_rows, ws->csc_vals,
+                                     &ws->lists, st);
+            if (rc != SB200_OK && rc != SB200_ERR_UNSUPPORTED) return rc;
+        }
+    }
     free_blocked(&ws->blk_rows, st);
     free_blocked(&ws->blk_cols, st);
     if (strat == SB200_STRATEGY_PCG)

@@ -327,6 +327,92 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
     return SB200_OK;
 }
 
+// ---- pattern-only row / column lists (CompactLists) ---------------------------------------------------------
+__global__ void k_list_chunk_counts(int cnt, const int *__restrict__ ptr, unsigned int *__restrict__ out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= cnt; i += gridDim.x * blockDim.x)
+        out[i] = i < cnt ? (unsigned int)(ptr[i + 1] - ptr[i] + 7) >> 3 : 0u;
+}
+// a warp per list: ids narrowed to 2 bytes, the tail of the last chunk filled with `pad`
+__global__ void k_pack_lists16(int cnt, const int *__restrict__ ptr, const int *__restrict__ ids,
+                               const unsigned int *__restrict__ cptr, unsigned short *__restrict__ out, unsigned short pad)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < cnt; i += gridDim.x * wpb)
+    {
+        const int a = ptr[i], len = ptr[i + 1] - a;
+        const size_t o = (size_t)cptr[i] << 3;
+        const int padded = (int)(cptr[i + 1] - cptr[i]) << 3;
+        for (int t = lane; t < padded; t += 32) out[o + t] = t < len ? (unsigned short)ids[a + t] : pad;
+    }
+}
+__global__ void k_col_sign(int n, const int *__restrict__ colptr, const double *__restrict__ vals, double *__restrict__ sign)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        sign[j] = colptr[j + 1] > colptr[j] ? vals[colptr[j]] : 1.0;
+}
+
+void free_compact_lists(CompactLists *p, cudaStream_t st)
+{
+    if (p->row_ptr) cudaFreeAsync(p->row_ptr, st);
+    if (p->col_ptr) cudaFreeAsync(p->col_ptr, st);
+    if (p->row16) cudaFreeAsync(p->row16, st);
+    if (p->col16) cudaFreeAsync(p->col16, st);
+    if (p->col_sign) cudaFreeAsync(p->col_sign, st);
+    *p = CompactLists{};
+}
+
+static int pack_one(ErrorSink &err, int cnt, const int *ptr, const int *ids, unsigned short pad, unsigned int **cptr_out,
+                    unsigned short **list_out, unsigned int *chunks_out, cudaStream_t st)
+{
+    unsigned int *counts = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    SB200_CUDA_TRY(err, cudaMallocAsync(&counts, 4 * (size_t)(cnt + 1), st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(cptr_out, 4 * (size_t)(cnt + 1), st));
+    k_list_chunk_counts<<<grid_for(cnt + 1, 256, 148 * 8), 256, 0, st>>>(cnt, ptr, counts);
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, *cptr_out, cnt + 1, st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(&tmp, tmp_bytes, st));
+    SB200_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, *cptr_out, cnt + 1, st));
+    unsigned int total = 0;
+    SB200_CUDA_TRY(err, cudaMemcpyAsync(&total, *cptr_out + cnt, 4, cudaMemcpyDeviceToHost, st));
+    SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
+    SB200_CUDA_TRY(err, cudaMallocAsync(list_out, 16 * ((size_t)total + 1), st));
+    k_pack_lists16<<<grid_for((long long)cnt * 32, 256, 148 * 8), 256, 0, st>>>(cnt, ptr, ids, *cptr_out, *list_out, pad);
+    SB200_CUDA_TRY(err, cudaGetLastError());
+    cudaFreeAsync(counts, st);
+    cudaFreeAsync(tmp, st);
+    *chunks_out = total;
+    g_launch_count += 3;
+    return SB200_OK;
+}
+
+int build_compact_lists(ErrorSink &err, int m, int n, const int *csr_offs, const int *csr_inds, const int *csc_colptr,
+                        const int *csc_rows, const double *csc_vals, CompactLists *out, cudaStream_t st)
+{
+    free_compact_lists(out, st);
+    if (m >= 65535 || n >= 65535)
+    {
+        err.msg = "build_compact_lists: ids do not fit 2 bytes";
+        return SB200_ERR_UNSUPPORTED;
+    }
+    int rc = pack_one(err, m, csr_offs, csr_inds, (unsigned short)n, &out->row_ptr, &out->row16, &out->row_chunks, st);
+    if (rc == SB200_OK)
+        rc = pack_one(err, n, csc_colptr, csc_rows, (unsigned short)m, &out->col_ptr, &out->col16, &out->col_chunks, st);
+    if (rc != SB200_OK)
+    {
+        free_compact_lists(out, st);
+        return rc;
+    }
+    SB200_CUDA_TRY(err, cudaMallocAsync(&out->col_sign, 8 * (size_t)(n > 0 ? n : 1), st));
+    k_col_sign<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(n, csc_colptr, csc_vals, out->col_sign);
+    SB200_CUDA_TRY(err, cudaGetLastError());
+    ++g_launch_count;
+    out->m = m;
+    out->n = n;
+    return SB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // numeric assembly: one thread per lower-triangular entry
 // ---------------------------------------------------------------------------------------------

@@ -534,8 +534,8 @@ __device__ void cta_solve(const CtaLp &L, double *rhs, unsigned char *smem)
 
 // out[row] = alpha (A x)_row + beta z[row], rows < m: warp per row, four index/value pairs per lane in flight, x staged
 // in shared memory when it fits (every gather is then a shared-memory read)
-__device__ void cta_spmv_csr(const CtaLp &L, const double *x, const double *z, double *out, double alpha, double beta,
-                             unsigned char *smem)
+__device__ void cta_spmv_csr12(const CtaLp &L, const double *x, const double *z, double *out, double alpha, double beta,
+                               unsigned char *smem)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const double *xs = x;
@@ -574,7 +574,7 @@ __device__ void cta_spmv_csr(const CtaLp &L, const double *x, const double *z, d
 // w = A' v by 8 lanes per column (v staged in shared memory), with the epilogues of k_spmv_csc; returns the two minima
 // in every thread
 template <int MODE>
-__device__ void cta_spmv_csc(const CtaLp &L, const double *v, double *red, double *min0, double *min1, unsigned char *smem)
+__device__ void cta_spmv_csc12(const CtaLp &L, const double *v, double *red, double *min0, double *min1, unsigned char *smem)
 {
     const IpmVecs &V = L.V;
     const int tid = threadIdx.x, gl = tid & 7;
@@ -634,6 +634,168 @@ __device__ void cta_spmv_csc(const CtaLp &L, const double *v, double *red, doubl
         *min1 = cta_min(m1, red);
     }
     __syncthreads();
+}
+
+// ---- the same two products over the pattern-only lists of the base model (CompactLists): 2 bytes per entry instead of
+//      12, whole 16-byte chunks per load, chunk pointers and vectors staged in shared memory so that every global load of
+//      a row / column is independent of the others (the 12-byte forms above are chains of dependent loads per column).
+//      The node's branch rows (coef x_var - slack) and their slack columns are added from d_var / d_coef. ----------------
+__device__ void cta_av16(const CtaLp &L, const double *x, const double *z, double *out, double alpha, double beta,
+                         unsigned char *smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int bm = L.base_m, bn = L.base_n;
+    double *xs = reinterpret_cast<double *>(smem);                         // [bn + 1]: sign_j x_j, then the pad slot
+    unsigned int *rp = reinterpret_cast<unsigned int *>(xs + bn + 1);      // [bm + 1]
+    __syncthreads();
+    for (int j = tid; j < bn; j += NT) xs[j] = L.col_sign[j] * x[j];
+    if (tid == 0) xs[bn] = 0.0;
+    for (int i = tid; i <= bm; i += NT) rp[i] = L.row_ptr[i];
+    __syncthreads();
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int r0 = w; r0 < bm; r0 += 2 * NW)
+    {   // two rows per warp at a time, two chunks per lane and row in flight
+        const int r1 = r0 + NW;
+        const bool two = r1 < bm;
+        unsigned int ca = rp[r0] + lane, cb = two ? rp[r1] + lane : 0u;
+        const unsigned int ea = rp[r0 + 1], eb = two ? rp[r1 + 1] : 0u;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        while (ca < ea || cb < eb)
+        {
+            const bool ha0 = ca < ea, ha1 = ca + 32 < ea, hb0 = cb < eb, hb1 = cb + 32 < eb;
+            const uint4 ua0 = ha0 ? __ldg(L.row16 + ca) : zero4, ua1 = ha1 ? __ldg(L.row16 + ca + 32) : zero4;
+            const uint4 ub0 = hb0 ? __ldg(L.row16 + cb) : zero4, ub1 = hb1 ? __ldg(L.row16 + cb + 32) : zero4;
+            if (ha0) a0 += gather8(ua0, xs);
+            if (ha1) a1 += gather8(ua1, xs);
+            if (hb0) b0 += gather8(ub0, xs);
+            if (hb1) b1 += gather8(ub1, xs);
+            ca += 64;
+            cb += 64;
+        }
+        const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
+        if (lane == 0)
+        {
+            out[r0] = (beta == 0.0) ? alpha * sa : alpha * sa + beta * z[r0];
+            if (two) out[r1] = (beta == 0.0) ? alpha * sb : alpha * sb + beta * z[r1];
+        }
+    }
+    for (int r = tid; r < L.node_k; r += NT)
+    {
+        const double acc = L.d_coef[r] * x[L.d_var[r]] - x[bn + r];
+        out[bm + r] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[bm + r];
+    }
+    __syncthreads();
+}
+
+template <int MODE>
+__device__ void cta_atv16(const CtaLp &L, const double *v, double *red, double *min0, double *min1, unsigned char *smem)
+{
+    const IpmVecs &V = L.V;
+    const int tid = threadIdx.x, gl = tid & 7, g = tid >> 3;
+    const int bm = L.base_m, bn = L.base_n, k = L.node_k, n = V.n;
+    double *vs = reinterpret_cast<double *>(smem);                         // [bm + 1 + k]: v of the base rows, pad, node rows
+    double *accs = vs + bm + 1 + k;                                        // [bn + k]: (A' v)_j
+    unsigned int *cp = reinterpret_cast<unsigned int *>(accs + bn + k);    // [bn + 1]
+    __syncthreads();
+    for (int i = tid; i < bm; i += NT) vs[i] = v[i];
+    if (tid == 0) vs[bm] = 0.0;
+    for (int r = tid; r < k; r += NT) vs[bm + 1 + r] = v[bm + r];
+    for (int j = tid; j <= bn; j += NT) cp[j] = L.col_ptr[j];
+    __syncthreads();
+    constexpr int G = NT / 8;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int c0 = g; c0 < bn; c0 += 4 * G)
+    {   // 8 lanes per column, four columns per group in flight
+        unsigned int a[4], e[4];
+        double acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const int cq = c0 + q * G;
+            const bool in = cq < bn;
+            a[q] = in ? cp[cq] + gl : 0u;
+            e[q] = in ? cp[cq + 1] : 0u;
+            acc[q] = 0.0;
+        }
+        while (a[0] < e[0] || a[1] < e[1] || a[2] < e[2] || a[3] < e[3])
+        {
+            uint4 u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[q] = a[q] < e[q] ? __ldg(L.col16 + a[q]) : zero4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                if (a[q] < e[q]) acc[q] += gather8(u[q], vs);
+                a[q] += 8;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const double t = group8_sum(acc[q]);
+            const int cq = c0 + q * G;
+            if (gl == 0 && cq < bn) accs[cq] = t;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < bn; j += NT) accs[j] *= L.col_sign[j];
+    for (int r = tid; r < k; r += NT) accs[bn + r] = -vs[bm + 1 + r];
+    if (k)
+    {
+        __syncthreads();
+        if (tid == 0)
+            for (int r = 0; r < k; ++r) accs[L.d_var[r]] += L.d_coef[r] * vs[bm + 1 + r];
+    }
+    __syncthreads();
+    double m0 = DBL_MAX, m1 = DBL_MAX;
+#pragma unroll 2
+    for (int col = tid; col < n; col += NT)
+    {
+        const double acc = accs[col];
+        if (MODE == CSC_RECOVER)
+        {
+            const double ds = V.resC[col] - acc;
+            const double xj = V.x[col], sj = V.s[col];
+            const double dx = (V.resXS[col] - xj * ds) / sj;
+            V.ds[col] = ds;
+            V.dx[col] = dx;
+            if (dx < 0.0) m0 = fmin(m0, -xj / dx);
+            if (ds < 0.0) m1 = fmin(m1, -sj / ds);
+        }
+        else if (MODE == CSC_START_X)
+        {
+            V.x[col] = acc;
+            m0 = fmin(m0, acc);
+        }
+        else if (MODE == CSC_START_S)
+        {
+            const double sj = V.c[col] - acc;
+            V.s[col] = sj;
+            m1 = fmin(m1, sj);
+        }
+        else if (MODE == CSC_RESC)
+            V.resC[col] = V.c[col] - V.s[col] - acc;
+    }
+    if (MODE != CSC_RESC)
+    {
+        *min0 = cta_min(m0, red);
+        *min1 = cta_min(m1, red);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cta_spmv_csr(const CtaLp &L, const double *x, const double *z, double *out, double alpha,
+                                             double beta, unsigned char *smem)
+{
+    if (L.row16) cta_av16(L, x, z, out, alpha, beta, smem);
+    else cta_spmv_csr12(L, x, z, out, alpha, beta, smem);
+}
+template <int MODE>
+__device__ __forceinline__ void cta_spmv_csc(const CtaLp &L, const double *v, double *red, double *min0, double *min1,
+                                             unsigned char *smem)
+{
+    if (L.row16) cta_atv16<MODE>(L, v, red, min0, min1, smem);
+    else cta_spmv_csc12<MODE>(L, v, red, min0, min1, smem);
 }
 
 __device__ __forceinline__ void prologue_elem(const IpmVecs &V, int j, double xj, double sj, double rc)
@@ -926,6 +1088,13 @@ __global__ void __launch_bounds__(NT, 1) k_ipm_cta(const CtaLp *lps)
 } // namespace
 
 int cta_lp_smem_bytes() { return SMEM_BYTES; }
+
+bool cta_lists_fit(int base_m, int base_n, int node_k)
+{
+    const size_t av = 8 * ((size_t)base_n + 1) + 4 * ((size_t)base_m + 1);
+    const size_t atv = 8 * ((size_t)base_m + 1 + node_k) + 8 * ((size_t)base_n + node_k) + 4 * ((size_t)base_n + 1);
+    return av <= (size_t)OFF_W && atv <= (size_t)OFF_W;
+}
 
 int launch_ipm_cta(const CtaLp *lps, int count, cudaStream_t st)
 {

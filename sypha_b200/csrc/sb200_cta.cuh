@@ -28,6 +28,10 @@ struct CtaLp
     const double *d_coef;
     const int *base_colptr, *base_rows;
     const double *base_cvals;
+    // pattern-only lists of the BASE model for the products (CompactLists), or nullptr: the 12-byte CSR / CSC is read
+    const unsigned int *row_ptr, *col_ptr;
+    const uint4 *row16, *col16;
+    const double *col_sign;
     // factorisation
     double *M;                      // mpad x mpad row-major, identity pad; L in place (lower)
     int ld;
@@ -42,6 +46,8 @@ struct CtaLp
 
 static constexpr int CTA_MAX_MPAD = 2048;      // vectors of the solves live in shared memory
 int cta_lp_smem_bytes();
+// whether the staging of the pattern-only products (vectors + chunk pointers) fits the block's shared memory
+bool cta_lists_fit(int base_m, int base_n, int node_k);
 // one LP per CTA: grid = number of LPs in `lps` (device array)
 int launch_ipm_cta(const CtaLp *lps, int count, cudaStream_t st);
 

@@ -121,6 +121,21 @@ struct NormalPattern
     unsigned int n_chunks = 0;
     int pad_id = -1;                    // the id the pad slots carry (d[pad_id] = 0)
 };
+// pattern-only copies of the model for the one-block solver's products (every column all +1 or all -1, ids < 65535):
+// row i = the column ids of its entries, column j = the row ids, 2 bytes each in whole 16-byte chunks (pad ids: n for
+// the rows, m for the columns - the product kernels keep a zero there), and the sign of every column
+struct CompactLists
+{
+    int m = 0, n = 0;
+    unsigned int *row_ptr = nullptr;    // [m+1], in chunks
+    unsigned int *col_ptr = nullptr;    // [n+1], in chunks
+    unsigned short *row16 = nullptr, *col16 = nullptr;
+    double *col_sign = nullptr;         // [n]
+    unsigned int row_chunks = 0, col_chunks = 0;
+};
+int build_compact_lists(ErrorSink &err, int m, int n, const int *csr_offs, const int *csr_inds, const int *csc_colptr,
+                        const int *csc_rows, const double *csc_vals, CompactLists *out, cudaStream_t st);
+void free_compact_lists(CompactLists *p, cudaStream_t st = 0);
 int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int *csc_colptr,
                          const int *csc_rows, const double *csc_vals, NormalPattern *out,
                          cudaStream_t st, int pad_id = -1);

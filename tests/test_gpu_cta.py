@@ -98,6 +98,37 @@ def test_node_models_and_infeasible_fixings_in_both_forms():
             sb.releaseIpmWorkspace(w)
 
 
+def test_pattern_only_products_match_the_value_carrying_products():
+    """The one-block solver's A v / A' v over the 2-byte pattern lists of the base model (CompactLists, the default where
+    every column is all +1 or all -1) against the same solver reading the 12-byte CSR / CSC entries
+    (SB200_COMPACT_PRODUCTS=0): root LP and node LPs with branch rows, including two rows on one variable."""
+    import os
+    inst, _ = load_golden("scpnre1")
+    env = sb.SyphaEnvironment()
+    cfg = sb.SolverExecutionConfig(maxIterations=100)
+    decs = [(), ((5, 1), (17, 0), (400, 1)), tuple((7 * i + 2, (i + 1) % 2) for i in range(24)), ((9, 1), (9, 1), (30, 0))]
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["SB200_COMPACT_PRODUCTS"] = flag
+        try:
+            base = sb.SyphaNodeSparse.from_csr(inst.m, inst.n, inst.n_orig, inst.offs, inst.inds, inst.vals, inst.c, inst.b, env)
+            wss = [S.workspace_for_nodes(base, 32) for _ in decs]
+            for w in wss:
+                S.set_solver_form(w, "throughput")
+            out[flag] = S.solve_batch_nodes(base, decs, cfg, wss)
+            for w in wss:
+                sb.releaseIpmWorkspace(w)
+        finally:
+            os.environ.pop("SB200_COMPACT_PRODUCTS", None)
+    for a, b in zip(out["1"], out["0"]):
+        assert a.status == b.status == sb.CODE_SUCCESSFUL and a.terminationReason == b.terminationReason
+        assert a.iterations == b.iterations
+        assert abs(a.primalObj - b.primalObj) <= 1e-9 * max(1, abs(b.primalObj))
+        assert abs(a.dualObj - b.dualObj) <= 1e-9 * max(1, abs(b.dualObj))
+        assert np.max(np.abs(a.primalSolution - b.primalSolution)) <= 1e-7 * (1 + np.abs(b.primalSolution).max())
+        assert np.max(np.abs(a.dualSolution - b.dualSolution)) <= 1e-7 * (1 + np.abs(b.dualSolution).max())
+
+
 def test_forms_search_the_same_tree():
     """BatchedBnb over one-CTA node LPs (the default with several slots) and over the multi-kernel form."""
     import os

@@ -704,8 +704,10 @@ __device__ void cta_atv16(const CtaLp &L, const double *v, double *red, double *
     __syncthreads();
     constexpr int G = NT / 8;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    for (int c0 = g; c0 < bn; c0 += 4 * G)
-    {   // 8 lanes per column, four columns per group in flight
+    for (int cw = g & ~3; cw < bn; cw += 4 * G)
+    {   // 8 lanes per column, four columns per group in flight; the trip count is the warp's (the shuffles below need
+        // all 32 lanes), columns beyond the last are empty lists
+        const int c0 = cw + (g & 3);
         unsigned int a[4], e[4];
         double acc[4];
 #pragma unroll

@@ -40,6 +40,7 @@ constexpr int OFF_T = OFF_W + TB * SP * 8;               // 16 x 48 scratch of t
 constexpr int TP = 49;
 constexpr int OFF_RED = OFF_T + 16 * TP * 8;             // reduction scratch
 constexpr int SMEM_BYTES = OFF_RED + 64 * 8;             // 206,?00
+constexpr int ASM_RING = 384;                            // chunks of a warp's ring in the streamed assembly (6 KB)
 constexpr int D_STAGE_MAX = OFF_W / 8;                   // doubles of a staged vector (below the persistent regions)
 static_assert(TB * SP * 8 <= STAGE_A, "the tile scratch must fit the A part of a stage");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -106,6 +107,76 @@ __device__ void cta_assemble(const CtaLp &L, const double *d, unsigned char *sme
     }
     double *M = L.M;
     const int ld = L.ld;
+    const size_t ring_off = ((size_t)L.nd * 8 + 15) & ~(size_t)15;
+    if (dd != d && ring_off + (size_t)NW * ASM_RING * 16 <= (size_t)OFF_RED)
+    {   // STREAMED form.  The chunk lists of a row's entries are ONE contiguous run of 16-byte chunks: the warp copies it
+        // through a ring in shared memory with cp.async, up to ASM_RING chunks ahead of the entries it is summing, so the
+        // DRAM latency of the lists (148 blocks x 38 MB never sit in L2) is paid once per row instead of once per step.
+        // Same accumulators per entry as the loop below ((a0 + a1) + a2 by chunk position), so the same sums.
+        uint4 *ring = reinterpret_cast<uint4 *>(smem + ring_off) + (size_t)w * ASM_RING;
+        for (int i = 1 + w; i < L.base_m; i += NW)
+        {
+            const long long p0 = (long long)i * (i + 1) / 2;
+            const unsigned int cs = __ldg(L.chunk_ptr + p0), ce = __ldg(L.chunk_ptr + p0 + i);
+            unsigned int prod = cs;                                       // first chunk not yet requested
+            unsigned int a_l = ce, e_l = ce;
+            if (lane < i)
+            {
+                a_l = __ldg(L.chunk_ptr + p0 + lane);
+                e_l = __ldg(L.chunk_ptr + p0 + lane + 1);
+            }
+            for (int k0 = 0; k0 < i; k0 += 32)
+            {
+                unsigned int a_n = ce, e_n = ce;                          // the next step's pointers, a step early
+                if (k0 + 32 + lane < i)
+                {
+                    a_n = __ldg(L.chunk_ptr + p0 + k0 + 32 + lane);
+                    e_n = __ldg(L.chunk_ptr + p0 + k0 + 33 + lane);
+                }
+                const unsigned int a_t = __shfl_sync(0xffffffffu, a_l, 0);
+                const unsigned int b_t = __shfl_sync(0xffffffffu, e_l, min(31, i - k0 - 1));
+                __syncwarp();
+                const bool ahead = b_t <= prod;                           // this step's chunks were requested earlier
+                const unsigned int lim = min(ce, a_t + (unsigned int)ASM_RING);
+                for (unsigned int c = prod + lane; c < lim; c += 32) cp_async16(ring + (c - cs) % ASM_RING, L.term8 + c);
+                if (lim > prod) prod = lim;
+                cp_async_commit();
+                if (ahead) cp_async_wait<1>();
+                else cp_async_wait<0>();
+                __syncwarp();
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                if (b_t <= prod)
+                {
+                    for (unsigned int c = a_l; c < e_l; c += 3)
+                    {
+                        const bool h1 = c + 1 < e_l, h2 = c + 2 < e_l;
+                        const uint4 v0 = ring[(c - cs) % ASM_RING];
+                        a0 += gather8(v0, dd);
+                        if (h1) a1 += gather8(ring[(c + 1 - cs) % ASM_RING], dd);
+                        if (h2) a2 += gather8(ring[(c + 2 - cs) % ASM_RING], dd);
+                    }
+                }
+                else
+                {   // a step whose lists exceed the ring: straight from global memory
+                    for (unsigned int c = a_l; c < e_l; c += 3)
+                    {
+                        const bool h1 = c + 1 < e_l, h2 = c + 2 < e_l;
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        const uint4 v0 = __ldg(L.term8 + c), v1 = h1 ? __ldg(L.term8 + c + 1) : z, v2 = h2 ? __ldg(L.term8 + c + 2) : z;
+                        a0 += gather8(v0, dd);
+                        if (h1) a1 += gather8(v1, dd);
+                        if (h2) a2 += gather8(v2, dd);
+                    }
+                }
+                if (k0 + lane < i) M[(size_t)i * ld + k0 + lane] = (a0 + a1) + a2;
+                a_l = a_n;
+                e_l = e_n;
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+        }
+    }
+    else
     // off-diagonal entries (i, k), k < i: a warp per row, lanes along the row (the entry list of a row is contiguous),
     // two entries per lane in flight (16 warps have little else to hide the chunk loads behind).  The accumulator a
     // chunk goes to depends on its position in the entry's list only: the same sums as k_assemble_normal16.

@@ -126,10 +126,10 @@ def test_pattern_only_products_match_the_value_carrying_products():
         assert abs(a.primalObj - b.primalObj) <= 1e-9 * max(1, abs(b.primalObj))
         assert abs(a.dualObj - b.dualObj) <= 1e-9 * max(1, abs(b.dualObj))
         assert np.max(np.abs(a.primalSolution - b.primalSolution)) <= 1e-7 * (1 + np.abs(b.primalSolution).max())
-        if len(set(v for v, _ in dec)) == len(dec):
-            # (the same bound twice is a degenerate pair of active rows: their duals are not determined and the normal
-            # matrix is singular along their difference at the optimum, so only objectives and x are compared there)
-            assert np.max(np.abs(a.dualSolution - b.dualSolution)) <= 1e-7 * (1 + np.abs(b.dualSolution).max())
+        # duals: the base rows only.  A "fix to 0" row (-x_j - t = 0, x_j, t >= 0) has no interior, its dual grows like
+        # 1 / mu and is not a number two summation orders agree on; the same bound twice is a degenerate pair
+        m0 = inst.m
+        assert np.max(np.abs(a.dualSolution[:m0] - b.dualSolution[:m0])) <= 1e-6 * (1 + np.abs(b.dualSolution[:m0]).max())
 
 
 def test_forms_search_the_same_tree():

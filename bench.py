@@ -320,7 +320,8 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
                           "rank0_idle_at_final_barrier_ms": idle_ms,
                           "nodes_sent_by_rank0": st.nodes_sent, "nodes_received_by_rank0": st.nodes_received}
                          if dist else None),
-            "rank0": {"round_ms": st.round_ms[-steps:], "lp_at_iteration_cap": st.maxiter_nodes,
+            "rank0": {"round_ms": st.round_ms[-steps:], "solve_ms": st.solve_ms[-steps:], "window_device_ms": st.window_ms[-steps:],
+                      "heuristics_ms": st.heur_ms[-steps:], "lp_at_iteration_cap": st.maxiter_nodes,
                       "lp_gap_stalled": st.gap_stalled_nodes, "lp_failed": st.infeasible, "pruned": st.pruned_by_bound,
                       "integral": st.integral},
             "h2d_bytes_per_round": int(20 * drows / max(steps, 1)),

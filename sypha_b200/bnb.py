@@ -24,7 +24,7 @@ import numpy as np
 from .instances import ScpModel
 from .solver import (CODE_SUCCESSFUL, IpmWorkspace, SolverExecutionConfig, SolverGapStagnationConfig,
                      SyphaEnvironment, SyphaNodeSparse, get_cover, get_primal, get_rounded, initializeIpmWorkspace,
-                     node_heuristics, releaseIpmWorkspace, set_heuristic_rules, solve_batch, solve_batch_nodes,
+                     last_window, node_heuristics, releaseIpmWorkspace, set_heuristic_rules, solve_batch, solve_batch_nodes,
                      workspace_for_nodes)
 
 TERM_CONVERGED, TERM_MAX_ITER, TERM_GAP_STALLED, TERM_NUMERICAL = 0, 1, 2, 3
@@ -181,6 +181,11 @@ class BnbStats:
     exchange_wait_ms: float = 0.0   # host time blocked in inter-rank collectives (this rank's idle time)
     round_max_iterations: int = 0   # sum over rounds of the longest LP of the window (what a round waits for)
     round_ms: list = dataclasses.field(default_factory=list)
+    # where a round's wall time goes (ms): node deltas + the window's launch + its wait | of which the window's kernel on the
+    # device (CUDA events) | the node-heuristics launch + read-back | host bookkeeping (bounds, branching, frontier)
+    solve_ms: list = dataclasses.field(default_factory=list)
+    window_ms: list = dataclasses.field(default_factory=list)
+    heur_ms: list = dataclasses.field(default_factory=list)
 
 
 class BatchedBnb:
@@ -400,10 +405,15 @@ class BatchedBnb:
                 on_dev = self.device_heuristics
                 export = [self._new_export(i, len(nd.decisions)) for i, nd in enumerate(batch)] if self.warm_start else None
                 warm = [self._warm_arg(nd) for nd in batch] if self.warm_start else None
+                t_s = time.perf_counter()
                 results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self.ws,
                                             fetch_solutions=not on_dev, warm=warm, export=export,
-                                            warm_floor=self.warm_floor)
+                                            warm_floor=self.warm_floor, fetch_trace=False)
+                t_h = time.perf_counter()
                 heur = node_heuristics(self.ws[:len(batch)]) if on_dev else None
+                self.stats.solve_ms.append(round(1e3 * (t_h - t_s), 2))
+                self.stats.heur_ms.append(round(1e3 * (time.perf_counter() - t_h), 2))
+                self.stats.window_ms.append(round(last_window(self.ws[0])[0], 2))
                 self.stats.delta_rows += sum(len(nd.decisions) for nd in batch)
             else:
                 nodes = []

@@ -114,6 +114,8 @@ struct sb200_ws
     CtaLp *batch_dev = nullptr, *batch_host = nullptr;      // a window of LPs in one launch (owned by the window's first slot)
     HeurArgs *hbatch_dev = nullptr, *hbatch_host = nullptr;
     int batch_cap = 0;
+    unsigned char *nd_host = nullptr, *nd_dev = nullptr;   // a window's node deltas: descriptors | var | coef | rhs (lead only)
+    size_t nd_cap = 0;
     double window_ms = 0.0;                 // device time (CUDA events on the launching stream) of the last one-launch window
     int window_lps = 0;
     const double *warm_ptr = nullptr;                  // parent's x | y | s for the next solve (one use)
@@ -347,6 +349,101 @@ __global__ void k_node_csc(int n0, int m0, int k, const int *__restrict__ bptr, 
         }
     }
 }
+// ---- the deltas of a whole window in ONE launch (grid.y = slot): what the four copies and three kernels per slot of
+//      apply_node_delta do, fed from one staged host->device copy ----------------------------------------------------------
+struct NodeDeltaDesc
+{
+    int m0, n0, k, mpad;            // k < 0: the slot keeps its model as it is
+    long long nnz0;
+    const int *s_var;               // staged on the device: var[k], coef[k], rhs[k]
+    const double *s_coef, *s_rhs;
+    int *d_var;
+    double *d_coef, *b, *c;
+    int *csr_offs, *csr_inds;
+    double *csr_vals;
+    const int *bptr, *brows;
+    const double *bvals;
+    int *colptr, *rows;
+    double *vals;
+    double *M;
+};
+__global__ void k_node_delta_batch(const NodeDeltaDesc *__restrict__ descs)
+{
+    const NodeDeltaDesc D = descs[blockIdx.y];
+    const int k = D.k;
+    if (k < 0) return;
+    const int m0 = D.m0, n0 = D.n0, m = m0 + k, mpad = D.mpad;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int r = gt; r < k; r += gsz)
+    {   // the delta arrays the solver reads, the node's right-hand side and objective tail, its CSR rows
+        const int v = D.s_var[r];
+        const double cf = D.s_coef[r];
+        D.d_var[r] = v;
+        D.d_coef[r] = cf;
+        D.b[m0 + r] = D.s_rhs[r];
+        D.c[n0 + r] = 0.0;
+        const long long p = D.nnz0 + 2ll * r;
+        D.csr_inds[p] = v;
+        D.csr_vals[p] = cf;
+        D.csr_inds[p + 1] = n0 + r;
+        D.csr_vals[p + 1] = -1.0;
+        D.csr_offs[m0 + 1 + r] = (int)(p + 2);
+    }
+    {   // node CSC from the base CSC (k_node_csc)
+        const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+        for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j <= n0 + k; j += gridDim.x * wpb)
+        {
+            if (j >= n0)
+            {
+                const int r = j - n0;
+                const int start = D.bptr[n0] + k + r;
+                if (lane == 0)
+                {
+                    D.colptr[j] = start;
+                    if (r < k)
+                    {
+                        D.rows[start] = m0 + r;
+                        D.vals[start] = -1.0;
+                    }
+                }
+                continue;
+            }
+            int shift = 0;
+            for (int r = 0; r < k; ++r) shift += (D.s_var[r] < j) ? 1 : 0;
+            const int a = D.bptr[j], e = D.bptr[j + 1];
+            if (lane == 0) D.colptr[j] = a + shift;
+            for (int t = a + lane; t < e; t += 32)
+            {
+                D.rows[t + shift] = D.brows[t];
+                D.vals[t + shift] = D.bvals[t];
+            }
+            if (lane == 0)
+            {
+                int o = e + shift;
+                for (int r = 0; r < k; ++r)
+                    if (D.s_var[r] == j)
+                    {
+                        D.rows[o] = m0 + r;
+                        D.vals[o] = D.s_coef[r];
+                        ++o;
+                    }
+            }
+        }
+    }
+    // identity pad of M: rows m .. mpad-1 whole, columns m .. mpad-1 of the rows above
+    const int pad = mpad - m;
+    for (long long idx = gt; idx < (long long)pad * mpad; idx += gsz)
+    {
+        const int r = m + (int)(idx / mpad), c = (int)(idx % mpad);
+        D.M[(size_t)r * mpad + c] = (r == c) ? 1.0 : 0.0;
+    }
+    for (long long idx = gt; idx < (long long)m * pad; idx += gsz)
+    {
+        const int r = (int)(idx / pad), c = m + (int)(idx % pad);
+        D.M[(size_t)r * mpad + c] = 0.0;
+    }
+}
+
 // rows m0 .. m0+k-1 of M = A D A' for the node (written whole every iteration: the factorisation is in place)
 __global__ void k_assemble_extra_rows(int m0, int n0, int k, int ld, const int *__restrict__ var,
                                       const double *__restrict__ coef, const int *__restrict__ bptr,
@@ -485,8 +582,16 @@ int run_iteration_pcg(sb200_ws *ws)
 }
 
 // node = base + delta; no allocation, no device-wide synchronisation once the one-time buffers exist
-int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
+struct NodeDeltaHost            // a slot's part of a batched delta: the descriptor + the caller's arrays to stage
 {
+    NodeDeltaDesc d;
+    const int *var;
+    const double *coef, *rhs;
+};
+
+int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta, NodeDeltaHost *batched = nullptr)
+{
+    if (batched) batched->d.k = -1;
     if (!ws->loaded) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: no model loaded");
     const int k = delta ? delta->n_extra_rows : 0;
     if (k < 0) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: negative row count");
@@ -526,6 +631,7 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
         WS_TRY(cudaMemcpyAsync(ws->base_colptr, ws->csc_colptr, sizeof(int) * ((size_t)n0 + 1), cudaMemcpyDeviceToDevice, st));
         WS_TRY(cudaMemcpyAsync(ws->base_rows, ws->csc_rows, sizeof(int) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
         WS_TRY(cudaMemcpyAsync(ws->base_cvals, ws->csc_vals, sizeof(double) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
+        if (batched) WS_TRY(cudaStreamSynchronize(st));       // the batched kernel runs on another stream (the lead's)
         ws->base_csc_valid = true;
     }
     if (k > ws->delta_cap)
@@ -535,6 +641,8 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
         if ((rc = grow(ws, &ws->d_var, (size_t)cap))) return rc;
         if ((rc = grow(ws, &ws->d_coef, (size_t)cap))) return rc;
         if (ws->h_delta) cudaFreeHost(ws->h_delta);
+    if (ws->nd_host) cudaFreeHost(ws->nd_host);
+    if (ws->nd_dev) cudaFree(ws->nd_dev);
         ws->h_delta = nullptr;
         WS_TRY(cudaMallocHost(&ws->h_delta, (size_t)cap * 20));
         ws->delta_cap = cap;
@@ -548,38 +656,56 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta)
         ws->iter_graph = g->second.first;
         ws->iter_graph_kernels = g->second.second;
     }
-    if (k)
+    if (batched)
+    {   // staged and applied with the rest of the window (apply_node_deltas_batched)
+        NodeDeltaDesc &D = batched->d;
+        D.m0 = m0; D.n0 = n0; D.k = k; D.mpad = round_up(m0 + k, SB200_TILE);
+        D.nnz0 = nnz0;
+        D.s_var = nullptr; D.s_coef = nullptr; D.s_rhs = nullptr;
+        D.d_var = ws->d_var; D.d_coef = ws->d_coef; D.b = ws->b; D.c = ws->c;
+        D.csr_offs = ws->csr_offs; D.csr_inds = ws->csr_inds; D.csr_vals = ws->csr_vals;
+        D.bptr = ws->base_colptr; D.brows = ws->base_rows; D.bvals = ws->base_cvals;
+        D.colptr = ws->csc_colptr; D.rows = ws->csc_rows; D.vals = ws->csc_vals;
+        D.M = ws->M;
+        batched->var = k ? delta->var : nullptr;
+        batched->coef = k ? delta->coef : nullptr;
+        batched->rhs = k ? delta->rhs : nullptr;
+    }
+    else
     {
-        // the previous solve's staging copies have completed (every solve ends with a stream sync)
-        int *hv = reinterpret_cast<int *>(ws->h_delta);
-        double *hc = reinterpret_cast<double *>(ws->h_delta + 4 * (size_t)ws->delta_cap);
-        double *hr = hc + ws->delta_cap;
-        for (int r = 0; r < k; ++r)
+        if (k)
         {
-            if (delta->var[r] < 0 || delta->var[r] >= n0)
-                return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: branch variable out of range");
-            hv[r] = delta->var[r];
-            hc[r] = delta->coef[r];
-            hr[r] = delta->rhs[r];
+            // the previous solve's staging copies have completed (every solve ends with a stream sync)
+            int *hv = reinterpret_cast<int *>(ws->h_delta);
+            double *hc = reinterpret_cast<double *>(ws->h_delta + 4 * (size_t)ws->delta_cap);
+            double *hr = hc + ws->delta_cap;
+            for (int r = 0; r < k; ++r)
+            {
+                if (delta->var[r] < 0 || delta->var[r] >= n0)
+                    return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: branch variable out of range");
+                hv[r] = delta->var[r];
+                hc[r] = delta->coef[r];
+                hr[r] = delta->rhs[r];
+            }
+            WS_TRY(cudaMemcpyAsync(ws->d_var, hv, sizeof(int) * k, cudaMemcpyHostToDevice, st));
+            WS_TRY(cudaMemcpyAsync(ws->d_coef, hc, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+            WS_TRY(cudaMemcpyAsync(ws->b + m0, hr, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+            WS_TRY(cudaMemsetAsync(ws->c + n0, 0, sizeof(double) * k, st));
+            k_node_csr_append<<<(k + 63) / 64, 64, 0, st>>>(m0, nnz0, n0, k, ws->d_var, ws->d_coef, ws->csr_offs,
+                                                           ws->csr_inds, ws->csr_vals);
+            ++g_launch_count;
         }
-        WS_TRY(cudaMemcpyAsync(ws->d_var, hv, sizeof(int) * k, cudaMemcpyHostToDevice, st));
-        WS_TRY(cudaMemcpyAsync(ws->d_coef, hc, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        WS_TRY(cudaMemcpyAsync(ws->b + m0, hr, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        WS_TRY(cudaMemsetAsync(ws->c + n0, 0, sizeof(double) * k, st));
-        k_node_csr_append<<<(k + 63) / 64, 64, 0, st>>>(m0, nnz0, n0, k, ws->d_var, ws->d_coef, ws->csr_offs,
-                                                       ws->csr_inds, ws->csr_vals);
+        k_node_csc<<<grid_for((long long)(n0 + k + 1) * 32, 256, 148 * 8), 256, 0, st>>>(
+            n0, m0, k, ws->base_colptr, ws->base_rows, ws->base_cvals, ws->d_var, ws->d_coef, ws->csc_colptr, ws->csc_rows,
+            ws->csc_vals);
         ++g_launch_count;
     }
-    k_node_csc<<<grid_for((long long)(n0 + k + 1) * 32, 256, 148 * 8), 256, 0, st>>>(
-        n0, m0, k, ws->base_colptr, ws->base_rows, ws->base_cvals, ws->d_var, ws->d_coef, ws->csc_colptr, ws->csc_rows,
-        ws->csc_vals);
-    ++g_launch_count;
     ws->m = m0 + k;
     ws->n = n0 + k;
     ws->nnz = nnz0 + 2ll * k;
     ws->mpad = round_up(ws->m, SB200_TILE);
     ws->node_k = k;
-    launch_pad_identity(ws->m, ws->M, ws->mpad, st);
+    if (!batched) launch_pad_identity(ws->m, ws->M, ws->mpad, st);
     int rc = chol_work_ensure(ws->err, ws->chol, ws->mpad);
     if (rc) return rc;
     carve(ws);
@@ -1239,6 +1365,84 @@ static int abort_batch(sb200_ws **wss, int k, int rc)
 // A window of LPs in the throughput form as ONE launch: block i of k_ipm_cta solves the LP resident in wss[i].  The node
 // deltas run on the slots' own streams (a few small kernels each); the first slot's stream waits for them, carries the one
 // LP launch, and is the only thing the host waits on.  No limit of 128 concurrent kernels, no launch per LP.
+// the node deltas of a whole window: host bookkeeping per slot, then ONE staged copy and ONE kernel on the lead's stream
+// (the window's launch follows on the same stream) instead of four copies and three kernels per slot
+static bool deltas_can_batch(sb200_ws **wss, int k)
+{
+    if (k < 2) return false;
+    const char *off = getenv("SB200_BATCHED_DELTAS");
+    if (off && off[0] == '0') return false;
+    for (int i = 0; i < k; ++i)
+        if (!wss[i] || !wss[i]->loaded || wss[i]->device != wss[0]->device || wss[i]->strategy != SB200_STRATEGY_CHOLESKY)
+            return false;
+    return true;
+}
+
+static int apply_node_deltas_batched(sb200_ws **wss, int k, const sb200_node_delta *deltas)
+{
+    sb200_ws *lead = wss[0];
+    sb200_ws *ws = lead;                    // for WS_TRY
+    std::vector<NodeDeltaHost> hd((size_t)k);
+    size_t rows = 0;
+    int rc = SB200_OK, live = 0;
+    for (int i = 0; i < k; ++i)
+    {
+        if ((rc = apply_node_delta(wss[i], &deltas[i], &hd[i])))
+        {   // a rejected delta: the slots before it have changed their dimensions already, so their data still goes out
+            k = i;
+            break;
+        }
+        if (hd[i].d.k >= 0) ++live;
+        if (hd[i].d.k > 0) rows += (size_t)hd[i].d.k;
+    }
+    const int rc_slot = rc;
+    if (!live) return rc_slot;
+    WS_TRY(cudaSetDevice(lead->device));
+    const size_t rows_pad = (rows + 1) & ~(size_t)1;                 // the doubles behind the ids stay 8-byte aligned
+    const size_t off_var = sizeof(NodeDeltaDesc) * (size_t)k, off_coef = off_var + 4 * rows_pad,
+                 off_rhs = off_coef + 8 * rows_pad, bytes = off_rhs + 8 * rows_pad;
+    if (bytes > lead->nd_cap)
+    {
+        if (lead->nd_host) cudaFreeHost(lead->nd_host);
+        if (lead->nd_dev) cudaFree(lead->nd_dev);
+        lead->nd_host = lead->nd_dev = nullptr;
+        lead->nd_cap = 0;
+        const size_t cap = bytes + bytes / 2 + 4096;
+        WS_TRY(cudaMallocHost(&lead->nd_host, cap));
+        WS_TRY(cudaMalloc(&lead->nd_dev, cap));
+        lead->nd_cap = cap;
+    }
+    // (the previous window's copy out of this staging completed: every window ends with a stream synchronisation)
+    NodeDeltaDesc *hdesc = reinterpret_cast<NodeDeltaDesc *>(lead->nd_host);
+    int *hv = reinterpret_cast<int *>(lead->nd_host + off_var);
+    double *hc = reinterpret_cast<double *>(lead->nd_host + off_coef), *hr = reinterpret_cast<double *>(lead->nd_host + off_rhs);
+    size_t o = 0;
+    for (int i = 0; i < k; ++i)
+    {
+        NodeDeltaDesc D = hd[i].d;
+        if (D.k > 0)
+        {
+            for (int r = 0; r < D.k; ++r)
+            {
+                hv[o + r] = hd[i].var[r];
+                hc[o + r] = hd[i].coef[r];
+                hr[o + r] = hd[i].rhs[r];
+            }
+            D.s_var = reinterpret_cast<const int *>(lead->nd_dev + off_var) + o;
+            D.s_coef = reinterpret_cast<const double *>(lead->nd_dev + off_coef) + o;
+            D.s_rhs = reinterpret_cast<const double *>(lead->nd_dev + off_rhs) + o;
+            o += (size_t)D.k;
+        }
+        hdesc[i] = D;
+    }
+    cudaStream_t main = lead->stream;
+    WS_TRY(cudaMemcpyAsync(lead->nd_dev, lead->nd_host, bytes, cudaMemcpyHostToDevice, main));
+    k_node_delta_batch<<<dim3(16, (unsigned)k), 256, 0, main>>>(reinterpret_cast<const NodeDeltaDesc *>(lead->nd_dev));
+    WS_TRY(cudaGetLastError());
+    ++g_launch_count;
+    return rc_slot;
+}
+
 static bool batch_is_one_launch(sb200_ws **wss, int k, const sb200_result *results)
 {
     if (k < 2) return false;
@@ -1255,7 +1459,8 @@ static bool batch_is_one_launch(sb200_ws **wss, int k, const sb200_result *resul
     return true;
 }
 
-static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *params, sb200_result *results)
+static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *params, sb200_result *results,
+                                  bool deltas_on_lead_stream)
 {
     sb200_ws *lead = wss[0];
     sb200_ws *ws = lead;                    // for WS_TRY
@@ -1300,7 +1505,7 @@ static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *par
         w->sc_host->done = 0;
         w->cta_launched = true;
         w->active = true;
-        if (i)
+        if (i && !deltas_on_lead_stream)
         {   // the slot's node-delta kernels (its own stream) before the window's launch
             WS_TRY(cudaEventRecord(w->ev[0], w->stream));
             WS_TRY(cudaStreamWaitEvent(main, w->ev[0], 0));
@@ -1344,14 +1549,26 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     if (!wss || k <= 0 || !params || !results) return SB200_ERR_INVALID;
     std::vector<int> live(k, 0);
     int rc, remaining = 0;
+    bool deltas_on_lead_stream = false;
     if (deltas)
-        for (int i = 0; i < k; ++i)
-            if ((rc = apply_node_delta(wss[i], &deltas[i]))) return abort_batch(wss, k, rc);
+    {
+        if (deltas_can_batch(wss, k))
+        {
+            if ((rc = apply_node_deltas_batched(wss, k, deltas))) return abort_batch(wss, k, rc);
+            deltas_on_lead_stream = true;
+        }
+        else
+            for (int i = 0; i < k; ++i)
+                if ((rc = apply_node_delta(wss[i], &deltas[i]))) return abort_batch(wss, k, rc);
+    }
     for (int i = 0; i < k; ++i)
         if (deltas && deltas[i].export_xys && !results[i].xys_device) results[i].xys_device = deltas[i].export_xys;
-    if (batch_is_one_launch(wss, k, results))
+    const bool one_launch = batch_is_one_launch(wss, k, results);
+    if (deltas_on_lead_stream && !one_launch && cudaStreamSynchronize(wss[0]->stream) != cudaSuccess)
+        return abort_batch(wss, k, SB200_ERR_CUDA);          // the per-slot streams below must see the applied deltas
+    if (one_launch)
     {
-        if ((rc = solve_batch_one_launch(wss, k, params, results))) return abort_batch(wss, k, rc);
+        if ((rc = solve_batch_one_launch(wss, k, params, results, deltas_on_lead_stream))) return abort_batch(wss, k, rc);
         return SB200_OK;
     }
     for (int i = 0; i < k; ++i)

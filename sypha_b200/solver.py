@@ -192,7 +192,7 @@ def _params_from(node: SyphaNodeSparse, config: SolverExecutionConfig) -> L.sb20
     return p
 
 
-def _fill_result(node, ws, res: L.sb200_result, result: SolverExecutionResult, x, y, s):
+def _fill_result(node, ws, res: L.sb200_result, result: SolverExecutionResult, x, y, s, fetch_trace=True):
     lib = L.load()
     result.status = CODE_SUCCESSFUL if res.status == L.SB200_OK else CODE_GENERIC_ERROR
     result.terminationReason = res.reason
@@ -204,9 +204,12 @@ def _fill_result(node, ws, res: L.sb200_result, result: SolverExecutionResult, x
     result.strategyUsed = res.strategy_used
     result.cgIterations = res.cg_iterations
     result.kernelsLaunched = res.kernels_launched
-    tr = np.zeros((max(res.iterations, 1), L.TRACE_COLS))
-    rows = lib.sb200_get_trace(ws.handle, tr.ctypes.data, tr.shape[0])
-    result.trace = tr[:rows]
+    if fetch_trace:
+        tr = np.zeros((max(res.iterations, 1), L.TRACE_COLS))
+        rows = lib.sb200_get_trace(ws.handle, tr.ctypes.data, tr.shape[0])
+        result.trace = tr[:rows]
+    else:
+        result.trace = None
     # node.* outputs, src/sypha_solver.cpp:774-797
     node.iterations = res.iterations
     node.objvalPrim, node.objvalDual = res.primal_obj, res.dual_obj
@@ -396,7 +399,8 @@ def get_rounded(workspace: IpmWorkspace, n_orig: int) -> np.ndarray:
 
 
 def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecutionConfig, workspaces,
-                      fetch_solutions: bool = True, warm=None, export=None, warm_floor: float = 0.1):
+                      fetch_solutions: bool = True, warm=None, export=None, warm_floor: float = 0.1,
+                      fetch_trace: bool = True):
     """B&B node body, batched and device-resident: workspace i holds the base model; node i = base + one row
     per (var, fix) decision (bnb.cpp:453-468) is formed on the device (``sb200_node_delta``) and the LPs are
     solved concurrently.  Returns one SolverExecutionResult per node (solutions have the node's dimensions).
@@ -410,17 +414,23 @@ def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecu
     handles = (C.c_void_p * k)(*[ws.handle for ws in workspaces[:k]])
     deltas = (L.sb200_node_delta * k)()
     res = (L.sb200_result * k)()
-    keep, bufs = [], []
-    for i, dec in enumerate(decisions_list):
-        d = len(dec)
-        var = np.fromiter((v for v, _ in dec), dtype=np.int32, count=d)
-        fix = np.fromiter((f for _, f in dec), dtype=np.float64, count=d)
-        coef = np.where(fix == 0.0, -1.0, 1.0)
-        keep.append((var, coef, fix))
+    bufs = []
+    # every node's (variable, fixing) pairs in three flat arrays; the deltas point into them
+    lens = [len(dec) for dec in decisions_list]
+    flat = np.array([pair for dec in decisions_list for pair in dec], dtype=np.float64).reshape(-1, 2)
+    var = np.ascontiguousarray(flat[:, 0].astype(np.int32))
+    fix = np.ascontiguousarray(flat[:, 1])
+    coef = np.where(fix == 0.0, -1.0, 1.0)
+    keep = (var, coef, fix)
+    vb, cb, fb = var.ctypes.data, coef.ctypes.data, fix.ctypes.data
+    PI, PD = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    o = 0
+    for i, d in enumerate(lens):
         deltas[i].n_extra_rows = d
-        deltas[i].var = var.ctypes.data_as(C.POINTER(C.c_int))
-        deltas[i].coef = coef.ctypes.data_as(C.POINTER(C.c_double))
-        deltas[i].rhs = fix.ctypes.data_as(C.POINTER(C.c_double))
+        deltas[i].var = C.cast(vb + 4 * o, PI)
+        deltas[i].coef = C.cast(cb + 8 * o, PD)
+        deltas[i].rhs = C.cast(fb + 8 * o, PD)
+        o += d
         if warm is not None and warm[i] is not None:
             deltas[i].warm_start, deltas[i].warm_n, deltas[i].warm_m = warm[i]
             deltas[i].warm_floor = warm_floor
@@ -440,6 +450,7 @@ def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecu
     for i in range(k):
         r = SolverExecutionResult()
         shadow = SyphaNodeSparse(base.env)
-        _fill_result(shadow, workspaces[i], res[i], r, *bufs[i])
+        _fill_result(shadow, workspaces[i], res[i], r, *bufs[i], fetch_trace=fetch_trace)
         out.append(r)
+    del keep
     return out

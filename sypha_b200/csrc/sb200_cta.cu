@@ -114,6 +114,7 @@ __device__ void cta_assemble(const CtaLp &L, const double *d, unsigned char *sme
         // DRAM latency of the lists (148 blocks x 38 MB never sit in L2) is paid once per row instead of once per step.
         // Same accumulators per entry as the loop below ((a0 + a1) + a2 by chunk position), so the same sums.
         uint4 *ring = reinterpret_cast<uint4 *>(smem + ring_off) + (size_t)w * ASM_RING;
+        const double *dsm = reinterpret_cast<const double *>(smem);      // = dd, in a form the compiler knows is shared memory
         for (int i = 1 + w; i < L.base_m; i += NW)
         {
             const long long p0 = (long long)i * (i + 1) / 2;
@@ -151,9 +152,9 @@ __device__ void cta_assemble(const CtaLp &L, const double *d, unsigned char *sme
                     {
                         const bool h1 = c + 1 < e_l, h2 = c + 2 < e_l;
                         const uint4 v0 = ring[(c - cs) % ASM_RING];
-                        a0 += gather8(v0, dd);
-                        if (h1) a1 += gather8(ring[(c + 1 - cs) % ASM_RING], dd);
-                        if (h2) a2 += gather8(ring[(c + 2 - cs) % ASM_RING], dd);
+                        a0 += gather8(v0, dsm);
+                        if (h1) a1 += gather8(ring[(c + 1 - cs) % ASM_RING], dsm);
+                        if (h2) a2 += gather8(ring[(c + 2 - cs) % ASM_RING], dsm);
                     }
                 }
                 else
@@ -163,9 +164,9 @@ __device__ void cta_assemble(const CtaLp &L, const double *d, unsigned char *sme
                         const bool h1 = c + 1 < e_l, h2 = c + 2 < e_l;
                         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                         const uint4 v0 = __ldg(L.term8 + c), v1 = h1 ? __ldg(L.term8 + c + 1) : z, v2 = h2 ? __ldg(L.term8 + c + 2) : z;
-                        a0 += gather8(v0, dd);
-                        if (h1) a1 += gather8(v1, dd);
-                        if (h2) a2 += gather8(v2, dd);
+                        a0 += gather8(v0, dsm);
+                        if (h1) a1 += gather8(v1, dsm);
+                        if (h2) a2 += gather8(v2, dsm);
                     }
                 }
                 if (k0 + lane < i) M[(size_t)i * ld + k0 + lane] = (a0 + a1) + a2;

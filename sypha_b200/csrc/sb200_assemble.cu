@@ -199,6 +199,71 @@ __global__ void k_pack_terms16(long long n_pairs, const unsigned int *__restrict
     }
 }
 
+// The one-block solver sums 16 consecutive entries of a row side by side (a half-warp), chunk position by chunk position,
+// and every id is an 8-byte gather from shared memory: 16 random ids hit the 16 double-wide banks three deep on average,
+// and that bank-conflict replay is what bounds its assembly.  The order of the ids INSIDE a chunk is free, so it is chosen
+// here, once per model: for every group of 16 entries and every chunk position the ids are dealt to the 8 slots so that
+// the 16 lanes' ids of one slot fall into different banks wherever a free slot allows it (greedy, pads last).
+__global__ void k_decollide_chunks16(int m, const unsigned int *__restrict__ chunk_ptr, unsigned short *__restrict__ term16,
+                                     unsigned short pad)
+{
+    const int i = blockIdx.y + 1;
+    if (i >= m) return;
+    const long long p0 = (long long)i * (i + 1) / 2;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g * 16 < i; g += gridDim.x * blockDim.x)
+    {
+        const int k0 = g * 16, cnt = min(16, i - k0);
+        unsigned int a[16], len[16];
+        unsigned int maxlen = 0;
+        for (int l = 0; l < 16; ++l)
+        {
+            a[l] = l < cnt ? chunk_ptr[p0 + k0 + l] : 0u;
+            len[l] = l < cnt ? chunk_ptr[p0 + k0 + l + 1] - a[l] : 0u;
+            maxlen = max(maxlen, len[l]);
+        }
+        for (unsigned int j = 0; j < maxlen; ++j)
+        {
+            unsigned int mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // banks taken, per slot
+            for (int l = 0; l < cnt; ++l)
+            {
+                if (j >= len[l]) continue;
+                uint4 *chunk = reinterpret_cast<uint4 *>(term16) + a[l] + j;
+                const uint4 v = *chunk;
+                const unsigned short ids[8] = {(unsigned short)(v.x & 0xffffu), (unsigned short)(v.x >> 16),
+                                               (unsigned short)(v.y & 0xffffu), (unsigned short)(v.y >> 16),
+                                               (unsigned short)(v.z & 0xffffu), (unsigned short)(v.z >> 16),
+                                               (unsigned short)(v.w & 0xffffu), (unsigned short)(v.w >> 16)};
+                unsigned short out[8];
+                unsigned int used = 0;
+                for (int t = 0; t < 8; ++t)
+                {
+                    const unsigned short id = ids[t];
+                    if (id == pad) continue;
+                    const unsigned int bit = 1u << (id & 15);
+                    int best = -1;
+                    for (int qq = 0; qq < 8 && best < 0; ++qq)
+                    {
+                        const int q = (qq + l) & 7;
+                        if (!((used >> q) & 1u) && !(mask[q] & bit)) best = q;
+                    }
+                    for (int qq = 0; qq < 8 && best < 0; ++qq)
+                    {
+                        const int q = (qq + l) & 7;
+                        if (!((used >> q) & 1u)) best = q;
+                    }
+                    used |= 1u << best;
+                    out[best] = id;
+                    mask[best] |= bit;
+                }
+                for (int q = 0; q < 8; ++q)
+                    if (!((used >> q) & 1u)) out[q] = pad;
+                *chunk = make_uint4((unsigned int)out[0] | ((unsigned int)out[1] << 16), (unsigned int)out[2] | ((unsigned int)out[3] << 16),
+                                    (unsigned int)out[4] | ((unsigned int)out[5] << 16), (unsigned int)out[6] | ((unsigned int)out[7] << 16));
+            }
+        }
+    }
+}
+
 void free_normal_pattern(NormalPattern *p, cudaStream_t st)
 {
     if (p->chunk_ptr) cudaFreeAsync(p->chunk_ptr, st);
@@ -311,6 +376,15 @@ int build_normal_pattern(ErrorSink &err, int m, int n, long long nnz, const int 
         SB200_CUDA_TRY(err, cudaMallocAsync(&out->term16, 16 * ((size_t)total + 1), st));
         k_pack_terms16<<<grid_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(n_pairs, out->pair_ptr, out->term_col,
                                                                         out->chunk_ptr, out->term16, (unsigned short)pad_id);
+        {
+            const char *off = getenv("SB200_DECOLLIDE");
+            if (!(off && off[0] == '0') && m > 1)
+            {
+                k_decollide_chunks16<<<dim3((unsigned)((m / 16 + 63) / 64 > 0 ? (m / 16 + 63) / 64 : 1), (unsigned)(m - 1)), 64, 0, st>>>(
+                    m, out->chunk_ptr, out->term16, (unsigned short)pad_id);
+                ++g_launch_count;
+            }
+        }
         SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
         out->n_chunks = total;
         out->pad_id = pad_id;

@@ -5,7 +5,7 @@ tag=${1:-prof}
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pcg-block --no-bnb-block --no-e2e --no-phases --quick-single"
 $B > gpurun_out/${tag}_plain_bench.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/${tag}_launches_bench.csv $B > gpurun_out/${tag}_ncu_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/${tag}_launches_bench.csv $B > gpurun_out/${tag}_ncu_bench.log 2>&1
 echo "bench launch list rc=$?"
 P="python scripts/prof_window.py 148 2"
 $P > gpurun_out/${tag}_plain_window.log 2>&1 && \

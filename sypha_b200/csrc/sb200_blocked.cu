@@ -16,6 +16,8 @@
 #include "sb200_kernels.cuh"
 #include "sb200_pcg.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 namespace sb200 {
@@ -285,8 +287,13 @@ static void launch_blk_rows(const BlockedPattern &B, bool abs_mode, const double
         cudaFuncSetAttribute(k_blk_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16386 * 8);
         cudaFuncSetAttribute(k_blk_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16386 * 8);
     }
-    // row chunks so that (vector blocks x chunks) fills the SMs about once
-    int chunks = (148 + B.nblk - 1) / B.nblk;
+    // row chunks: (vector blocks x chunks) CTAs at one CTA per SM (the staged block takes 128 KB).  About four waves of
+    // the 148 SMs, so that the last, partial wave costs little (65 blocks x 3 chunks = 195 CTAs ran as 148 + 47: the GPU
+    // a third full for half of the kernel), but never fewer than two segments per thread
+    int chunks = (148 * 4) / B.nblk;
+    const char *cw = getenv("SB200_BLK_ROW_WAVES");
+    if (cw && atoi(cw) > 0) chunks = (148 * atoi(cw)) / B.nblk;
+    chunks = std::min(chunks, B.majors / (2 * BLK_ROW_THREADS));
     if (chunks < 1) chunks = 1;
     int rows_per_chunk = (B.majors + chunks - 1) / chunks;
     rows_per_chunk = (rows_per_chunk + 31) / 32 * 32;

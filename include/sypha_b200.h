@@ -187,7 +187,12 @@ int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result);
  * sb200_solve / x_host, y_host, s_host have the node's dimensions (m + k, n + k). */
 int sb200_set_node_delta(sb200_ws *ws, const sb200_node_delta *delta);
 /* k independent LPs, one workspace (own stream) each, solved concurrently.  deltas == NULL: the
- * workspaces' resident models as they are; otherwise deltas[i] is applied to wss[i] first. */
+ * workspaces' resident models as they are; otherwise deltas[i] is applied to wss[i] first.
+ * With every workspace on one device and in the throughput form (sb200_set_solver_form / sb200_set_concurrency_hint)
+ * the batch is a WINDOW: all deltas are staged in one host->device copy and applied by one kernel, the k LPs are ONE
+ * launch of k thread blocks on wss[0]'s stream (any k; 148 = one block per SM of a B200; more blocks queue in the
+ * hardware scheduler and start as SMs free up), results[i].x_host / y_host / s_host are filled behind it.
+ * sb200_last_window(wss[0], ...) then reports the device time of that launch. */
 int sb200_solve_batch(sb200_ws **ws, int k, const sb200_node_delta *deltas,
                       const sb200_params *params, sb200_result *results);
 

@@ -223,107 +223,6 @@ k_blk_rows(BlockedPattern B, const double *__restrict__ v, int rows_per_chunk, c
     }
 }
 
-// ---- streamed form of the same kernel -------------------------------------------------------------------------
-// The segments a CTA sums are ONE contiguous run of 16-byte chunks (entries are ordered by (vector block, row)).  Thread
-// per segment with its own global loads pays a DRAM latency per segment and thread (~4 us per batch of 1024 segments
-// measured, against ~1.6 us of shared-memory gather work).  Here the CTA copies the run of the NEXT batch of 1024 rows
-// into a shared-memory ring with cp.async while it sums the current one out of the ring: the global latency leaves the
-// per-segment chain.  Same sums in the same order as blk_segment_sum.
-static constexpr int BLK_RING_HALF = 3072;       // chunks per half of the ring (48 KB)
-
-__device__ __forceinline__ void blk_cp_async16(void *dst_smem, const void *src)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
-}
-
-template <bool USE_SIGN>
-__device__ __forceinline__ double blk_segment_sum_ring(const uint4 *ring, unsigned a, unsigned e, const double *xs)
-{
-    double acc0 = 0.0, acc1 = 0.0;
-    for (unsigned ch = a; ch < e; ch += 3)
-    {
-        const uint4 v0 = ring[ch];
-        blk_chunk<USE_SIGN>(v0, xs, acc0, acc1);
-        if (ch + 1 < e) blk_chunk<USE_SIGN>(ring[ch + 1], xs, acc0, acc1);
-        if (ch + 2 < e) blk_chunk<USE_SIGN>(ring[ch + 2], xs, acc0, acc1);
-    }
-    return acc0 + acc1;
-}
-
-template <bool ABS>
-__global__ void __launch_bounds__(BLK_ROW_THREADS, 1)
-k_blk_rows_stream(BlockedPattern B, const double *__restrict__ v, int rows_per_chunk, const int *__restrict__ skip, int xs_doubles)
-{
-    extern __shared__ __align__(16) double xs[];
-    if (skip && *skip) return;
-    uint4 *ring = reinterpret_cast<uint4 *>(xs + xs_doubles);
-    const int cb = blockIdx.x, tid = threadIdx.x;
-    const int base = cb * B.nb, width = min(B.nb, B.minors - base);
-    const int r_lo = blockIdx.y * rows_per_chunk, r_hi = min(B.majors, r_lo + rows_per_chunk);
-    const unsigned *__restrict__ ptr = B.ptr + (size_t)cb * B.majors;
-    const uint4 *ent8 = reinterpret_cast<const uint4 *>(B.ent);
-    double *out = B.partial + (size_t)cb * B.majors;
-    const int nbatch = (r_hi - r_lo + BLK_ROW_THREADS - 1) / BLK_ROW_THREADS;
-    // chunk range of batch b (block-uniform): [ptr[r_lo + 1024 b], ptr[min(r_lo + 1024 (b + 1), r_hi)])
-    unsigned ba = 0, be = 0;
-    if (nbatch > 0)
-    {
-        ba = __ldg(ptr + r_lo);
-        be = __ldg(ptr + min(r_lo + BLK_ROW_THREADS, r_hi));
-        if (be - ba <= (unsigned)BLK_RING_HALF)
-            for (unsigned c = ba + tid; c < be; c += BLK_ROW_THREADS) blk_cp_async16(ring + (c - ba), ent8 + c);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int i = tid; i < width; i += BLK_ROW_THREADS)
-        xs[i] = v[base + i];
-    if (tid == 0) xs[B.nb] = 0.0;
-    int row = r_lo + tid;
-    unsigned a = 0, e = 0;
-    if (row < r_hi)
-    {
-        a = __ldg(ptr + row);
-        e = __ldg(ptr + row + 1);
-    }
-    for (int b = 0; b < nbatch; ++b)
-    {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                      // batch b is in its half (and xs is staged); everybody is done with batch b - 1
-        unsigned na_b = 0, ne_b = 0;
-        if (b + 1 < nbatch)
-        {
-            const int rb = r_lo + (b + 1) * BLK_ROW_THREADS;
-            na_b = __ldg(ptr + rb);
-            ne_b = __ldg(ptr + min(rb + BLK_ROW_THREADS, r_hi));
-            if (ne_b - na_b <= (unsigned)BLK_RING_HALF)
-            {
-                uint4 *dst = ring + ((b + 1) & 1) * BLK_RING_HALF;
-                for (unsigned c = na_b + tid; c < ne_b; c += BLK_ROW_THREADS) blk_cp_async16(dst + (c - na_b), ent8 + c);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        const int nrow = row + BLK_ROW_THREADS;
-        unsigned na = 0, ne = 0;
-        if (nrow < r_hi)
-        {
-            na = __ldg(ptr + nrow);
-            ne = __ldg(ptr + nrow + 1);
-        }
-        if (row < r_hi)
-        {
-            if (be - ba <= (unsigned)BLK_RING_HALF)
-                out[row] = blk_segment_sum_ring<!ABS>(ring + (b & 1) * BLK_RING_HALF - ba, a, e, xs);
-            else
-                out[row] = blk_segment_sum<!ABS>(ent8, a, e, xs);       // a batch whose run exceeds the ring
-        }
-        row = nrow;
-        a = na;
-        e = ne;
-        ba = na_b;
-        be = ne_b;
-    }
-}
-
 // out[row] = epilogue(sum_cb partial[cb][row]);  EPI 0: alpha*s + beta*z, 1: s, 2: CG (Ap = s, p.Ap)
 template <int EPI>
 __global__ void __launch_bounds__(256)
@@ -401,28 +300,7 @@ static void launch_blk_rows(const BlockedPattern &B, bool abs_mode, const double
     chunks = (B.majors + rows_per_chunk - 1) / rows_per_chunk;
     const dim3 grid(B.nblk, chunks);
     const size_t smem = sizeof(double) * ((size_t)B.nb + 2);
-    const int xs_doubles = (B.nb + 2 + 1) & ~1;                                   // the ring behind it stays 16-byte aligned
-    const size_t smem_stream = sizeof(double) * (size_t)xs_doubles + 2 * (size_t)BLK_RING_HALF * 16;
-    static int stream_on = -1;
-    if (stream_on < 0)
-    {
-        const char *off = getenv("SB200_BLK_STREAM");
-        stream_on = (off && off[0] == '0') ? 0 : 1;
-    }
-    if (stream_on && smem_stream <= 227 * 1024)
-    {
-        static unsigned long long attr_seen2 = 0;
-        if (first_use_on_device(attr_seen2))
-        {
-            cudaFuncSetAttribute(k_blk_rows_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            cudaFuncSetAttribute(k_blk_rows_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        }
-        if (abs_mode)
-            k_blk_rows_stream<true><<<grid, BLK_ROW_THREADS, smem_stream, st>>>(B, v, rows_per_chunk, skip, xs_doubles);
-        else
-            k_blk_rows_stream<false><<<grid, BLK_ROW_THREADS, smem_stream, st>>>(B, v, rows_per_chunk, skip, xs_doubles);
-    }
-    else if (abs_mode)
+    if (abs_mode)
         k_blk_rows<true><<<grid, BLK_ROW_THREADS, smem, st>>>(B, v, rows_per_chunk, skip);
     else
         k_blk_rows<false><<<grid, BLK_ROW_THREADS, smem, st>>>(B, v, rows_per_chunk, skip);

@@ -233,22 +233,30 @@ k_blk_rows_reduce(BlockedPattern B, const double *__restrict__ z, double *__rest
     if (EPI == 2)
         if (sc->cg_done) return;
     double dot = 0.0;
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < B.majors; row += gridDim.x * blockDim.x)
+    // 8 lanes per row: lane l takes the vector blocks l, l + 8, ... (65 strided reads per row at 50k x 1M; one thread per
+    // row summed them as four chains of 16 dependent latencies: 33.6 us for 26 MB that sit in L2), then a fixed-order
+    // shuffle reduction inside the group
+    const int gl = threadIdx.x & 7;
+    const int groups = (gridDim.x * blockDim.x) >> 3;
+    const int rows_round = (B.majors + groups - 1) / groups * groups;          // whole warps stay in the loop (shuffles)
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < rows_round; row += groups)
     {
-        // four independent chains: the loads of one row are nblk strided reads (65 at 50k x 1M); summed
-        // one after the other they exposed one latency each (33.6 us for 26 MB in the CG epilogue form)
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int cb = 0;
-        for (; cb + 4 <= B.nblk; cb += 4)
+        double s0 = 0.0, s1 = 0.0;
+        if (row < B.majors)
         {
-            s0 += B.partial[(size_t)cb * B.majors + row];
-            s1 += B.partial[(size_t)(cb + 1) * B.majors + row];
-            s2 += B.partial[(size_t)(cb + 2) * B.majors + row];
-            s3 += B.partial[(size_t)(cb + 3) * B.majors + row];
+            int cb = gl;
+            for (; cb + 8 < B.nblk; cb += 16)
+            {
+                s0 += B.partial[(size_t)cb * B.majors + row];
+                s1 += B.partial[(size_t)(cb + 8) * B.majors + row];
+            }
+            if (cb < B.nblk) s0 += B.partial[(size_t)cb * B.majors + row];
         }
-        for (; cb < B.nblk; ++cb)
-            s0 += B.partial[(size_t)cb * B.majors + row];
-        const double s = (s0 + s1) + (s2 + s3);
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (gl != 0 || row >= B.majors) continue;
         if (EPI == 0)
             out[row] = (beta == 0.0) ? alpha * s : alpha * s + beta * z[row];
         else if (EPI == 1)
@@ -311,19 +319,19 @@ void launch_blk_spmv_rows(const BlockedPattern &B, const double *x, const double
                           double beta, cudaStream_t st)
 {
     launch_blk_rows(B, false, x, nullptr, st);
-    k_blk_rows_reduce<0><<<grid_for(B.majors, 256), 256, 0, st>>>(B, z, out, alpha, beta, PcgVecs{}, nullptr);
+    k_blk_rows_reduce<0><<<grid_for((long long)B.majors * 8, 256, 148 * 8), 256, 0, st>>>(B, z, out, alpha, beta, PcgVecs{}, nullptr);
     ++g_launch_count;
 }
 void launch_blk_jacobi_diag(const BlockedPattern &B, const double *d, double *diag, cudaStream_t st)
 {
     launch_blk_rows(B, true, d, nullptr, st);
-    k_blk_rows_reduce<1><<<grid_for(B.majors, 256), 256, 0, st>>>(B, nullptr, diag, 1.0, 0.0, PcgVecs{}, nullptr);
+    k_blk_rows_reduce<1><<<grid_for((long long)B.majors * 8, 256, 148 * 8), 256, 0, st>>>(B, nullptr, diag, 1.0, 0.0, PcgVecs{}, nullptr);
     ++g_launch_count;
 }
 void launch_blk_cg_matvec(const BlockedPattern &B, const PcgVecs &C, Scalars *sc, cudaStream_t st)
 {
     launch_blk_rows(B, false, C.q, &sc->cg_done, st);
-    k_blk_rows_reduce<2><<<grid_for(B.majors, 256), 256, 0, st>>>(B, nullptr, nullptr, 1.0, 0.0, C, sc);
+    k_blk_rows_reduce<2><<<grid_for((long long)B.majors * 8, 256, 148 * 8), 256, 0, st>>>(B, nullptr, nullptr, 1.0, 0.0, C, sc);
     ++g_launch_count;
 }
 

@@ -78,6 +78,70 @@ __global__ void k_blk_pad(int majors, int nblk, int nb, const unsigned *__restri
             ent[pos] = (unsigned short)nb;
 }
 
+// Both product kernels sum 16 consecutive majors side by side (a half-warp), chunk position by chunk position, every entry
+// an 8-byte gather from the staged vector block: the order of the entries INSIDE a chunk is free and is chosen here so that
+// the 16 lanes' entries of one slot fall into different shared-memory banks where a free slot allows it (greedy, pads
+// last) - the same idea as k_decollide_chunks16 for the normal-matrix structure.
+__global__ void k_blk_decollide(int majors, int nblk, const unsigned *__restrict__ ptr, unsigned short *__restrict__ ent,
+                                unsigned short pad)
+{
+    const int groups = (majors + 15) / 16;
+    const size_t total = (size_t)nblk * groups;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    {
+        const int cb = (int)(t / groups), g = (int)(t % groups);
+        const int i0 = g * 16, cnt = min(16, majors - i0);
+        const unsigned *p = ptr + (size_t)cb * majors + i0;
+        unsigned a[16], len[16], maxlen = 0;
+        for (int l = 0; l < 16; ++l)
+        {
+            a[l] = l < cnt ? p[l] : 0u;
+            len[l] = l < cnt ? p[l + 1] - a[l] : 0u;
+            maxlen = max(maxlen, len[l]);
+        }
+        for (unsigned j = 0; j < maxlen; ++j)
+        {
+            unsigned mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int l = 0; l < cnt; ++l)
+            {
+                if (j >= len[l]) continue;
+                uint4 *chunk = reinterpret_cast<uint4 *>(ent) + a[l] + j;
+                const uint4 v = *chunk;
+                const unsigned short ids[8] = {(unsigned short)(v.x & 0xffffu), (unsigned short)(v.x >> 16),
+                                               (unsigned short)(v.y & 0xffffu), (unsigned short)(v.y >> 16),
+                                               (unsigned short)(v.z & 0xffffu), (unsigned short)(v.z >> 16),
+                                               (unsigned short)(v.w & 0xffffu), (unsigned short)(v.w >> 16)};
+                unsigned short out[8];
+                unsigned used = 0;
+                for (int q8 = 0; q8 < 8; ++q8)
+                {
+                    const unsigned short id = ids[q8];
+                    if (id == pad) continue;
+                    const unsigned bit = 1u << (id & 15);
+                    int best = -1;
+                    for (int qq = 0; qq < 8 && best < 0; ++qq)
+                    {
+                        const int q = (qq + l) & 7;
+                        if (!((used >> q) & 1u) && !(mask[q] & bit)) best = q;
+                    }
+                    for (int qq = 0; qq < 8 && best < 0; ++qq)
+                    {
+                        const int q = (qq + l) & 7;
+                        if (!((used >> q) & 1u)) best = q;
+                    }
+                    used |= 1u << best;
+                    out[best] = id;
+                    mask[best] |= bit;
+                }
+                for (int q = 0; q < 8; ++q)
+                    if (!((used >> q) & 1u)) out[q] = pad;
+                *chunk = make_uint4((unsigned)out[0] | ((unsigned)out[1] << 16), (unsigned)out[2] | ((unsigned)out[3] << 16),
+                                    (unsigned)out[4] | ((unsigned)out[5] << 16), (unsigned)out[6] | ((unsigned)out[7] << 16));
+            }
+        }
+    }
+}
+
 void free_blocked(BlockedPattern *p, cudaStream_t st)
 {
     if (p->ptr) cudaFreeAsync(p->ptr, st);
@@ -125,6 +189,15 @@ int build_blocked(ErrorSink &err, int majors, int minors, long long nnz, const i
     k_blk_fill<<<grid_for(majors, 128, 148 * 32), 128, 0, st>>>(majors, mptr, midx, vals, nb, cursor, out->ent);
     k_blk_pad<<<grid_for((long long)nseg, 256, 148 * 16), 256, 0, st>>>(majors, nblk, nb, out->ptr, cursor, out->ent);
     g_launch_count += 5;
+    {
+        const char *off = getenv("SB200_DECOLLIDE");
+        if (!(off && off[0] == '0'))
+        {
+            k_blk_decollide<<<grid_for((long long)nblk * ((majors + 15) / 16), 128, 148 * 32), 128, 0, st>>>(
+                majors, nblk, out->ptr, out->ent, (unsigned short)nb);
+            ++g_launch_count;
+        }
+    }
     if (with_partials) SB200_CUDA_TRY(err, cudaMallocAsync(&out->partial, sizeof(double) * nseg, st));
     SB200_CUDA_TRY(err, cudaStreamSynchronize(st));
     cudaFreeAsync(cnt, st); cudaFreeAsync(cursor, st); cudaFreeAsync(general, st); cudaFreeAsync(tmp, st);

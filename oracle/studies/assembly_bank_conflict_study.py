@@ -49,3 +49,37 @@ for i in (200,500,800,999):
             half=[e[j] for e in ent if j<len(e)]
             tot0+=wave(half); tot1+=wave(greedy(half)); cnt+=8
 print('avg wavefronts per half-warp gather: before',tot0/cnt,'after',tot1/cnt)
+
+
+def greedy_counts(half):
+    """place every id in the lane's free slot where its bank has been used least (counts instead of a taken/free mask)"""
+    cntq = [[0] * 16 for _ in range(8)]
+    out = []
+    for l, c in enumerate(half):
+        o = [None] * 8
+        used = 0
+        for id_ in c:
+            if id_ == pad:
+                continue
+            b = id_ & 15
+            best, bc = -1, 1 << 30
+            for qq in range(8):
+                q = (qq + l) & 7
+                if not (used >> q) & 1 and cntq[q][b] < bc:
+                    best, bc = q, cntq[q][b]
+            used |= 1 << best
+            o[best] = id_
+            cntq[best][b] += 1
+        out.append([pad if x is None else x for x in o])
+    return out
+
+
+tot2 = cnt2 = 0
+for i in (200, 500, 800, 999):
+    for g in range(0, min(i, 160), 16):
+        ent = [chunks_of(i, k) for k in range(g, min(g + 16, i))]
+        for j in range(max(len(e) for e in ent)):
+            half = [e[j] for e in ent if j < len(e)]
+            tot2 += wave(greedy_counts(half))
+            cnt2 += 8
+print('count-balancing greedy:', tot2 / cnt2)

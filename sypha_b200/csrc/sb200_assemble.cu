@@ -203,7 +203,7 @@ __global__ void k_pack_terms16(long long n_pairs, const unsigned int *__restrict
 // and every id is an 8-byte gather from shared memory: 16 random ids hit the 16 double-wide banks three deep on average,
 // and that bank-conflict replay is what bounds its assembly.  The order of the ids INSIDE a chunk is free, so it is chosen
 // here, once per model: for every group of 16 entries and every chunk position the ids are dealt to the 8 slots so that
-// the 16 lanes' ids of one slot fall into different banks wherever a free slot allows it (greedy, pads last).
+// the 16 lanes' ids of one slot fall into different banks as far as possible (greedy: every id goes to the free slot where its bank has been used least; pads last).
 __global__ void k_decollide_chunks16(int m, const unsigned int *__restrict__ chunk_ptr, unsigned short *__restrict__ term16,
                                      unsigned short pad)
 {
@@ -223,7 +223,9 @@ __global__ void k_decollide_chunks16(int m, const unsigned int *__restrict__ chu
         }
         for (unsigned int j = 0; j < maxlen; ++j)
         {
-            unsigned int mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // banks taken, per slot
+            unsigned char load[8][16];                                     // ids per (slot, bank) so far
+            for (int q = 0; q < 8; ++q)
+                for (int b = 0; b < 16; ++b) load[q][b] = 0;
             for (int l = 0; l < cnt; ++l)
             {
                 if (j >= len[l]) continue;
@@ -239,21 +241,20 @@ __global__ void k_decollide_chunks16(int m, const unsigned int *__restrict__ chu
                 {
                     const unsigned short id = ids[t];
                     if (id == pad) continue;
-                    const unsigned int bit = 1u << (id & 15);
-                    int best = -1;
-                    for (int qq = 0; qq < 8 && best < 0; ++qq)
-                    {
+                    const int bank = id & 15;
+                    int best = -1, best_load = 1 << 30;
+                    for (int qq = 0; qq < 8; ++qq)
+                    {   // the free slot where this bank has been used least
                         const int q = (qq + l) & 7;
-                        if (!((used >> q) & 1u) && !(mask[q] & bit)) best = q;
-                    }
-                    for (int qq = 0; qq < 8 && best < 0; ++qq)
-                    {
-                        const int q = (qq + l) & 7;
-                        if (!((used >> q) & 1u)) best = q;
+                        if (!((used >> q) & 1u) && (int)load[q][bank] < best_load)
+                        {
+                            best = q;
+                            best_load = load[q][bank];
+                        }
                     }
                     used |= 1u << best;
                     out[best] = id;
-                    mask[best] |= bit;
+                    ++load[best][bank];
                 }
                 for (int q = 0; q < 8; ++q)
                     if (!((used >> q) & 1u)) out[q] = pad;

@@ -101,7 +101,9 @@ __global__ void k_blk_decollide(int majors, int nblk, const unsigned *__restrict
         }
         for (unsigned j = 0; j < maxlen; ++j)
         {
-            unsigned mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            unsigned char load[8][16];                                     // ids per (slot, bank) so far
+            for (int q = 0; q < 8; ++q)
+                for (int b = 0; b < 16; ++b) load[q][b] = 0;
             for (int l = 0; l < cnt; ++l)
             {
                 if (j >= len[l]) continue;
@@ -117,21 +119,20 @@ __global__ void k_blk_decollide(int majors, int nblk, const unsigned *__restrict
                 {
                     const unsigned short id = ids[q8];
                     if (id == pad) continue;
-                    const unsigned bit = 1u << (id & 15);
-                    int best = -1;
-                    for (int qq = 0; qq < 8 && best < 0; ++qq)
-                    {
+                    const int bank = id & 15;
+                    int best = -1, best_load = 1 << 30;
+                    for (int qq = 0; qq < 8; ++qq)
+                    {   // the free slot where this bank has been used least
                         const int q = (qq + l) & 7;
-                        if (!((used >> q) & 1u) && !(mask[q] & bit)) best = q;
-                    }
-                    for (int qq = 0; qq < 8 && best < 0; ++qq)
-                    {
-                        const int q = (qq + l) & 7;
-                        if (!((used >> q) & 1u)) best = q;
+                        if (!((used >> q) & 1u) && (int)load[q][bank] < best_load)
+                        {
+                            best = q;
+                            best_load = load[q][bank];
+                        }
                     }
                     used |= 1u << best;
                     out[best] = id;
-                    mask[best] |= bit;
+                    ++load[best][bank];
                 }
                 for (int q = 0; q < 8; ++q)
                     if (!((used >> q) & 1u)) out[q] = pad;

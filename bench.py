@@ -259,6 +259,7 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
     drv = bnb.BatchedBnb.with_reference_presolve(
         mdl, slots=slots, device=local_rank, device_heuristics=not args.host_heuristics, share_gpu=not args.no_share,
         poll_every=1, node_lp=args.node_lp, async_exchange=ax, warm_start=args.warm_start,
+        pipeline=1 if stream_factor > 0 else args.bnb_pipeline,
         rebalance=rebalance if (dist is not None and not args.no_donation) else None)
     red = drv.base
     # every rank expands the same first levels (deterministic, no exchange yet), then keeps its round-robin share
@@ -270,6 +271,7 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
     drv.frontier.extend(mine)
     for _ in range(warmup):                        # untimed full windows: every slot has solved a node before t0
         drv.round()
+    drv.drain()                                    # nothing in flight when the clock starts
     drv.async_exchange = ax
     warm_nodes = drv.stats.processed
     torch.cuda.synchronize()
@@ -281,6 +283,7 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
     t0 = time.perf_counter()
     # a step = one round: a window of K node LPs, or (stream_factor F) F*K nodes through the continuous batcher
     drv.run(max_nodes=10 ** 9, rounds=steps, stream_nodes=stream_factor * slots)
+    drv.drain()                                    # ... and nothing when it stops: every node counted was solved inside
     torch.cuda.synchronize()
     busy = time.perf_counter() - t0               # this rank's own time for its K rounds
     if dist:
@@ -311,7 +314,9 @@ def bnb_measure(args, rank, world, local_rank, dist, instance, steps, warmup, sl
             "incumbent": drv.incumbent, "root_bound": drv.stats.root_bound,
             "slots_per_gpu": slots, "node_lp": args.node_lp, "warm_start": bool(args.warm_start),
             "batching": (f"continuous (sb200_solve_stream), {stream_factor} x slots nodes per round"
-                         if stream_factor > 0 else "windows of K nodes (sb200_solve_batch)"),
+                         if stream_factor > 0 else "windows of K nodes (sb200_solve_batch)" if drv.pipeline == 1 else
+                         f"windows of K nodes, {drv.pipeline} in flight over alternating workspace sets "
+                         "(sb200_window_begin / sb200_window_finish)"),
             "exchange": ({"kind": "asynchronous all_gather of (incumbent objective, open nodes, processed nodes) per "
                                   "round, collected 2 rounds later; incumbent vector fetched once at the end; node "
                                   "donation (blocking) only when the gathered frontier sizes differ by > slots/2",
@@ -925,6 +930,8 @@ def main():
     ap.add_argument("--node-lp", default="reference", choices=["reference", "converged"],
                     help="bnb: node LP configuration - the reference's (gap-stagnation exit, window 5, 1 %%) or to mu <= 1e-4")
     ap.add_argument("--warm-start", action="store_true", help="bnb: children start from their parent's iterate (sb200_node_delta.warm_start)")
+    ap.add_argument("--bnb-pipeline", type=int, default=2,
+                    help="bnb: windows in flight per GPU (2: the next window is queued while the host processes the previous one)")
     ap.add_argument("--no-bnb-block", action="store_true", help="skip the B&B block of the default line")
     ap.add_argument("--bnb-rounds", type=int, default=8, help="rounds per instance in the B&B block of the default line")
     ap.add_argument("--host-heuristics", action="store_true",

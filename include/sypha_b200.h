@@ -252,6 +252,17 @@ int sb200_set_solver_form(sb200_ws *ws, int form);
  * stream.  Device time of the last such window on `ws` (= the first workspace of that batch), measured with CUDA events on
  * the launching stream around the kernel, and the number of LPs it held. */
 int sb200_last_window(sb200_ws *ws, double *ms, int *lps);
+/* The same window in two halves, so that a caller can keep the GPU fed: begin applies the deltas, launches the window on
+ * wss[0]'s stream and - with_node_rules != 0 - the window's node-rules kernel (sb200_node_heuristics) right behind it,
+ * and returns without waiting; finish waits for that stream and fills results[] (the SAME array that was passed to begin:
+ * its x_host / y_host / s_host / xys_device pointers are used by the copies queued in begin) and rules_out[] (may be NULL).
+ * Two sets of workspaces used alternately - begin(A), begin(B), finish(A), ..., begin(A'), finish(B), ... - leave no gap
+ * between windows: B's thread blocks start on the SMs A's finished blocks free.  SB200_ERR_UNSUPPORTED: the batch is not a
+ * one-launch window (see sb200_solve_batch); any deltas have then been applied and sb200_solve_batch(wss, k, NULL, ...)
+ * solves it. */
+int sb200_window_begin(sb200_ws **wss, int k, const sb200_node_delta *deltas, const sb200_params *params,
+                       sb200_result *results, int with_node_rules);
+int sb200_window_finish(sb200_ws **wss, int k, sb200_result *results, sb200_heur_result *rules_out);
 
 /* Continuous batching of B&B node LPs over k workspaces that hold the same base model: whenever a slot is
  * free `next(user, slot, &delta)` is asked for a node (return 1 with the decision list filled in - the arrays

@@ -14,6 +14,7 @@ incumbents, pruning by the parent / node dual bound with integer costs.
 from __future__ import annotations
 
 import collections
+import itertools
 import dataclasses
 import math
 import time
@@ -24,7 +25,7 @@ import numpy as np
 from .instances import ScpModel
 from .solver import (CODE_SUCCESSFUL, IpmWorkspace, SolverExecutionConfig, SolverGapStagnationConfig,
                      SyphaEnvironment, SyphaNodeSparse, get_cover, get_primal, get_rounded, initializeIpmWorkspace,
-                     last_window, node_heuristics, releaseIpmWorkspace, set_heuristic_rules, solve_batch, solve_batch_nodes,
+                     last_window, node_heuristics, releaseIpmWorkspace, window_begin, window_finish, set_heuristic_rules, solve_batch, solve_batch_nodes,
                      workspace_for_nodes)
 
 TERM_CONVERGED, TERM_MAX_ITER, TERM_GAP_STALLED, TERM_NUMERICAL = 0, 1, 2, 3
@@ -196,7 +197,8 @@ class BatchedBnb:
                  heuristic_threads: int = 0, device_heuristics: bool = True, rebalance=None, rebalance_every: int = 1,
                  share_gpu: bool = True, poll_every: int = 1, node_lp: str = "reference", async_exchange=None,
                  rebalance_min_imbalance: Optional[int] = None, heuristic_rules: str = "reference",
-                 branch_rule: str = "most_fractional", warm_start: bool = False, warm_floor: float = 0.1):
+                 branch_rule: str = "most_fractional", warm_start: bool = False, warm_floor: float = 0.1,
+                 pipeline: int = 1):
         self.base = base
         self.device_nodes = device_nodes      # False: the reference's way (host CSR per node + full upload)
         self.max_depth = max_depth
@@ -218,10 +220,15 @@ class BatchedBnb:
         gs = SolverGapStagnationConfig(True, 5, 1.0) if node_lp == "reference" else SolverGapStagnationConfig(False, 0, 0.0)
         self.cfg = SolverExecutionConfig(maxIterations=max_iter, gapStagnation=gs)
         self.slots = slots
+        # pipeline = 2: two sets of `slots` workspaces used alternately (sb200_window_begin / _finish): while the host
+        # reads one window's results, branches and stages the next deltas, the other window's thread blocks are running and
+        # the first set's next window is already queued behind it - no idle GPU between windows, and a window's late LPs
+        # share the GPU with the next window's early ones.  Needs the device node path with the device rules.
+        self.pipeline = max(1, pipeline) if (device_nodes and device_heuristics and not warm_start and slots > 1) else 1
         self.ws: List[IpmWorkspace] = []
         self.base_node = SyphaNodeSparse.from_csr(base.m, base.n, base.n_orig, base.offs, base.inds, base.vals,
                                                   base.c, base.b, self.env)
-        for _ in range(slots):
+        for _ in range(slots * self.pipeline):
             if device_nodes:
                 self.ws.append(workspace_for_nodes(self.base_node, max_depth, device))   # base model resident
             else:
@@ -248,6 +255,10 @@ class BatchedBnb:
             from . import _lib as L
             for w in self.ws:
                 L.load().sb200_set_concurrency_hint(w.handle, slots)
+        self._sets = [self.ws[i * slots:(i + 1) * slots] for i in range(self.pipeline)]
+        self._free_sets = list(range(self.pipeline))
+        self._inflight: collections.deque = collections.deque()      # (batch, NodeWindow, set index, begin time)
+        self._cur_ws = self.ws                                       # the set whose results are being processed
         self.heur = CoverHeuristic(base)
         self.frontier: collections.deque = collections.deque([BnbNode((), -math.inf)])
         self.incumbent = math.inf
@@ -302,9 +313,25 @@ class BatchedBnb:
             self._offer(*fut.result())
         self._pending = []
 
+    def drain(self):
+        """Finish and process the windows still in flight (pipeline > 1)."""
+        while self._inflight:
+            batch, w, si = self._inflight.popleft()
+            results, heur = window_finish(w)
+            self._cur_ws = self._sets[si]
+            self._process_batch(batch, results, heur)
+            self._free_sets.append(si)
+
+    def _open_nodes(self) -> int:
+        return len(self.frontier) + sum(len(b) for b, _, _ in self._inflight)
+
     def close(self):
         if self._pool is not None:
             self._pool.shutdown(wait=True)
+        try:
+            self.drain()
+        except Exception:
+            pass
         for w in self.ws:
             releaseIpmWorkspace(w)
         self.ws = []
@@ -346,13 +373,13 @@ class BatchedBnb:
         continuous drivers."""
         # heuristics in the reference's order; the first one that improves the incumbent is taken (bnb_driver.cpp:885-903)
         if nif_feasible and nif_obj < self.incumbent:
-            self._offer(nif_obj, get_rounded(self.ws[slot], self.base.n_orig))
+            self._offer(nif_obj, get_rounded(self._cur_ws[slot], self.base.n_orig))
         elif feasible and cover_obj < self.incumbent:
-            self._offer(cover_obj, get_cover(self.ws[slot], self.base.n_orig))
+            self._offer(cover_obj, get_cover(self._cur_ws[slot], self.base.n_orig))
         if branch_var < 0 or branch_frac < 1e-6:           # integral LP point
             self.stats.integral += 1
             if rounded_obj < self.incumbent:
-                x = get_primal(self.ws[slot], self.base.n + len(nd.decisions))[:self.base.n_orig]
+                x = get_primal(self._cur_ws[slot], self.base.n + len(nd.decisions))[:self.base.n_orig]
                 self._offer(rounded_obj, np.round(x))
             return
         warm = None
@@ -390,16 +417,106 @@ class BatchedBnb:
     def _warm_arg(nd: "BnbNode"):
         return None if nd.warm is None else (nd.warm[0].data_ptr(), nd.warm[1], nd.warm[2])
 
-    def round(self) -> int:
-        """Pop up to K nodes, solve their LPs as one batch, branch.  Returns the number processed."""
+    def _pop_batch(self) -> List[BnbNode]:
         batch: List[BnbNode] = []
-        t_round = time.perf_counter()
         while self.frontier and len(batch) < self.slots:
             nd = self.frontier.popleft()                       # FIFO, bnb.cpp:42-43
             if self._prunable(nd.parent_bound):                # bnb_driver.cpp:797
                 self.stats.pruned_by_bound += 1
                 continue
             batch.append(nd)
+        return batch
+
+    def _process_batch(self, batch, results, heur):
+        """bounds, incumbent offers and children of a solved window (bnb_driver.cpp:844-1005)"""
+        self.stats.round_max_iterations += max(r.iterations for r in results)
+        for slot, (nd, res) in enumerate(zip(batch, results)):
+            self.stats.processed += 1
+            self.stats.lp_iterations += res.iterations
+            self.stats.lp_device_ms += res.msStart + res.msSetup + res.msLoop
+            self.stats.kernels_launched += int(res.kernelsLaunched)
+            bound = self._node_bound(nd, res.status == CODE_SUCCESSFUL, res.terminationReason, res.primalObj,
+                                     res.dualObj)
+            if bound is None:                              # failed non-root node is skipped (bnb_driver.cpp:844-859)
+                continue
+            if not nd.decisions:
+                self.stats.root_bound = bound
+            if self._prunable(bound):
+                self.stats.pruned_by_bound += 1
+                continue
+            if heur is not None:                           # same rules, computed on the device
+                h = heur[slot]
+                self.stats.kernels_launched += 1
+                self._branch_from_device(nd, slot, bound, h.feasible, h.coverObj, h.branchVar, h.branchFrac,
+                                         h.roundedObj, h.nifFeasible, h.nifObj)
+                continue
+            x = res.primalSolution[:self.base.n_orig]
+            zero_fixed = [v for v, f in nd.decisions if f == 0]
+            if self._pool is not None:
+                self._pending.append(self._pool.submit(self.heur, x.copy(), zero_fixed))
+            else:
+                self._offer(*self.heur(x, zero_fixed))
+            frac = np.abs(x - np.round(x))
+            j = int(np.argmax(frac))
+            if frac[j] < 1e-6:                             # integral LP point
+                self.stats.integral += 1
+                self._offer(float(self.base.c[:self.base.n_orig] @ np.round(x)), np.round(x))
+                continue
+            self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
+            self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+
+    def _round_pipelined(self) -> int:
+        """One window's worth of results per call, with up to ``pipeline`` windows in flight (sb200_window_begin /
+        _finish over alternating workspace sets)."""
+        t_round = time.perf_counter()
+        while self._free_sets and self.frontier:
+            if any(len(nd.decisions) > self.max_depth for nd in itertools.islice(self.frontier, self.slots)):
+                break                                          # deeper than the slots take: drained below, then the plain path
+            batch = self._pop_batch()
+            if not batch:
+                continue
+            si = self._free_sets.pop()
+            w = window_begin(self.base_node, [nd.decisions for nd in batch], self.cfg, self._sets[si], with_rules=True)
+            if w is None:                                      # not a one-launch window: solve it here and now
+                results = solve_batch_nodes(self.base_node, [nd.decisions for nd in batch], self.cfg, self._sets[si],
+                                            fetch_solutions=False, fetch_trace=False)
+                heur = node_heuristics(self._sets[si][:len(batch)])
+                self._cur_ws = self._sets[si]
+                self._process_batch(batch, results, heur)
+                self._free_sets.append(si)
+                continue
+            self.stats.delta_rows += sum(len(nd.decisions) for nd in batch)
+            self._inflight.append((batch, w, si))
+        done = 0
+        if self._inflight:
+            batch, w, si = self._inflight.popleft()
+            t_s = time.perf_counter()
+            results, heur = window_finish(w)
+            self.stats.solve_ms.append(round(1e3 * (time.perf_counter() - t_s), 2))      # time blocked waiting for the window
+            self.stats.window_ms.append(round(last_window(self._sets[si][0])[0], 2))
+            self.stats.heur_ms.append(0.0)
+            self._cur_ws = self._sets[si]
+            self._process_batch(batch, results, heur)
+            self._free_sets.append(si)
+            done = len(batch)
+        elif self.frontier:                                    # nodes deeper than max_depth: the plain path takes them
+            self._cur_ws = self.ws
+            return self._round_plain()
+        self._collectives()
+        self.stats.rounds += 1
+        self.stats.round_ms.append(round(1e3 * (time.perf_counter() - t_round), 2))
+        return done
+
+    def round(self) -> int:
+        """Pop up to K nodes, solve their LPs as one batch, branch.  Returns the number processed."""
+        if self.pipeline > 1 and self.device_nodes and self.device_heuristics:
+            return self._round_pipelined()
+        return self._round_plain()
+
+    def _round_plain(self) -> int:
+        t_round = time.perf_counter()
+        self._cur_ws = self.ws
+        batch = self._pop_batch()
         if batch:
             if self.device_nodes and all(len(nd.decisions) <= self.max_depth for nd in batch):
                 on_dev = self.device_heuristics
@@ -425,41 +542,7 @@ class BatchedBnb:
                 heur = None
                 self.device_nodes = self.device_heuristics = False      # the slots no longer hold the base model
             self._fold_pending()               # heuristics of the previous round (ran beside this solve)
-            self.stats.round_max_iterations += max(r.iterations for r in results)
-            for slot, (nd, res) in enumerate(zip(batch, results)):
-                self.stats.processed += 1
-                self.stats.lp_iterations += res.iterations
-                self.stats.lp_device_ms += res.msStart + res.msSetup + res.msLoop
-                self.stats.kernels_launched += int(res.kernelsLaunched)
-                bound = self._node_bound(nd, res.status == CODE_SUCCESSFUL, res.terminationReason, res.primalObj,
-                                         res.dualObj)
-                if bound is None:                              # failed non-root node is skipped (bnb_driver.cpp:844-859)
-                    continue
-                if not nd.decisions:
-                    self.stats.root_bound = bound
-                if self._prunable(bound):
-                    self.stats.pruned_by_bound += 1
-                    continue
-                if heur is not None:                           # same rules, computed on the device
-                    h = heur[slot]
-                    self.stats.kernels_launched += 1
-                    self._branch_from_device(nd, slot, bound, h.feasible, h.coverObj, h.branchVar, h.branchFrac,
-                                             h.roundedObj, h.nifFeasible, h.nifObj)
-                    continue
-                x = res.primalSolution[:self.base.n_orig]
-                zero_fixed = [v for v, f in nd.decisions if f == 0]
-                if self._pool is not None:
-                    self._pending.append(self._pool.submit(self.heur, x.copy(), zero_fixed))
-                else:
-                    self._offer(*self.heur(x, zero_fixed))
-                frac = np.abs(x - np.round(x))
-                j = int(np.argmax(frac))
-                if frac[j] < 1e-6:                             # integral LP point
-                    self.stats.integral += 1
-                    self._offer(float(self.base.c[:self.base.n_orig] @ np.round(x)), np.round(x))
-                    continue
-                self.frontier.append(BnbNode(nd.decisions + ((j, 0),), bound))
-                self.frontier.append(BnbNode(nd.decisions + ((j, 1),), bound))
+            self._process_batch(batch, results, heur)
             if self.warm_start:
                 for nd in batch:                               # children solved: their parent's buffer may be free now
                     if nd.warm is not None:
@@ -480,7 +563,7 @@ class BatchedBnb:
             # every rank reads identically - so every rank adopts the same bound and takes the same decision to
             # rebalance, without waiting for anybody's current round
             t0 = time.perf_counter()
-            ax.post(self.incumbent, len(self.frontier), self.stats.processed)
+            ax.post(self.incumbent, self._open_nodes(), self.stats.processed)
             for rows in ax.collect():
                 self._apply_gather(rows)
             self.stats.exchange_wait_ms += 1e3 * (time.perf_counter() - t0)
@@ -642,7 +725,7 @@ class BatchedBnb:
                 return self.global_open > 0 and (self.global_processed or 0) < max_nodes
             if self.rebalance is not None and self.rebalance_every == 1 and self.global_open is not None:
                 return self.global_open > 0
-            return bool(self.frontier) and self.stats.processed < max_nodes
+            return (bool(self.frontier) or bool(self._inflight)) and self.stats.processed < max_nodes
         while more():
             if stream_nodes > 0 and self.device_nodes and self.device_heuristics:
                 if self.stream_round(stream_nodes) == 0 and self.frontier and rounds is None:
@@ -652,10 +735,12 @@ class BatchedBnb:
             r += 1
             if not self.frontier and self._pending:            # last word of the heuristics before stopping
                 self._fold_pending()
+        if rounds is None:
+            self.drain()
         self._fold_pending()
         if rounds is None:
             self.finish_exchange()
         self.stats.wall_s += time.perf_counter() - t0
         self.stats.incumbent = self.incumbent
-        self.stats.open_nodes = len(self.frontier)
+        self.stats.open_nodes = self._open_nodes()
         return self.stats

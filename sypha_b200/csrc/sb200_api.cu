@@ -116,6 +116,7 @@ struct sb200_ws
     int batch_cap = 0;
     unsigned char *nd_host = nullptr, *nd_dev = nullptr;   // a window's node deltas: descriptors | var | coef | rhs (lead only)
     size_t nd_cap = 0;
+    bool window_pending = false;            // sb200_window_begin without its sb200_window_finish yet
     double window_ms = 0.0;                 // device time (CUDA events on the launching stream) of the last one-launch window
     int window_lps = 0;
     const double *warm_ptr = nullptr;                  // parent's x | y | s for the next solve (one use)
@@ -1459,8 +1460,8 @@ static bool batch_is_one_launch(sb200_ws **wss, int k, const sb200_result *resul
     return true;
 }
 
-static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *params, sb200_result *results,
-                                  bool deltas_on_lead_stream)
+static int window_launch(sb200_ws **wss, int k, const sb200_params *params, sb200_result *results,
+                         bool deltas_on_lead_stream)
 {
     sb200_ws *lead = wss[0];
     sb200_ws *ws = lead;                    // for WS_TRY
@@ -1528,17 +1529,35 @@ static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *par
         copies = copies || r.x_host || r.y_host || r.s_host;
     }
     (void)copies;
-    WS_TRY(cudaStreamSynchronize(main));
+    lead->window_lps = k;
+    lead->window_pending = true;
+    return SB200_OK;
+}
+
+// wait for the window launched on wss[0]'s stream (and whatever was queued behind it) and collect the results
+static int window_collect(sb200_ws **wss, int k, sb200_result *results)
+{
+    sb200_ws *lead = wss[0];
+    sb200_ws *ws = lead;                    // for WS_TRY
+    WS_TRY(cudaSetDevice(lead->device));
+    WS_TRY(cudaStreamSynchronize(lead->stream));
     float wms = 0.f;
     cudaEventElapsedTime(&wms, lead->ev[1], lead->ev[2]);
     lead->window_ms = wms;
-    lead->window_lps = k;
+    lead->window_pending = false;
     for (int i = 0; i < k; ++i)
     {
         finish_from_mirror(wss[i], &results[i]);
         results[i].kernels_launched = i == 0 ? 1 : 0;        // one launch for the whole window
     }
     return SB200_OK;
+}
+
+static int solve_batch_one_launch(sb200_ws **wss, int k, const sb200_params *params, sb200_result *results,
+                                  bool deltas_on_lead_stream)
+{
+    const int rc = window_launch(wss, k, params, results, deltas_on_lead_stream);
+    return rc ? rc : window_collect(wss, k, results);
 }
 
 int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, const sb200_params *params,
@@ -1648,30 +1667,43 @@ static int enqueue_node_heuristics(sb200_ws *ws)
     return SB200_OK;
 }
 
+// the node rules of a whole window as ONE launch (a block per node) on wss[0]'s stream, behind whatever is queued there
+static int enqueue_heuristics_window(sb200_ws **wss, int k)
+{
+    sb200_ws *ws = wss[0];
+    int rc;
+    for (int i = 0; i < k; ++i)
+    {
+        if ((rc = ensure_heur_buffers(wss[i]))) return rc;
+        ws->hbatch_host[i] = heur_args_of(wss[i]);
+        ws->hbatch_host[i].host_flag = nullptr;          // the host waits on the stream
+    }
+    WS_TRY(cudaMemcpyAsync(ws->hbatch_dev, ws->hbatch_host, sizeof(HeurArgs) * (size_t)k, cudaMemcpyHostToDevice, ws->stream));
+    rc = launch_node_heuristics_batch(ws->hbatch_dev, k, ws->base_m, ws->n_orig, ws->stream);
+    if (rc) return fail(ws, rc, "sb200_node_heuristics: window launch failed");
+    WS_TRY(cudaGetLastError());
+    return SB200_OK;
+}
+static bool heuristics_window_ok(sb200_ws **wss, int k, bool allow_active)
+{
+    bool one = k >= 2 && wss[0] && wss[0]->batch_cap >= k;
+    for (int i = 0; one && i < k; ++i)
+        one = wss[i] && wss[i]->loaded && (allow_active || !wss[i]->active) && wss[i]->device == wss[0]->device &&
+              wss[i]->heur_rules == SB200_HEUR_REFERENCE && wss[i]->base_m == wss[0]->base_m &&
+              wss[i]->n_orig == wss[0]->n_orig && wss[i]->csr_offs && wss[i]->csc_colptr;
+    return one;
+}
+
 int sb200_node_heuristics(sb200_ws **wss, int k, sb200_heur_result *out)
 {
     if (!wss || k <= 0 || !out) return SB200_ERR_INVALID;
     int rc;
     {   // a window of nodes of the same base model with the reference's rules: ONE launch, a block per node
-        bool one = k >= 2 && wss[0] && wss[0]->batch_cap >= k;
-        for (int i = 0; one && i < k; ++i)
-            one = wss[i] && wss[i]->loaded && !wss[i]->active && wss[i]->device == wss[0]->device &&
-                  wss[i]->heur_rules == SB200_HEUR_REFERENCE && wss[i]->base_m == wss[0]->base_m &&
-                  wss[i]->n_orig == wss[0]->n_orig && wss[i]->csr_offs && wss[i]->csc_colptr;
-        if (one)
+        if (heuristics_window_ok(wss, k, false))
         {
             sb200_ws *ws = wss[0];
             WS_TRY(cudaSetDevice(ws->device));
-            for (int i = 0; i < k; ++i)
-            {
-                if ((rc = ensure_heur_buffers(wss[i]))) return rc;
-                ws->hbatch_host[i] = heur_args_of(wss[i]);
-                ws->hbatch_host[i].host_flag = nullptr;          // the host waits on the stream
-            }
-            WS_TRY(cudaMemcpyAsync(ws->hbatch_dev, ws->hbatch_host, sizeof(HeurArgs) * (size_t)k, cudaMemcpyHostToDevice, ws->stream));
-            rc = launch_node_heuristics_batch(ws->hbatch_dev, k, ws->base_m, ws->n_orig, ws->stream);
-            if (rc) return fail(ws, rc, "sb200_node_heuristics: window launch failed");
-            WS_TRY(cudaGetLastError());
+            if ((rc = enqueue_heuristics_window(wss, k))) return rc;
             WS_TRY(cudaStreamSynchronize(ws->stream));
             for (int i = 0; i < k; ++i) out[i] = *wss[i]->heur_out_host;
             return SB200_OK;
@@ -1788,6 +1820,58 @@ int sb200_set_concurrency_hint(sb200_ws *ws, int concurrent_lps)
     // many LPs in flight: one CTA per LP (sb200_cta.cu) unless SB200_CTA_SOLVER=0 asks for the shared multi-kernel form
     const char *cs = getenv("SB200_CTA_SOLVER");
     ws->solver_form = (concurrent_lps > 1 && !(cs && atoi(cs) == 0)) ? SB200_FORM_THROUGHPUT : SB200_FORM_LATENCY;
+    return SB200_OK;
+}
+
+int sb200_window_begin(sb200_ws **wss, int k, const sb200_node_delta *deltas, const sb200_params *params,
+                       sb200_result *results, int with_node_rules)
+{
+    if (!wss || k <= 0 || !params || !results) return SB200_ERR_INVALID;
+    for (int i = 0; i < k; ++i)
+        if (!wss[i] || wss[i]->active || wss[i]->window_pending) return SB200_ERR_INVALID;
+    int rc;
+    // only what the one-launch window can run is accepted here; nothing has changed when it is not
+    {
+        const char *off = getenv("SB200_WINDOW_LAUNCH");
+        if ((off && off[0] == '0') || k < 2 || (deltas && !deltas_can_batch(wss, k))) return SB200_ERR_UNSUPPORTED;
+        for (int i = 0; i < k; ++i)
+            if (!wss[i]->loaded || wss[i]->device != wss[0]->device || wss[i]->solver_form != SB200_FORM_THROUGHPUT ||
+                !cta_eligible(wss[i]) || results[i].x0_host || results[i].y0_host || results[i].s0_host)
+                return SB200_ERR_UNSUPPORTED;
+    }
+    if (deltas && (rc = apply_node_deltas_batched(wss, k, deltas))) return abort_batch(wss, k, rc);
+    for (int i = 0; i < k; ++i)
+        if (deltas && deltas[i].export_xys && !results[i].xys_device) results[i].xys_device = deltas[i].export_xys;
+    if (!batch_is_one_launch(wss, k, results))
+    {   // (a node deeper than the one-block solver takes: the deltas are applied, the caller solves with sb200_solve_batch
+        // and deltas = NULL)
+        cudaStreamSynchronize(wss[0]->stream);
+        return SB200_ERR_UNSUPPORTED;
+    }
+    if ((rc = window_launch(wss, k, params, results, deltas != nullptr))) return abort_batch(wss, k, rc);
+    if (with_node_rules)
+    {
+        if (!heuristics_window_ok(wss, k, true))
+        {
+            window_collect(wss, k, results);
+            return fail(wss[0], SB200_ERR_INVALID, "sb200_window_begin: the node rules need sb200_set_heuristic_rules(REFERENCE) on every slot");
+        }
+        if ((rc = enqueue_heuristics_window(wss, k)))
+        {
+            window_collect(wss, k, results);
+            return rc;
+        }
+    }
+    return SB200_OK;
+}
+
+int sb200_window_finish(sb200_ws **wss, int k, sb200_result *results, sb200_heur_result *rules_out)
+{
+    if (!wss || k <= 0 || !results || !wss[0] || !wss[0]->window_pending || wss[0]->window_lps != k) return SB200_ERR_INVALID;
+    const int rc = window_collect(wss, k, results);
+    if (rc) return abort_batch(wss, k, rc);
+    if (rules_out)
+        for (int i = 0; i < k; ++i) rules_out[i] = *wss[i]->heur_out_host;
     return SB200_OK;
 }
 

@@ -454,3 +454,67 @@ def solve_batch_nodes(base: SyphaNodeSparse, decisions_list, config: SolverExecu
         out.append(r)
     del keep
     return out
+
+
+class NodeWindow:
+    """A window of node LPs in flight between ``window_begin`` and ``window_finish`` (keeps the ctypes arrays alive)."""
+    __slots__ = ("handles", "k", "deltas", "res", "keep", "workspaces", "base", "with_rules", "params")
+
+
+def window_begin(base: SyphaNodeSparse, decisions_list, config: SolverExecutionConfig, workspaces,
+                 with_rules: bool = True) -> Optional["NodeWindow"]:
+    """``sb200_window_begin``: apply the nodes' deltas, launch the window (one thread block per node LP) and - with
+    ``with_rules`` - the node-rules kernel behind it, and return WITHOUT waiting.  ``None`` when the batch cannot be a
+    one-launch window; the deltas are applied then and ``solve_batch(..)``-style synchronous solving is the caller's
+    fallback (``window_finish`` accepts that case too)."""
+    lib = L.load()
+    k = len(decisions_list)
+    w = NodeWindow()
+    w.k, w.base, w.with_rules, w.workspaces = k, base, with_rules, list(workspaces[:k])
+    w.params = _params_from(base, config)
+    w.handles = (C.c_void_p * k)(*[ws.handle for ws in w.workspaces])
+    w.deltas = (L.sb200_node_delta * k)()
+    w.res = (L.sb200_result * k)()
+    lens = [len(dec) for dec in decisions_list]
+    flat = np.array([pair for dec in decisions_list for pair in dec], dtype=np.float64).reshape(-1, 2)
+    var = np.ascontiguousarray(flat[:, 0].astype(np.int32))
+    fix = np.ascontiguousarray(flat[:, 1])
+    coef = np.where(fix == 0.0, -1.0, 1.0)
+    w.keep = (var, coef, fix)
+    vb, cb, fb = var.ctypes.data, coef.ctypes.data, fix.ctypes.data
+    PI, PD = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    o = 0
+    for i, d in enumerate(lens):
+        w.deltas[i].n_extra_rows = d
+        w.deltas[i].var = C.cast(vb + 4 * o, PI)
+        w.deltas[i].coef = C.cast(cb + 8 * o, PD)
+        w.deltas[i].rhs = C.cast(fb + 8 * o, PD)
+        o += d
+    rc = lib.sb200_window_begin(w.handles, k, w.deltas, C.byref(w.params), w.res, 1 if with_rules else 0)
+    if rc == L.SB200_ERR_UNSUPPORTED:
+        return None
+    if rc != L.SB200_OK:
+        msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in w.workspaces)
+        raise Sb200Error(f"sb200_window_begin failed (code {rc}): {msgs}")
+    return w
+
+
+def window_finish(w: "NodeWindow"):
+    """``sb200_window_finish``: wait for the window and return (results, node-rule results or None); solutions stay on the
+    device (``get_primal`` / ``get_cover`` read them)."""
+    lib = L.load()
+    heur = (L.sb200_heur_result * w.k)() if w.with_rules else None
+    rc = lib.sb200_window_finish(w.handles, w.k, w.res, heur)
+    if rc != L.SB200_OK:
+        msgs = "; ".join(lib.sb200_last_error(ws.handle).decode() for ws in w.workspaces)
+        raise Sb200Error(f"sb200_window_finish failed (code {rc}): {msgs}")
+    out = []
+    for i in range(w.k):
+        r = SolverExecutionResult()
+        _fill_result(SyphaNodeSparse(w.base.env), w.workspaces[i], w.res[i], r, None, None, None, fetch_trace=False)
+        out.append(r)
+    rules = None
+    if heur is not None:
+        rules = [NodeHeuristicResult(bool(h.feasible), h.cover_obj, h.n_chosen, h.branch_var, h.branch_frac,
+                                     h.rounded_obj, h.repair_steps, bool(h.nif_feasible), h.nif_obj) for h in heur]
+    return out, rules

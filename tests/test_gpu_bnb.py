@@ -331,3 +331,64 @@ def test_node_at_the_iteration_cap_is_kept_and_branched_on():
         finally:
             drv.close()
     assert finished > 0 and hit > 0, (finished, hit)
+
+
+# ---- windows in flight (sb200_window_begin / sb200_window_finish) ------------------------------------------------
+def test_window_begin_finish_equals_the_synchronous_window():
+    """The two halves of a window against sb200_solve_batch + sb200_node_heuristics on the same nodes: same kernels,
+    so the same numbers bit for bit; two windows over two workspace sets in flight at once."""
+    import sypha_b200 as sb
+    from sypha_b200 import solver as S
+    mdl = gen_scp(60, 400, 0.06, 3)
+    env = sb.SyphaEnvironment()
+    cfg = sb.SolverExecutionConfig(maxIterations=100)
+    base = sb.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+    decs_a = [(), ((5, 1),), ((5, 0), (17, 1)), ((9, 1), (30, 0), (44, 1))]
+    decs_b = [((3, 0),), ((3, 1), (8, 0)), ((100, 1),), ()]
+    sets = [[S.workspace_for_nodes(base, 16) for _ in range(4)] for _ in range(3)]
+    try:
+        for st in sets:
+            for w in st:
+                S.set_solver_form(w, "throughput")
+                S.set_heuristic_rules(w, "reference", "most_fractional", 1e-6)
+        ref = []
+        for decs in (decs_a, decs_b):
+            r = S.solve_batch_nodes(base, decs, cfg, sets[2], fetch_solutions=False, fetch_trace=False)
+            ref.append((r, S.node_heuristics(sets[2])))
+        wa = S.window_begin(base, decs_a, cfg, sets[0])
+        wb = S.window_begin(base, decs_b, cfg, sets[1])            # queued behind / beside the first
+        assert wa is not None and wb is not None
+        for w, (r_ref, h_ref) in ((wa, ref[0]), (wb, ref[1])):
+            res, rules = S.window_finish(w)
+            for a, b in zip(res, r_ref):
+                assert (a.status, a.terminationReason, a.iterations) == (b.status, b.terminationReason, b.iterations)
+                assert a.primalObj == b.primalObj and a.dualObj == b.dualObj
+            for a, b in zip(rules, h_ref):
+                assert a == b
+        ms, k = S.last_window(sets[1][0])
+        assert k == 4 and ms > 0
+    finally:
+        for st in sets:
+            for w in st:
+                sb.releaseIpmWorkspace(w)
+
+
+@pytest.mark.parametrize("name", ["scp41", "scp48", "scp410"])
+def test_pipelined_windows_reach_the_reference_held_ip_optimum(name):
+    """BatchedBnb(pipeline=2): two windows in flight over alternating workspace sets; the frontier order differs from
+    the one-window search by the lag of one window, the optimum does not."""
+    import json
+    from conftest import GOLDEN
+    from sypha_b200.instances import load_npz
+    gold = json.load(open(GOLDEN / "ip_optima.json"))[name]
+    mdl = load_npz(GOLDEN / f"{name}.npz")
+    drv = bnb.BatchedBnb(mdl, slots=8, pipeline=2)
+    try:
+        assert drv.pipeline == 2
+        st = drv.run(max_nodes=20000)
+        assert st.open_nodes == 0 and not drv._inflight, f"search did not finish: {st}"
+        assert st.incumbent == gold, (st.incumbent, gold)
+        x = drv.incumbent_x
+        assert np.all(drv.heur.A @ x >= 1.0) and float(mdl.c[:mdl.n_orig] @ x) == gold
+    finally:
+        drv.close()

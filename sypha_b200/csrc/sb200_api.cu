@@ -642,8 +642,6 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta, NodeDeltaHost 
         if ((rc = grow(ws, &ws->d_var, (size_t)cap))) return rc;
         if ((rc = grow(ws, &ws->d_coef, (size_t)cap))) return rc;
         if (ws->h_delta) cudaFreeHost(ws->h_delta);
-    if (ws->nd_host) cudaFreeHost(ws->nd_host);
-    if (ws->nd_dev) cudaFree(ws->nd_dev);
         ws->h_delta = nullptr;
         WS_TRY(cudaMallocHost(&ws->h_delta, (size_t)cap * 20));
         ws->delta_cap = cap;
@@ -1140,6 +1138,8 @@ int sb200_ws_destroy(sb200_ws *ws)
                     ws->c, ws->b, ws->denseA, ws->M, ws->slab, ws->sc, ws->dparams, ws->base_colptr, ws->base_rows,
                     ws->base_cvals, ws->fp_dev, ws->d_var, ws->d_coef, ws->heur_list, ws->heur_sorted, ws->heur_cover, ws->heur_nif, ws->heur_score, ws->heur_out};
     if (ws->h_delta) cudaFreeHost(ws->h_delta);
+    if (ws->nd_host) cudaFreeHost(ws->nd_host);
+    if (ws->nd_dev) cudaFree(ws->nd_dev);
     if (ws->heur_out_host) cudaFreeHost(ws->heur_out_host);
     if (ws->heur_flag_host) cudaFreeHost(ws->heur_flag_host);
     if (ws->cta_dev) cudaFree(ws->cta_dev);

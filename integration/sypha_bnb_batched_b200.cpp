@@ -253,14 +253,17 @@ SyphaStatus solver_sparse_branch_and_bound_batched(SyphaNodeSparse &node, const 
     caps.m_max = base.nrows + S.maxDepth;
     caps.n_max = base.ncols + S.maxDepth;
     caps.nnz_max = static_cast<long long>(base.nnz) + 2LL * S.maxDepth;
-    S.ws.resize(static_cast<size_t>(K), nullptr);
-    S.inSlot.resize(static_cast<size_t>(K));
-    S.slotVar.resize(static_cast<size_t>(K));
-    S.slotCoef.resize(static_cast<size_t>(K));
-    S.slotRhs.resize(static_cast<size_t>(K));
+    // windows in flight: P sets of K slots used alternately (slot index = set * K + position)
+    const int P = (cfg.continuousBatching || K < 2) ? 1 : std::max(1, cfg.windowsInFlight);
+    const int KP = K * P;
+    S.ws.resize(static_cast<size_t>(KP), nullptr);
+    S.inSlot.resize(static_cast<size_t>(KP));
+    S.slotVar.resize(static_cast<size_t>(KP));
+    S.slotCoef.resize(static_cast<size_t>(KP));
+    S.slotRhs.resize(static_cast<size_t>(KP));
     const int branchRule = node.env->getBnbVarSelectionStrategy() == "highest_cost_fractional"
                                ? SB200_BRANCH_HIGHEST_COST_FRACTIONAL : SB200_BRANCH_MOST_FRACTIONAL;
-    for (int i = 0; i < K; ++i)
+    for (int i = 0; i < KP; ++i)
     {
         int rc = sb200_ws_create(dev, &caps, &S.ws[static_cast<size_t>(i)]);
         if (rc != SB200_OK) fatal("sb200_ws_create", rc, nullptr);
@@ -294,26 +297,60 @@ SyphaStatus solver_sparse_branch_and_bound_batched(SyphaNodeSparse &node, const 
         rc = sb200_solve_stream(S.ws.data(), K, &p, nextNode, nodeDone, &S);
     else
     {   // windows of up to K nodes (the reference's DeviceNodeWindow, sypha_solver_bnb.cpp:32-69, pops one at a time):
-        // K one-block LPs launched together, the K node kernels behind them, then the host-side node rule
-        std::vector<sb200_node_delta> deltas(static_cast<size_t>(K));
-        std::vector<sb200_result> results(static_cast<size_t>(K));
-        std::vector<sb200_heur_result> heur(static_cast<size_t>(K));
+        // K one-block LPs launched together, the K node kernels behind them, then the host-side node rule.  With P > 1
+        // sets of slots the next window is already on the GPU while this loop branches on the finished one.
+        std::vector<sb200_node_delta> deltas(static_cast<size_t>(KP));
+        std::vector<sb200_result> results(static_cast<size_t>(KP));
+        std::vector<sb200_heur_result> heur(static_cast<size_t>(KP));
+        struct Window { int set, cnt; };
+        std::deque<Window> inFlight;
+        std::vector<int> freeSets;
+        for (int s = P - 1; s >= 0; --s) freeSets.push_back(s);
         while (rc == SB200_OK)
         {
-            int cnt = 0;
-            while (cnt < K)
+            while (rc == SB200_OK && !freeSets.empty())
             {
-                deltas[static_cast<size_t>(cnt)] = sb200_node_delta{};
-                if (!nextNode(&S, cnt, &deltas[static_cast<size_t>(cnt)])) break;
-                results[static_cast<size_t>(cnt)] = sb200_result{};
-                ++cnt;
+                const int set = freeSets.back(), base = set * K;
+                int cnt = 0;
+                while (cnt < K)
+                {
+                    deltas[static_cast<size_t>(base + cnt)] = sb200_node_delta{};
+                    if (!nextNode(&S, base + cnt, &deltas[static_cast<size_t>(base + cnt)])) break;
+                    results[static_cast<size_t>(base + cnt)] = sb200_result{};
+                    ++cnt;
+                }
+                if (cnt == 0) break;
+                sb200_ws **w = S.ws.data() + base;
+                rc = sb200_window_begin(w, cnt, deltas.data() + base, &p, results.data() + base, 1);
+                if (rc == SB200_ERR_UNSUPPORTED)
+                {   // not a one-launch window (one node, or a node deeper than a thread block takes): the deltas are applied,
+                    // solve it here and now
+                    rc = sb200_solve_batch(w, cnt, nullptr, &p, results.data() + base);
+                    if (rc == SB200_OK) rc = sb200_node_heuristics(w, cnt, heur.data() + base);
+                    if (rc != SB200_OK) break;
+                    for (int i = 0; i < cnt; ++i)
+                        nodeDone(&S, base + i, &results[static_cast<size_t>(base + i)], &heur[static_cast<size_t>(base + i)]);
+                    continue;
+                }
+                if (rc != SB200_OK) break;
+                freeSets.pop_back();
+                inFlight.push_back(Window{set, cnt});
             }
-            if (cnt == 0) break;
-            rc = sb200_solve_batch(S.ws.data(), cnt, deltas.data(), &p, results.data());
+            if (rc != SB200_OK || inFlight.empty()) break;
+            const Window win = inFlight.front();
+            inFlight.pop_front();
+            const int base = win.set * K;
+            rc = sb200_window_finish(S.ws.data() + base, win.cnt, results.data() + base, heur.data() + base);
             if (rc != SB200_OK) break;
-            rc = sb200_node_heuristics(S.ws.data(), cnt, heur.data());
-            if (rc != SB200_OK) break;
-            for (int i = 0; i < cnt; ++i) nodeDone(&S, i, &results[static_cast<size_t>(i)], &heur[static_cast<size_t>(i)]);
+            for (int i = 0; i < win.cnt; ++i)
+                nodeDone(&S, base + i, &results[static_cast<size_t>(base + i)], &heur[static_cast<size_t>(base + i)]);
+            freeSets.push_back(win.set);
+        }
+        while (!inFlight.empty())
+        {   // an error path: let the GPU finish what was launched before the workspaces go away
+            const Window win = inFlight.front();
+            inFlight.pop_front();
+            sb200_window_finish(S.ws.data() + win.set * K, win.cnt, results.data() + win.set * K, nullptr);
         }
     }
     const double wallMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

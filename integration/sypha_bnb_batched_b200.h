@@ -14,6 +14,8 @@ struct SyphaBatchedBnbConfig
     int maxNodes = 0;                    // 0: env->getBnbMaxNodes()
     int maxDepth = 64;                   // branch decisions a workspace is sized for
     bool nodeLpToConvergence = false;    // false: the reference's gap-stagnation exit (bnb_driver.cpp:833-837)
+    int windowsInFlight = 2;             // windows: sets of `slots` workspaces used alternately (sb200_window_begin / _finish), so the next
+                                         // window is queued on the GPU while the host branches on the previous one; 1: one window at a time
     bool continuousBatching = false;     // true: sb200_solve_stream (a slot takes its next node at once) instead of windows of K
     bool referencePreprocessing = true;  // cost-driven and dominance reductions (bnb_driver.cpp:308-334)
 };

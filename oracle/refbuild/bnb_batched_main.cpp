@@ -53,6 +53,7 @@ int main(int argc, char **argv)
         else if (!std::strcmp(argv[i], "--verbosity") && i + 1 < argc) verbosity = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--converged")) cfg.nodeLpToConvergence = true;
         else if (!std::strcmp(argv[i], "--continuous")) cfg.continuousBatching = true;
+        else if (!std::strcmp(argv[i], "--windows-in-flight") && i + 1 < argc) cfg.windowsInFlight = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--no-preprocessing")) cfg.referencePreprocessing = false;
         else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }

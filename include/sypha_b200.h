@@ -252,6 +252,11 @@ int sb200_set_solver_form(sb200_ws *ws, int form);
  * stream.  Device time of the last such window on `ws` (= the first workspace of that batch), measured with CUDA events on
  * the launching stream around the kernel, and the number of LPs it held. */
 int sb200_last_window(sb200_ws *ws, double *ms, int *lps);
+/* Optional, once per base model (after sb200_load_model, before the first node): allocate what the node path otherwise
+ * allocates at a workspace's first node - the copy of the base CSC, the delta arrays for max_extra_rows decisions, the
+ * buffers of sb200_node_heuristics - so that no allocation (an implicit device synchronisation) falls into the search,
+ * where it would wait for a window in flight on another set of workspaces. */
+int sb200_prepare_nodes(sb200_ws *ws, int max_extra_rows);
 /* The same window in two halves, so that a caller can keep the GPU fed: begin applies the deltas, launches the window on
  * wss[0]'s stream and - with_node_rules != 0 - the window's node-rules kernel (sb200_node_heuristics) right behind it,
  * and returns without waiting; finish waits for that stream and fills results[] (the SAME array that was passed to begin:

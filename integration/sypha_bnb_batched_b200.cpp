@@ -273,6 +273,8 @@ SyphaStatus solver_sparse_branch_and_bound_batched(SyphaNodeSparse &node, const 
         if (rc != SB200_OK) fatal("sb200_load_model", rc, w);
         sb200_set_concurrency_hint(w, K);
         sb200_set_heuristic_rules(w, SB200_HEUR_REFERENCE, branchRule, S.intTol);
+        rc = sb200_prepare_nodes(w, S.maxDepth);           // no allocation inside the search (it would wait for a window in flight)
+        if (rc != SB200_OK) fatal("sb200_prepare_nodes", rc, w);
     }
 
     // ---- node LP configuration: the reference's (bnb_driver.cpp:833-837) ---------------------------------------------------------
@@ -303,6 +305,7 @@ SyphaStatus solver_sparse_branch_and_bound_batched(SyphaNodeSparse &node, const 
         std::vector<sb200_result> results(static_cast<size_t>(KP));
         std::vector<sb200_heur_result> heur(static_cast<size_t>(KP));
         struct Window { int set, cnt; };
+        const bool traceWindows = std::getenv("SB200_TRACE_WINDOWS") != nullptr;
         std::deque<Window> inFlight;
         std::vector<int> freeSets;
         for (int s = P - 1; s >= 0; --s) freeSets.push_back(s);
@@ -340,11 +343,23 @@ SyphaStatus solver_sparse_branch_and_bound_batched(SyphaNodeSparse &node, const 
             const Window win = inFlight.front();
             inFlight.pop_front();
             const int base = win.set * K;
+            const auto tf0 = std::chrono::steady_clock::now();
             rc = sb200_window_finish(S.ws.data() + base, win.cnt, results.data() + base, heur.data() + base);
             if (rc != SB200_OK) break;
+            const auto tf1 = std::chrono::steady_clock::now();
             for (int i = 0; i < win.cnt; ++i)
                 nodeDone(&S, base + i, &results[static_cast<size_t>(base + i)], &heur[static_cast<size_t>(base + i)]);
             freeSets.push_back(win.set);
+            if (traceWindows)
+            {
+                double wms = 0.0;
+                int wl = 0;
+                sb200_last_window(S.ws[static_cast<size_t>(base)], &wms, &wl);
+                std::fprintf(stderr, "[window] set %d, %d nodes: waited %.2f ms, kernel %.2f ms, node rule %.2f ms, at %.1f ms\n", win.set, win.cnt,
+                             std::chrono::duration<double, std::milli>(tf1 - tf0).count(), wms,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf1).count(),
+                             std::chrono::duration<double, std::milli>(tf1 - t0).count());
+            }
         }
         while (!inFlight.empty())
         {   // an error path: let the GPU finish what was launched before the workspaces go away

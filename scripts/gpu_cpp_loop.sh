@@ -12,8 +12,8 @@ from oracle import scp_io
 for nm in ("scpnre1", "scpnrg1"):
     inst, _ = load_golden(nm)
     scp_io.write_scp_text(inst, f"/tmp/{nm}.txt")
-    for wf in ("1", "2"):
-        r = subprocess.run(["oracle/_ref/bnb_batched_b200", f"/tmp/{nm}.txt", "--max-iter", "100", "--max-nodes", "6000", "--slots", "148",
+    for wf in ("1", "2", "2", "1"):
+        r = subprocess.run(["oracle/_ref/bnb_batched_b200", f"/tmp/{nm}.txt", "--max-iter", "100", "--max-nodes", "8000", "--slots", "148",
                             "--windows-in-flight", wf, "--no-preprocessing"], capture_output=True, text=True, timeout=300)
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         try:

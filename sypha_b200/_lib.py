@@ -92,6 +92,7 @@ SYMBOLS = {
     "sb200_set_concurrency_hint": (_i, [_vp, _i]),
     "sb200_set_solver_form": (_i, [_vp, _i]),
     "sb200_last_window": (_i, [_vp, C.POINTER(_d), C.POINTER(_i)]),
+    "sb200_prepare_nodes": (_i, [_vp, _i]),
     "sb200_window_begin": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_node_delta), C.POINTER(sb200_params), C.POINTER(sb200_result), _i]),
     "sb200_window_finish": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_result), C.POINTER(sb200_heur_result)]),
     "sb200_solve_stream": (_i, [C.POINTER(_vp), _i, C.POINTER(sb200_params), NEXT_NODE_FN, NODE_DONE_FN, _vp]),

@@ -583,6 +583,39 @@ int run_iteration_pcg(sb200_ws *ws)
 }
 
 // node = base + delta; no allocation, no device-wide synchronisation once the one-time buffers exist
+// one-time / grow-only buffers of the node path: the copy of the base CSC the node CSC is rebuilt from, the delta arrays
+static int ensure_node_buffers(sb200_ws *ws, int k, bool sync_copy)
+{
+    const int n0 = ws->base_n;
+    const long long nnz0 = ws->base_nnz;
+    cudaStream_t st = ws->stream;
+    if (!ws->base_csc_valid)
+    {   // one-time copy of the base CSC (the working CSC is rebuilt from it for every node)
+        if (ws->node_k != 0) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: base CSC lost");
+        int rc;
+        if ((rc = grow(ws, &ws->base_colptr, (size_t)n0 + 1))) return rc;
+        if ((rc = grow(ws, &ws->base_rows, (size_t)nnz0))) return rc;
+        if ((rc = grow(ws, &ws->base_cvals, (size_t)nnz0))) return rc;
+        WS_TRY(cudaMemcpyAsync(ws->base_colptr, ws->csc_colptr, sizeof(int) * ((size_t)n0 + 1), cudaMemcpyDeviceToDevice, st));
+        WS_TRY(cudaMemcpyAsync(ws->base_rows, ws->csc_rows, sizeof(int) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
+        WS_TRY(cudaMemcpyAsync(ws->base_cvals, ws->csc_vals, sizeof(double) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
+        if (sync_copy) WS_TRY(cudaStreamSynchronize(st));     // the batched kernel runs on another stream (the lead's)
+        ws->base_csc_valid = true;
+    }
+    if (k > ws->delta_cap)
+    {
+        const int cap = (std::max(64, k) + 1) & ~1;     // even: the coefficient staging behind the ids stays 8-byte aligned
+        int rc;
+        if ((rc = grow(ws, &ws->d_var, (size_t)cap))) return rc;
+        if ((rc = grow(ws, &ws->d_coef, (size_t)cap))) return rc;
+        if (ws->h_delta) cudaFreeHost(ws->h_delta);
+        ws->h_delta = nullptr;
+        WS_TRY(cudaMallocHost(&ws->h_delta, (size_t)cap * 20));
+        ws->delta_cap = cap;
+    }
+    return SB200_OK;
+}
+
 struct NodeDeltaHost            // a slot's part of a batched delta: the descriptor + the caller's arrays to stage
 {
     NodeDeltaDesc d;
@@ -622,29 +655,9 @@ int apply_node_delta(sb200_ws *ws, const sb200_node_delta *delta, NodeDeltaHost 
                     "sb200_set_node_delta: workspace capacity too small (create it with sb200_caps covering the deepest node)");
     WS_TRY(cudaSetDevice(ws->device));
     cudaStream_t st = ws->stream;
-    if (!ws->base_csc_valid)
-    {   // one-time copy of the base CSC (the working CSC is rebuilt from it for every node)
-        if (ws->node_k != 0) return fail(ws, SB200_ERR_INVALID, "sb200_set_node_delta: base CSC lost");
-        int rc;
-        if ((rc = grow(ws, &ws->base_colptr, (size_t)n0 + 1))) return rc;
-        if ((rc = grow(ws, &ws->base_rows, (size_t)nnz0))) return rc;
-        if ((rc = grow(ws, &ws->base_cvals, (size_t)nnz0))) return rc;
-        WS_TRY(cudaMemcpyAsync(ws->base_colptr, ws->csc_colptr, sizeof(int) * ((size_t)n0 + 1), cudaMemcpyDeviceToDevice, st));
-        WS_TRY(cudaMemcpyAsync(ws->base_rows, ws->csc_rows, sizeof(int) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
-        WS_TRY(cudaMemcpyAsync(ws->base_cvals, ws->csc_vals, sizeof(double) * (size_t)nnz0, cudaMemcpyDeviceToDevice, st));
-        if (batched) WS_TRY(cudaStreamSynchronize(st));       // the batched kernel runs on another stream (the lead's)
-        ws->base_csc_valid = true;
-    }
-    if (k > ws->delta_cap)
     {
-        const int cap = (std::max(64, k) + 1) & ~1;     // even: the coefficient staging behind the ids stays 8-byte aligned
         int rc;
-        if ((rc = grow(ws, &ws->d_var, (size_t)cap))) return rc;
-        if ((rc = grow(ws, &ws->d_coef, (size_t)cap))) return rc;
-        if (ws->h_delta) cudaFreeHost(ws->h_delta);
-        ws->h_delta = nullptr;
-        WS_TRY(cudaMallocHost(&ws->h_delta, (size_t)cap * 20));
-        ws->delta_cap = cap;
+        if ((rc = ensure_node_buffers(ws, k, batched != nullptr))) return rc;
     }
     // keep the iteration graph of the depth we leave, pick up the one of the depth we enter
     if (ws->iter_graph) ws->node_graphs[ws->node_k] = std::make_pair(ws->iter_graph, ws->iter_graph_kernels);
@@ -1872,6 +1885,20 @@ int sb200_window_finish(sb200_ws **wss, int k, sb200_result *results, sb200_heur
     if (rc) return abort_batch(wss, k, rc);
     if (rules_out)
         for (int i = 0; i < k; ++i) rules_out[i] = *wss[i]->heur_out_host;
+    return SB200_OK;
+}
+
+int sb200_prepare_nodes(sb200_ws *ws, int max_extra_rows)
+{
+    if (!ws || !ws->loaded || max_extra_rows < 0) return SB200_ERR_INVALID;
+    if (ws->strategy != SB200_STRATEGY_CHOLESKY)
+        return fail(ws, SB200_ERR_UNSUPPORTED, "sb200_prepare_nodes: only the sparse-assembly + Cholesky strategy folds node rows");
+    if (ws->node_k != 0) return fail(ws, SB200_ERR_INVALID, "sb200_prepare_nodes: call it on the base model");
+    WS_TRY(cudaSetDevice(ws->device));
+    int rc;
+    if ((rc = ensure_node_buffers(ws, max_extra_rows > 0 ? max_extra_rows : 1, true))) return rc;
+    if ((rc = ensure_heur_buffers(ws))) return rc;
+    WS_TRY(cudaStreamSynchronize(ws->stream));
     return SB200_OK;
 }
 

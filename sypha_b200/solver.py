@@ -300,6 +300,9 @@ def workspace_for_nodes(base: SyphaNodeSparse, max_depth: int, device: int = 0) 
     initializeIpmWorkspace(ws, maxKktNrows=2 * n_max + m_max, maxKktNnz=2 * nnz_max + 3 * n_max, maxNcols=n_max,
                            device=device)
     base.copyModelOnDevice(ws, "cholesky")
+    rc = L.load().sb200_prepare_nodes(ws.handle, max_depth)      # nothing is allocated at the workspace's first node
+    if rc != L.SB200_OK:
+        raise Sb200Error(f"sb200_prepare_nodes failed (code {rc}): {L.load().sb200_last_error(ws.handle).decode()}")
     return ws
 
 

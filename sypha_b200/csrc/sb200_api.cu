@@ -1367,18 +1367,17 @@ int sb200_solve(sb200_ws *ws, const sb200_params *params, sb200_result *result)
 static int abort_batch(sb200_ws **wss, int k, int rc)
 {
     for (int i = 0; i < k; ++i)
-        if (wss[i] && wss[i]->active)
+        if (wss[i] && (wss[i]->active || wss[i]->window_pending))
         {
             cudaSetDevice(wss[i]->device);
             cudaStreamSynchronize(wss[i]->stream);
             wss[i]->active = false;
+            wss[i]->window_pending = false;
+            wss[i]->cta_launched = false;
         }
     return rc;
 }
 
-// A window of LPs in the throughput form as ONE launch: block i of k_ipm_cta solves the LP resident in wss[i].  The node
-// deltas run on the slots' own streams (a few small kernels each); the first slot's stream waits for them, carries the one
-// LP launch, and is the only thing the host waits on.  No limit of 128 concurrent kernels, no launch per LP.
 // the node deltas of a whole window: host bookkeeping per slot, then ONE staged copy and ONE kernel on the lead's stream
 // (the window's launch follows on the same stream) instead of four copies and three kernels per slot
 static bool deltas_can_batch(sb200_ws **wss, int k)
@@ -1457,6 +1456,10 @@ static int apply_node_deltas_batched(sb200_ws **wss, int k, const sb200_node_del
     return rc_slot;
 }
 
+// A window of LPs in the throughput form as ONE launch: block i of k_ipm_cta solves the LP resident in wss[i].  The first
+// slot's stream carries the window's deltas (or waits for the slots' own streams where they were applied one by one), the
+// one LP launch and the result copies, and is the only thing the host waits on.  No limit of 128 concurrent kernels, no
+// launch per LP.
 static bool batch_is_one_launch(sb200_ws **wss, int k, const sb200_result *results)
 {
     if (k < 2) return false;
@@ -1579,6 +1582,9 @@ int sb200_solve_batch(sb200_ws **wss, int k, const sb200_node_delta *deltas, con
     // LPs of a batch are independent: every workspace runs on its own stream and the
     // host interleaves enqueue/poll so their kernels overlap on the device.
     if (!wss || k <= 0 || !params || !results) return SB200_ERR_INVALID;
+    for (int i = 0; i < k; ++i)
+        if (wss[i] && wss[i]->window_pending)
+            return fail(wss[i], SB200_ERR_INVALID, "sb200_solve_batch: a window begun on these workspaces has not been finished");
     std::vector<int> live(k, 0);
     int rc, remaining = 0;
     bool deltas_on_lead_stream = false;

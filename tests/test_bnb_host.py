@@ -68,3 +68,100 @@ def test_node_bound_rule():
     assert d._node_bound(nd, True, bnb.TERM_CONVERGED, 42.0, 43.0) == 40.0
     assert d._node_bound(nd, True, bnb.TERM_MAX_ITER, 50.0, 45.0) == 40.0 and d.stats.maxiter_nodes == 1
     assert d._node_bound(nd, True, bnb.TERM_GAP_STALLED, 50.0, 45.0) == 40.0 and d.stats.gap_stalled_nodes == 1
+
+
+def test_pipelined_rounds_with_a_stand_in_for_the_device(monkeypatch):
+    """BatchedBnb(pipeline=2) on the CPU: the window calls (sb200_window_begin / _finish) replaced by a stand-in that
+    solves each node's LP with SciPy and applies the host rules.  Checks the host logic of the windows in flight: never
+    more than two windows open, sets used alternately, every window finished, the MILP optimum reached, the same
+    optimum as with one window at a time."""
+    import scipy.sparse as sp
+    from scipy.optimize import Bounds, LinearConstraint, linprog, milp
+    from sypha_b200 import solver as S
+
+    mdl = gen_scp(30, 100, 0.1, 1)              # LP bound 179.33, integer optimum 183: the search has to branch
+    A = sp.csr_matrix((mdl.vals, mdl.inds, mdl.offs), shape=(mdl.m, mdl.n))[:, :mdl.n_orig]
+    c = mdl.c[:mdl.n_orig]
+    opt = milp(c, constraints=LinearConstraint(A, lb=1.0), integrality=np.ones(mdl.n_orig), bounds=Bounds(0, 1))
+    assert opt.success
+    cover = bnb.CoverHeuristic(mdl)
+    log = {"open": 0, "max_open": 0, "begun": 0, "finished": 0, "sets": []}
+
+    class FakeWs:
+        def __init__(self):
+            self.cover = None
+            self.x = None
+
+    def fake_window_begin(base, decisions_list, cfg, workspaces, with_rules=True):
+        assert len(decisions_list) >= 1
+        log["open"] += 1
+        log["begun"] += 1
+        log["max_open"] = max(log["max_open"], log["open"])
+        log["sets"].append(id(workspaces[0]))
+        return (list(decisions_list), list(workspaces))
+
+    def fake_window_finish(w):
+        decs, wss = w
+        log["open"] -= 1
+        log["finished"] += 1
+        results, rules = [], []
+        for dec, ws in zip(decs, wss):
+            lo, hi = np.zeros(mdl.n_orig), np.ones(mdl.n_orig)
+            for v, f in dec:
+                lo[v] = hi[v] = f
+            r = linprog(c, A_ub=-A, b_ub=-np.ones(mdl.m), bounds=list(zip(lo, hi)), method="highs")
+            res = S.SolverExecutionResult()
+            if r.status != 0:
+                res.status, res.terminationReason, res.iterations = S.CODE_GENERIC_ERROR, 3, 1
+                res.primalObj = res.dualObj = float("inf")
+                results.append(res)
+                rules.append(S.NodeHeuristicResult(False, float("inf"), 0, -1, 0.0, float("inf"), 0))
+                continue
+            res.status, res.terminationReason, res.iterations = S.CODE_SUCCESSFUL, 0, 7
+            res.primalObj = res.dualObj = float(r.fun)
+            res.msStart = res.msSetup = res.msLoop = 0.0
+            res.kernelsLaunched = 0
+            x = r.x
+            frac = np.abs(x - np.round(x))
+            j = int(np.argmax(frac))
+            # (no rounding heuristic here: incumbents come from integral LP points only, so that the tree is deep enough
+            # to keep two windows open)
+            ws.cover, ws.x = None, x
+            rules.append(S.NodeHeuristicResult(False, float("inf"), 0, j if frac[j] >= 1e-6 else -1, float(frac[j]),
+                                               float(c @ np.round(x)), 0))
+            results.append(res)
+        return results, rules
+
+    monkeypatch.setattr(bnb, "workspace_for_nodes", lambda base, depth, device=0: FakeWs())
+    monkeypatch.setattr(bnb, "set_heuristic_rules", lambda *a, **k: None)
+    monkeypatch.setattr(bnb, "releaseIpmWorkspace", lambda w: None)
+    monkeypatch.setattr(bnb, "window_begin", fake_window_begin)
+    monkeypatch.setattr(bnb, "window_finish", fake_window_finish)
+    monkeypatch.setattr(bnb, "last_window", lambda w: (0.0, 0))
+    monkeypatch.setattr(bnb, "get_cover", lambda w, n: w.cover)
+    monkeypatch.setattr(bnb, "get_primal", lambda w, n: np.concatenate([w.x, np.zeros(max(0, n - len(w.x)))]))
+
+    def solve_plain(base, decisions_list, cfg, workspaces, **kw):       # pipeline = 1 goes through the blocking pair
+        r, h = fake_window_finish((list(decisions_list), list(workspaces[:len(decisions_list)])))
+        log["open"] += 1
+        solve_plain.rules = h
+        return r
+    monkeypatch.setattr(bnb, "solve_batch_nodes", solve_plain)
+    monkeypatch.setattr(bnb, "node_heuristics", lambda wss: solve_plain.rules)
+
+    out = {}
+    for pl in (2, 1):
+        log.update(open=0, max_open=0, begun=0, finished=0, sets=[])
+        drv = bnb.BatchedBnb(mdl, slots=2, share_gpu=False, pipeline=pl, heuristic_rules="plain")
+        assert drv.pipeline == pl and len(drv.ws) == 2 * pl
+        st = drv.run(max_nodes=5000)
+        assert st.open_nodes == 0 and not drv._inflight and sorted(drv._free_sets) == list(range(pl))
+        assert st.incumbent == round(opt.fun), (st.incumbent, opt.fun)
+        assert np.all(cover.A @ drv.incumbent_x >= 1.0)
+        if pl == 2:
+            assert log["begun"] == log["finished"] and log["begun"] > 3, log
+            assert log["max_open"] == 2
+            assert len(set(log["sets"])) == 2                        # both sets of slots were used
+        out[pl] = st.incumbent
+        drv.close()
+    assert out[1] == out[2]

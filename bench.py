@@ -629,6 +629,18 @@ def run_ours(args, rank, world, local_rank):
                     raise
                 bnb_block[inst_name] = {"error": repr(e)}
 
+    if bnb_block and rank == 0:
+        # B&B against the roofline of its dominant kernel (SURVEY 8d iii): the FP64 tensor flops of the node LPs' Cholesky
+        # factorisations (m^3/3 each, one per iteration + the starting point's; m = base rows, the branch rows are not
+        # counted) over the WALL time of the search rounds - host work, node rules and exchange included - per GPU
+        for v in bnb_block.values():
+            if "error" in v:
+                continue
+            fl = (v["lp_iterations"] + v["nodes"]) * (v["model"]["m"] ** 3) / 3.0
+            tf = fl / (v["ms_per_round"] * v["rounds"] / 1e3) / world / 1e12
+            v["roofline"] = {"bound": "tensor", "kernel": "k_ipm_cta (node LPs)", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": tf / fp64_peak, "per": "GPU, wall time of the rounds"}
+
     # ---- max over ranks / sums ----------------------------------------------------------------
     if dist:
         t = torch.tensor([elapsed, e2e_elapsed, wall], device="cuda", dtype=torch.float64)

@@ -165,3 +165,49 @@ def test_pipelined_rounds_with_a_stand_in_for_the_device(monkeypatch):
         out[pl] = st.incumbent
         drv.close()
     assert out[1] == out[2]
+
+
+def test_node_decisions_are_marshalled_as_flat_arrays(monkeypatch):
+    """solve_batch_nodes / window_begin pass every node's (variable, fixing) pairs as three flat arrays with the deltas
+    pointing into them (sb200_node_delta {n_extra_rows, var, coef, rhs}): a stand-in for the library reads them back."""
+    import ctypes as C
+    from sypha_b200 import _lib as L, solver as S
+
+    seen = {}
+
+    class FakeLib:
+        def sb200_solve_batch(self, handles, k, deltas, params, res):
+            seen["batch"] = [(deltas[i].n_extra_rows,
+                              [deltas[i].var[r] for r in range(deltas[i].n_extra_rows)],
+                              [deltas[i].coef[r] for r in range(deltas[i].n_extra_rows)],
+                              [deltas[i].rhs[r] for r in range(deltas[i].n_extra_rows)]) for i in range(k)]
+            for i in range(k):
+                res[i].status, res[i].iterations = L.SB200_OK, 3
+            return L.SB200_OK
+
+        def sb200_window_begin(self, handles, k, deltas, params, res, with_rules):
+            seen["window"] = [(deltas[i].n_extra_rows, [deltas[i].var[r] for r in range(deltas[i].n_extra_rows)],
+                               [deltas[i].coef[r] for r in range(deltas[i].n_extra_rows)]) for i in range(k)]
+            return L.SB200_ERR_UNSUPPORTED
+
+        def sb200_last_error(self, h):
+            return b""
+
+        def sb200_default_params(self, p):
+            pass
+
+    monkeypatch.setattr(L, "load", lambda: FakeLib())
+    mdl = gen_scp(10, 30, 0.3, 1)
+    env = S.SyphaEnvironment()
+    base = S.SyphaNodeSparse.from_csr(mdl.m, mdl.n, mdl.n_orig, mdl.offs, mdl.inds, mdl.vals, mdl.c, mdl.b, env)
+
+    class W:
+        handle = C.c_void_p(0)
+    decs = [(), ((5, 1),), ((7, 0), (2, 1), (11, 0)), (), ((29, 0), (0, 1))]
+    out = S.solve_batch_nodes(base, decs, S.SolverExecutionConfig(maxIterations=5), [W() for _ in decs],
+                              fetch_solutions=False, fetch_trace=False)
+    assert [r.iterations for r in out] == [3] * len(decs)
+    want = [(len(d), [v for v, _ in d], [(-1.0 if f == 0 else 1.0) for _, f in d], [float(f) for _, f in d]) for d in decs]
+    assert seen["batch"] == want
+    assert S.window_begin(base, decs, S.SolverExecutionConfig(maxIterations=5), [W() for _ in decs]) is None
+    assert seen["window"] == [(n, v, c) for n, v, c, _ in want]

@@ -83,3 +83,52 @@ for i in (200, 500, 800, 999):
             tot2 += wave(greedy_counts(half))
             cnt2 += 8
 print('count-balancing greedy:', tot2 / cnt2)
+
+
+def local_search(half, passes=3):
+    """count-balancing greedy, then pairwise swaps inside a lane's chunk while they lower the wavefront count"""
+    out = [list(c) for c in greedy_counts(half)]
+    cntq = [[0] * 16 for _ in range(8)]
+    for c in out:
+        for q, id_ in enumerate(c):
+            if id_ != pad:
+                cntq[q][id_ & 15] += 1
+    for _ in range(passes):
+        improved = False
+        for c in out:
+            for q1 in range(8):
+                for q2 in range(q1 + 1, 8):
+                    a, b = c[q1], c[q2]
+                    if a == b:
+                        continue
+                    before = max(cntq[q1]) + max(cntq[q2])
+                    if a != pad:
+                        cntq[q1][a & 15] -= 1
+                        cntq[q2][a & 15] += 1
+                    if b != pad:
+                        cntq[q2][b & 15] -= 1
+                        cntq[q1][b & 15] += 1
+                    if max(cntq[q1]) + max(cntq[q2]) < before:
+                        c[q1], c[q2] = b, a
+                        improved = True
+                    else:
+                        if a != pad:
+                            cntq[q1][a & 15] += 1
+                            cntq[q2][a & 15] -= 1
+                        if b != pad:
+                            cntq[q2][b & 15] += 1
+                            cntq[q1][b & 15] -= 1
+        if not improved:
+            break
+    return out
+
+
+tot3 = cnt3 = 0
+for i in (200, 500, 800, 999):
+    for g in range(0, min(i, 160), 16):
+        ent = [chunks_of(i, k) for k in range(g, min(g + 16, i))]
+        for j in range(max(len(e) for e in ent)):
+            half = [e[j] for e in ent if j < len(e)]
+            tot3 += wave(local_search(half))
+            cnt3 += 8
+print('count-balancing greedy + local search:', tot3 / cnt3)

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE / study (CPU, NumPy): see DESIGN.md 8.1.  Not imported by the product, the tests or the bench."""
 import sys
-sys.path.insert(0, '/root/repo')
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np, scipy.linalg as sl
 from oracle import scp_io, mehrotra as mo
 
@@ -18,7 +19,8 @@ def pcg(matvec, diag, rhs, tol, cap, x0=None, store=False):
         z = r / diag; rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
     return x, cap, P, PAP
 
-m, n, dens = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
+# python oracle/studies/pcg_recycling_study.py [m n density]   (default: the 1000 x 20000 rung of the ladder)
+m, n, dens = (int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])) if len(sys.argv) > 3 else (1000, 20000, 0.005)
 inst = scp_io.gen_scp(m, n, dens, 0)
 A = inst.csr()
 x, y, s = mo.start_point(A, inst.b, inst.c)

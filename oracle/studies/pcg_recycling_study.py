@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE / study (CPU, NumPy): see DESIGN.md 8.1.  Not imported by the product, the tests or the bench."""
+"""TEST INFRASTRUCTURE / study (CPU, NumPy): see DESIGN.md section 8, item 1.  Not imported by the product, the tests or the bench."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[2]))

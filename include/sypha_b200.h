@@ -174,6 +174,29 @@ typedef struct sb200_scp_model {
     double *b;           /* [m] */
 } sb200_scp_model;
 int sb200_read_scp(const char *path, sb200_scp_model *out);
+
+/* A general row model (lb <= a.x <= ub per row, x >= 0, minimise or maximise c.x) -> the standard form the solver takes
+ * (every row an equality, surplus columns appended): what sypha::Solver::Impl::buildStandardForm does
+ * (src/sypha_api.cpp:136-250), row for row and column for column - an equality row (lb == ub) keeps its coefficients; a
+ * ">= lb" row gains a surplus column with -1; a "<= ub" row is negated (coefficients and right-hand side) and gains a
+ * surplus column with -1; a range row becomes those two rows in that order; a row without bounds is kept as "= 0".
+ * Surplus columns are numbered in row order behind the n_vars structural ones; their cost is 0; a maximised objective is
+ * negated.  O(nnz): a caller that holds its rows as arrays needs neither Variable / Constraint objects nor their
+ * O(row length) SetCoefficient.  Host code; the outputs are what sb200_load_model takes. */
+typedef struct sb200_row_model {
+    int n_vars, n_rows;
+    const int *row_offs;     /* [n_rows + 1] */
+    const int *row_inds;     /* variable of each coefficient, in the order the coefficients were set */
+    const double *row_vals;
+    const double *row_lb;    /* [n_rows], -INFINITY: none */
+    const double *row_ub;    /* [n_rows], +INFINITY: none */
+    const double *obj;       /* [n_vars] */
+    int maximize;
+} sb200_row_model;
+/* sizes of the standard form: rows, columns (structural + surplus), stored entries */
+int sb200_standard_form_size(const sb200_row_model *in, int *nrows, int *ncols, long long *nnz);
+/* fills caller-owned arrays of those sizes: csr_offs[nrows + 1], csr_inds[nnz], csr_vals[nnz], obj[ncols], rhs[nrows] */
+int sb200_build_standard_form(const sb200_row_model *in, int *csr_offs, int *csr_inds, double *csr_vals, double *obj, double *rhs);
 void sb200_free_scp(sb200_scp_model *mdl);
 
 /* ---- solve ---------------------------------------------------------------------------------- */

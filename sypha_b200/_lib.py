@@ -65,6 +65,12 @@ class sb200_scp_model(C.Structure):
                 ("c", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double))]
 
 
+class sb200_row_model(C.Structure):
+    _fields_ = [("n_vars", C.c_int), ("n_rows", C.c_int), ("row_offs", C.POINTER(C.c_int)), ("row_inds", C.POINTER(C.c_int)),
+                ("row_vals", C.POINTER(C.c_double)), ("row_lb", C.POINTER(C.c_double)), ("row_ub", C.POINTER(C.c_double)),
+                ("obj", C.POINTER(C.c_double)), ("maximize", C.c_int)]
+
+
 NEXT_NODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(sb200_node_delta))
 NODE_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(sb200_result), C.POINTER(sb200_heur_result))
 
@@ -80,6 +86,9 @@ SYMBOLS = {
     "sb200_default_params": (None, [C.POINTER(sb200_params)]),
     "sb200_read_scp": (_i, [C.c_char_p, C.POINTER(sb200_scp_model)]),
     "sb200_free_scp": (None, [C.POINTER(sb200_scp_model)]),
+    "sb200_standard_form_size": (_i, [C.POINTER(sb200_row_model), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll)]),
+    "sb200_build_standard_form": (_i, [C.POINTER(sb200_row_model), C.POINTER(_i), C.POINTER(_i), C.POINTER(_d), C.POINTER(_d),
+                                       C.POINTER(_d)]),
     "sb200_load_model": (_i, [_vp, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "sb200_solve": (_i, [_vp, C.POINTER(sb200_params), C.POINTER(sb200_result)]),
     "sb200_set_node_delta": (_i, [_vp, C.POINTER(sb200_node_delta)]),

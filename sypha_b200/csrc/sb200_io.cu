@@ -10,6 +10,7 @@
 // the CSR arrays are written directly at their final size.  Host code only; no CUDA call.
 #include "../../include/sypha_b200.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -135,4 +136,99 @@ extern "C" void sb200_free_scp(sb200_scp_model *mdl)
     free(mdl->c);
     free(mdl->b);
     memset(mdl, 0, sizeof *mdl);
+}
+
+// ---- general row model -> standard form (sypha::Solver::Impl::buildStandardForm, src/sypha_api.cpp:136-250) ---------------
+namespace {
+enum RowKind { ROW_EQ, ROW_GE, ROW_LE, ROW_RANGE, ROW_FREE };
+inline RowKind row_kind(double lb, double ub)
+{
+    const bool has_lb = std::isfinite(lb), has_ub = std::isfinite(ub);
+    if (has_lb && has_ub) return std::fabs(lb - ub) <= 1e-15 ? ROW_EQ : ROW_RANGE;     // sypha_api.cpp:145,164
+    if (has_lb) return ROW_GE;
+    if (has_ub) return ROW_LE;
+    return ROW_FREE;
+}
+inline bool row_model_ok(const sb200_row_model *in)
+{
+    if (!in || in->n_vars < 0 || in->n_rows < 0 || !in->row_offs || (in->n_rows && (!in->row_lb || !in->row_ub))) return false;
+    if (in->row_offs[0] != 0) return false;
+    for (int i = 0; i < in->n_rows; ++i)
+        if (in->row_offs[i + 1] < in->row_offs[i]) return false;
+    if (in->row_offs[in->n_rows] > 0 && (!in->row_inds || !in->row_vals)) return false;
+    return true;
+}
+} // namespace
+
+extern "C" int sb200_standard_form_size(const sb200_row_model *in, int *nrows, int *ncols, long long *nnz)
+{
+    if (!row_model_ok(in) || !nrows || !ncols || !nnz) return SB200_ERR_INVALID;
+    long long rows = 0, slacks = 0, entries = 0;
+    for (int i = 0; i < in->n_rows; ++i)
+    {
+        const long long len = in->row_offs[i + 1] - in->row_offs[i];
+        switch (row_kind(in->row_lb[i], in->row_ub[i]))
+        {
+        case ROW_EQ: case ROW_FREE: rows += 1; entries += len; break;
+        case ROW_GE: case ROW_LE: rows += 1; slacks += 1; entries += len + 1; break;
+        case ROW_RANGE: rows += 2; slacks += 2; entries += 2 * (len + 1); break;
+        }
+    }
+    if (rows > 0x7fffffffll || in->n_vars + slacks > 0x7fffffffll || entries > 0x7fffffffll) return SB200_ERR_UNSUPPORTED;
+    *nrows = (int)rows;
+    *ncols = (int)(in->n_vars + slacks);
+    *nnz = entries;
+    return SB200_OK;
+}
+
+extern "C" int sb200_build_standard_form(const sb200_row_model *in, int *csr_offs, int *csr_inds, double *csr_vals, double *obj,
+                                         double *rhs)
+{
+    int nrows = 0, ncols = 0;
+    long long nnz = 0;
+    const int rc = sb200_standard_form_size(in, &nrows, &ncols, &nnz);
+    if (rc != SB200_OK) return rc;
+    if (!csr_offs || !obj || (nrows && !rhs) || (nnz && (!csr_inds || !csr_vals))) return SB200_ERR_INVALID;
+    const int n = in->n_vars;
+    for (long long t = 0; t < in->row_offs[in->n_rows]; ++t)
+        if (in->row_inds[t] < 0 || in->row_inds[t] >= n) return SB200_ERR_INVALID;
+    for (int j = 0; j < ncols; ++j) obj[j] = 0.0;                                 // surplus columns cost nothing
+    if (in->obj)
+        for (int j = 0; j < n; ++j) obj[j] = in->maximize ? -in->obj[j] : in->obj[j];   // sypha_api.cpp:189-196
+    int r = 0, slack = n;
+    long long o = 0;
+    csr_offs[0] = 0;
+    // one output row: the coefficients (negated for a "<= ub" row), then the surplus entry; sypha_api.cpp:206-246
+    auto emit = [&](int i, bool negate, bool with_slack, double rhs_val) {
+        for (int t = in->row_offs[i]; t < in->row_offs[i + 1]; ++t)
+        {
+            csr_inds[o] = in->row_inds[t];
+            csr_vals[o] = negate ? -in->row_vals[t] : in->row_vals[t];
+            ++o;
+        }
+        if (with_slack)
+        {
+            csr_inds[o] = slack++;
+            csr_vals[o] = -1.0;
+            ++o;
+        }
+        rhs[r] = rhs_val;
+        csr_offs[++r] = (int)o;
+    };
+    for (int i = 0; i < in->n_rows; ++i)
+    {
+        const double lb = in->row_lb[i], ub = in->row_ub[i];
+        switch (row_kind(lb, ub))
+        {
+        case ROW_EQ: emit(i, false, false, lb); break;
+        case ROW_FREE: emit(i, false, false, 0.0); break;
+        case ROW_GE: emit(i, false, true, lb); break;
+        case ROW_LE: emit(i, true, true, -ub); break;
+        case ROW_RANGE:
+            emit(i, false, true, lb);
+            emit(i, true, true, -ub);
+            break;
+        }
+    }
+    return SB200_OK;
 }

@@ -126,3 +126,39 @@ def write_scp(mdl: ScpModel, path) -> None:
             out.append(" " + " ".join(map(str, cols[a:a + 12])))
     with open(path, "w") as fh:
         fh.write("\n".join(out) + "\n")
+
+
+def build_standard_form(n_vars: int, row_offs, row_inds, row_vals, row_lb, row_ub, obj, maximize: bool = False,
+                        name: str = "model") -> ScpModel:
+    """A general row model (lb <= a.x <= ub, x >= 0) -> the standard form the solver takes, through the library's
+    ``sb200_build_standard_form`` (csrc/sb200_io.cu; the reference's ``buildStandardForm``, src/sypha_api.cpp:136-250):
+    O(nnz), no Variable / Constraint objects.  Returns the arrays ``SyphaNodeSparse.from_csr`` / ``sb200_load_model`` take."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load()
+    ro = np.ascontiguousarray(row_offs, dtype=np.int32)
+    ri = np.ascontiguousarray(row_inds, dtype=np.int32)
+    rv = np.ascontiguousarray(row_vals, dtype=np.float64)
+    lb = np.ascontiguousarray(row_lb, dtype=np.float64)
+    ub = np.ascontiguousarray(row_ub, dtype=np.float64)
+    c = np.ascontiguousarray(obj, dtype=np.float64)
+    n_rows = len(ro) - 1
+    if len(lb) != n_rows or len(ub) != n_rows or len(c) != n_vars or len(ri) != len(rv) or (n_rows >= 0 and len(ri) < ro[-1]):
+        raise ValueError("build_standard_form: array lengths do not match the row model")
+    PI, PD = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    m = L.sb200_row_model(n_vars, n_rows, ro.ctypes.data_as(PI), ri.ctypes.data_as(PI), rv.ctypes.data_as(PD),
+                          lb.ctypes.data_as(PD), ub.ctypes.data_as(PD), c.ctypes.data_as(PD), 1 if maximize else 0)
+    nr, nc, nz = C.c_int(), C.c_int(), C.c_longlong()
+    rc = lib.sb200_standard_form_size(C.byref(m), C.byref(nr), C.byref(nc), C.byref(nz))
+    if rc != L.SB200_OK:
+        raise ValueError(f"sb200_standard_form_size failed with code {rc}")
+    offs = np.empty(nr.value + 1, dtype=np.int32)
+    inds = np.empty(nz.value, dtype=np.int32)
+    vals = np.empty(nz.value, dtype=np.float64)
+    cc = np.empty(nc.value, dtype=np.float64)
+    b = np.empty(nr.value, dtype=np.float64)
+    rc = lib.sb200_build_standard_form(C.byref(m), offs.ctypes.data_as(PI), inds.ctypes.data_as(PI), vals.ctypes.data_as(PD),
+                                       cc.ctypes.data_as(PD), b.ctypes.data_as(PD))
+    if rc != L.SB200_OK:
+        raise ValueError(f"sb200_build_standard_form failed with code {rc}")
+    return ScpModel(nr.value, nc.value, n_vars, offs, inds, vals, cc, b, name)

@@ -42,14 +42,14 @@ def test_struct_layouts_against_the_c_compiler(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("needs gcc")
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "sypha_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "sypha_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(sb200_caps),sizeof(sb200_params),sizeof(sb200_result),sizeof(sb200_node_delta),'
-                   'sizeof(sb200_heur_result),sizeof(sb200_scp_model));return 0;}\n')
+                   'sizeof(sb200_heur_result),sizeof(sb200_scp_model),sizeof(sb200_row_model));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-std=c99", "-I", str(_lib.LIB_PATH.parents[2] / "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(t) for t in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     mine = [ctypes.sizeof(getattr(_lib, n)) for n in ("sb200_caps", "sb200_params", "sb200_result", "sb200_node_delta",
-                                                      "sb200_heur_result", "sb200_scp_model")]
+                                                      "sb200_heur_result", "sb200_scp_model", "sb200_row_model")]
     assert sizes == mine
 
 

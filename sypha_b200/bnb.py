@@ -53,7 +53,10 @@ def build_branch_model(base: ScpModel, decisions: Sequence[Tuple[int, int]]) -> 
 def greedy_cover(base: ScpModel) -> Tuple[float, Optional[np.ndarray]]:
     """The reference's first incumbent (greedy_set_cover_heuristic, sypha_preprocessor.cpp:11-96): columns sorted
     by (cost ascending, rows covered descending) - full ties here by column index, the reference leaves them to
-    std::sort - and scanned once; a column is taken when it covers a row that is still uncovered."""
+    std::sort (unstable, so implementation-defined) - and scanned once; a column is taken when it covers a row that is
+    still uncovered.  Against the reference's own function (tests/test_bnb_host.py, oracle/_ref/libref_prep.so): identical
+    where no two columns tie, the same objective on the bench's instances (scpnre1 38, scpnrg1 266); on instances with
+    many full ties (unit costs) the two covers differ.  The C++ node loop calls the reference's function itself."""
     m, n0 = base.m, base.n_orig
     mask = (base.inds < n0) & (base.vals > 0.0)
     rows = np.repeat(np.arange(m), np.diff(base.offs))[mask]

@@ -211,3 +211,60 @@ def test_node_decisions_are_marshalled_as_flat_arrays(monkeypatch):
     assert seen["batch"] == want
     assert S.window_begin(base, decs, S.SolverExecutionConfig(maxIterations=5), [W() for _ in decs]) is None
     assert seen["window"] == [(n, v, c) for n, v, c, _ in want]
+
+
+def test_greedy_first_incumbent_against_the_references_own_function():
+    """bnb.greedy_cover (the first incumbent of the B&B bench) against greedy_set_cover_heuristic itself
+    (src/sypha_preprocessor.cpp:11-96, compiled in place into oracle/_ref/libref_prep.so).  The reference orders the
+    columns by (cost, rows covered) with std::sort and leaves FULL ties to it (unstable, implementation-defined);
+    greedy_cover breaks them by column index.  So: identical selections where no two columns tie, the same objective on
+    the bench's instances (scpnre1 38, scpnrg1 266 - what `reduce_by_incumbent` then cuts by), feasible covers whose
+    cost is what they report everywhere."""
+    import ctypes as C
+    from pathlib import Path
+    import pytest
+    from sypha_b200.instances import load_npz
+    so = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "libref_prep.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/libref_prep.so not built (make -C oracle all)")
+    lib = C.CDLL(str(so))
+    PI, PD = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lib.ref_greedy_set_cover.argtypes = [C.c_int, C.c_int, PI, PI, PD, PD, PI, PI, PD]
+
+    def reference(m):
+        offs, inds = np.ascontiguousarray(m.offs, dtype=np.int32), np.ascontiguousarray(m.inds, dtype=np.int32)
+        vals, c = np.ascontiguousarray(m.vals, dtype=np.float64), np.ascontiguousarray(m.c, dtype=np.float64)
+        sel, ns, obj = np.zeros(m.n_orig, dtype=np.int32), C.c_int(), C.c_double()
+        feas = lib.ref_greedy_set_cover(m.m, m.n_orig, offs.ctypes.data_as(PI), inds.ctypes.data_as(PI), vals.ctypes.data_as(PD),
+                                        c.ctypes.data_as(PD), sel.ctypes.data_as(PI), C.byref(ns), C.byref(obj))
+        return bool(feas), obj.value, set(sel[:ns.value].tolist())
+
+    # no ties: real-valued costs -> the same columns in the same scan order
+    for seed in range(4):
+        mdl = gen_scp(40, 300, 0.06, seed)
+        rng = np.random.default_rng(seed)
+        mdl.c[:mdl.n_orig] = rng.uniform(1.0, 100.0, mdl.n_orig)
+        feas, obj, sel = reference(mdl)
+        o, x = bnb.greedy_cover(mdl)
+        assert feas and x is not None and sel == set(np.nonzero(x)[0].tolist())
+        assert abs(o - obj) <= 1e-12 * obj
+    # the instances the bench runs its B&B on: same first incumbent, hence the same reduced model
+    golden = Path(__file__).resolve().parent / "golden"
+    for name, want in (("scpnre1", 38.0), ("scpnrg1", 266.0)):
+        mdl = load_npz(golden / f"{name}.npz")
+        feas, obj, _ = reference(mdl)
+        o, x = bnb.greedy_cover(mdl)
+        assert feas and obj == want and o == want
+        red_a, _ = bnb.reduce_by_incumbent(mdl, o)
+        red_b, _ = bnb.reduce_by_incumbent(mdl, obj)
+        assert (red_a.n_orig, red_a.nnz) == (red_b.n_orig, red_b.nnz)
+    # integer costs with ties: both are covers whose cost is what they report
+    for name in ("scp41", "scpclr10", "scpnrh1"):
+        mdl = load_npz(golden / f"{name}.npz")
+        h = bnb.CoverHeuristic(mdl)
+        feas, obj, sel = reference(mdl)
+        o, x = bnb.greedy_cover(mdl)
+        xr = np.zeros(mdl.n_orig)
+        xr[sorted(sel)] = 1.0
+        assert feas and np.all(h.A @ xr >= 1.0) and abs(float(mdl.c[:mdl.n_orig] @ xr) - obj) < 1e-9
+        assert x is not None and np.all(h.A @ x >= 1.0) and abs(float(mdl.c[:mdl.n_orig] @ x) - o) < 1e-9

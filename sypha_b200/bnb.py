@@ -54,7 +54,7 @@ def greedy_cover(base: ScpModel) -> Tuple[float, Optional[np.ndarray]]:
     """The reference's first incumbent (greedy_set_cover_heuristic, sypha_preprocessor.cpp:11-96): columns sorted
     by (cost ascending, rows covered descending) - full ties here by column index, the reference leaves them to
     std::sort (unstable, so implementation-defined) - and scanned once; a column is taken when it covers a row that is
-    still uncovered.  Against the reference's own function (tests/test_bnb_host.py, oracle/_ref/libref_prep.so): identical
+    still uncovered.  Against the reference's own function (compiled in place for tests/test_bnb_host.py): identical
     where no two columns tie, the same objective on the bench's instances (scpnre1 38, scpnrg1 266); on instances with
     many full ties (unit costs) the two covers differ.  The C++ node loop calls the reference's function itself."""
     m, n0 = base.m, base.n_orig
